@@ -1,0 +1,209 @@
+"""ctypes/numpy binding of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline leg -- never by the product package hiprt_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+RAY_DTYPE = np.dtype(
+    [("origin", "<f4", 3), ("minT", "<f4"), ("direction", "<f4", 3), ("maxT", "<f4")], align=False
+)
+HIT_DTYPE = np.dtype(
+    [
+        ("instanceIDs", "<u4", 4),
+        ("primID", "<u4"),
+        ("_pad", "<u4"),
+        ("uv", "<f4", 2),
+        ("normal", "<f4", 3),
+        ("t", "<f4"),
+    ],
+    align=False,
+)
+BOX4_DTYPE = np.dtype(
+    [
+        ("child", "<u4", 4),
+        ("box", "<f4", (4, 2, 3)),
+        ("parentAddr", "<u4"),
+        ("updateCounter", "<u4"),
+        ("childCount", "<u4"),
+        ("_pad", "<u4"),
+    ]
+)
+TRIPAIR_DTYPE = np.dtype(
+    [
+        ("v", "<f4", (4, 3)),
+        ("_pad", "<u4"),
+        ("primIndex0", "<u4"),
+        ("primIndex1", "<u4"),
+        ("flags", "<u4"),
+    ]
+)
+SCRATCH_DTYPE = np.dtype([("box", "<f4", (2, 3)), ("child0", "<u4"), ("child1", "<u4")])
+assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 48
+assert BOX4_DTYPE.itemsize == 128 and TRIPAIR_DTYPE.itemsize == 64 and SCRATCH_DTYPE.itemsize == 32
+
+INVALID = 0xFFFFFFFF
+FLT_MAX = np.float32(3.402823466e38)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "hiprt_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+        L.orc_pair_triangles.argtypes = [vp, u32, u32, vp]
+        L.orc_pair_triangles.restype = u32
+        L.orc_morton.argtypes = [vp, vp]
+        L.orc_morton.restype = u32
+        L.orc_geometry_create.argtypes = [vp, u32, u32, vp, u32, u32, vp, u32, i32]
+        L.orc_geometry_create.restype = vp
+        L.orc_geometry_destroy.argtypes = [vp]
+        L.orc_geometry_rebuild_from_sorted.argtypes = [vp, vp, vp]
+        L.orc_geometry_count.argtypes = [vp, i32]
+        L.orc_geometry_count.restype = u32
+        L.orc_geometry_read.argtypes = [vp, i32, vp]
+        L.orc_lbvh_topology.argtypes = [vp, vp, u32, u32, vp]
+        L.orc_lbvh_topology.restype = u32
+        L.orc_geometry_trace.argtypes = [vp, vp, u32, vp, i32, vp]
+        L.orc_trace_nodes.argtypes = [vp, vp, vp, u32, vp, i32]
+        L.orc_geometry_trace_all.argtypes = [vp, vp, u32, vp, vp, vp, u32]
+        L.orc_geometry_trace_all.restype = u64
+        L.orc_canonicalize.argtypes = [vp, vp, u32, vp, vp, vp]
+        L.orc_canonicalize.restype = u32
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def make_rays(origins, directions, min_t=0.0, max_t=FLT_MAX):
+    origins = np.asarray(origins, np.float32).reshape(-1, 3)
+    directions = np.asarray(directions, np.float32).reshape(-1, 3)
+    r = np.zeros(len(origins), RAY_DTYPE)
+    r["origin"], r["direction"] = origins, directions
+    r["minT"], r["maxT"] = min_t, max_t
+    return r
+
+
+def pair_triangles(indices):
+    idx = np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+    out = np.zeros((len(idx), 2), np.uint32)
+    n = lib().orc_pair_triangles(_p(idx), len(idx), 12, _p(out))
+    return out[:n].copy()
+
+
+def morton(pos, ext):
+    pos = np.ascontiguousarray(pos, np.float32)
+    ext = np.ascontiguousarray(ext, np.float32)
+    return int(lib().orc_morton(_p(pos), _p(ext)))
+
+
+class Geometry:
+    """LBVH-built triangle geometry of the oracle."""
+
+    def __init__(self, vertices, indices=None, pairs=None, allow_pairing=True):
+        self.vertices = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        self.indices = None if indices is None else np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
+        self.pairs_in = None if pairs is None else np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        ntri = 0 if self.indices is None else len(self.indices)
+        self.h = lib().orc_geometry_create(
+            _p(self.vertices), len(self.vertices), 12, _p(self.indices), ntri, 12,
+            _p(self.pairs_in), 0 if self.pairs_in is None else len(self.pairs_in), int(allow_pairing))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_geometry_destroy(self.h)
+            self.h = None
+
+    def _count(self, what):
+        return int(lib().orc_geometry_count(self.h, what))
+
+    prim_count = property(lambda s: s._count(0))
+    box_count = property(lambda s: s._count(1))
+    leaf_count = property(lambda s: s._count(2))
+    root = property(lambda s: s._count(3))
+
+    def _read(self, what, dtype, n):
+        out = np.zeros(n, dtype)
+        lib().orc_geometry_read(self.h, what, _p(out))
+        return out
+
+    pairs = property(lambda s: s._read(0, np.uint32, 2 * s.prim_count).reshape(-1, 2))
+    prim_boxes = property(lambda s: s._read(1, np.float32, 6 * s.prim_count).reshape(-1, 2, 3))
+    keys = property(lambda s: s._read(2, np.uint32, s.prim_count))
+    sorted_keys = property(lambda s: s._read(3, np.uint32, s.prim_count))
+    sorted_vals = property(lambda s: s._read(4, np.uint32, s.prim_count))
+    scratch = property(lambda s: s._read(5, SCRATCH_DTYPE, max(s.prim_count - 1, 0)))
+    box_nodes = property(lambda s: s._read(6, BOX4_DTYPE, s.box_count))
+    leaves = property(lambda s: s._read(7, TRIPAIR_DTYPE, s.leaf_count))
+    scene_box = property(lambda s: s._read(8, np.float32, 6).reshape(2, 3))
+    prim_nodes = property(lambda s: s._read(9, TRIPAIR_DTYPE, s.prim_count))
+
+    def rebuild_from_sorted(self, sorted_keys, sorted_vals):
+        k = np.ascontiguousarray(sorted_keys, np.uint32)
+        v = np.ascontiguousarray(sorted_vals, np.uint32)
+        assert len(k) == len(v) == self.prim_count
+        lib().orc_geometry_rebuild_from_sorted(self.h, _p(k), _p(v))
+
+    def trace(self, rays, tie_mode=1, want_visits=False):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        visits = np.zeros(2, np.uint32)
+        lib().orc_geometry_trace(self.h, _p(rays), len(rays), _p(hits), tie_mode, _p(visits))
+        return (hits, visits) if want_visits else hits
+
+    def trace_all(self, rays, max_per_ray=16):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        n = len(rays)
+        counts = np.zeros(n, np.uint32)
+        prims = np.full((n, max_per_ray), INVALID, np.uint32)
+        ts = np.zeros((n, max_per_ray), np.float32)
+        lib().orc_geometry_trace_all(self.h, _p(rays), n, _p(counts), _p(prims), _p(ts), max_per_ray)
+        return counts, prims, ts
+
+
+def lbvh_topology(sorted_keys, sorted_boxes, leaf_type=0):
+    k = np.ascontiguousarray(sorted_keys, np.uint32)
+    b = np.ascontiguousarray(sorted_boxes, np.float32).reshape(-1, 2, 3)
+    out = np.zeros(max(len(k) - 1, 0), SCRATCH_DTYPE)
+    root = lib().orc_lbvh_topology(_p(k), _p(b), len(k), leaf_type, _p(out))
+    return out, int(root)
+
+
+def trace_nodes(box_nodes, tri_nodes, rays, tie_mode=1):
+    bn = np.ascontiguousarray(box_nodes)
+    tn = np.ascontiguousarray(tri_nodes)
+    rays = np.ascontiguousarray(rays, RAY_DTYPE)
+    hits = np.zeros(len(rays), HIT_DTYPE)
+    lib().orc_trace_nodes(_p(bn), _p(tn), _p(rays), len(rays), _p(hits), tie_mode)
+    return hits
+
+
+def canonicalize(box_nodes, leaves):
+    """Renumber a 4-wide structure breadth-first (see orc_canonicalize)."""
+    bn = np.ascontiguousarray(box_nodes, BOX4_DTYPE)
+    lv = np.ascontiguousarray(leaves)
+    out_b = np.zeros(len(bn), BOX4_DTYPE)
+    out_l = np.zeros(len(lv), lv.dtype)
+    nleaf = C.c_uint32(0)
+    nb = lib().orc_canonicalize(_p(bn), _p(lv), lv.dtype.itemsize, _p(out_b), _p(out_l), C.byref(nleaf))
+    return out_b[:nb], out_l[: nleaf.value]
