@@ -1,0 +1,838 @@
+// C-ABI shim: the 37 hiprt* entry points + the hiprtB200* additions.
+// Mirrors the behaviour of the reference's shim/context (hiprt/impl/hiprt.cpp:34-776,
+// hiprt/impl/Context.cpp): argument validation -> hiprtErrorInvalidParameter, API version gate,
+// internal failures are caught, logged through the context's log mask and returned as
+// hiprtErrorInternal; geometries/scenes created together share one device allocation that is
+// released when its last member is destroyed (Context.cpp:99-142).
+// Runtime: plain CUDA runtime API on the caller's device (no Orochi, no backend switch).
+#include <hiprt/hiprt_b200.h>
+
+#include "builders.h"
+#include "compiler.h"
+#include "trace.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace hiprt;
+
+namespace
+{
+void checkCuda( cudaError_t e, const char* what )
+{
+	if ( e != cudaSuccess ) throw std::runtime_error( std::string( what ) + ": " + cudaGetErrorString( e ) );
+}
+
+struct OutOfDeviceMemory : std::runtime_error
+{
+	using std::runtime_error::runtime_error;
+};
+
+class Context
+{
+  public:
+	explicit Context( const hiprtContextCreationInput& input )
+	{
+		if ( input.deviceType != hiprtDeviceNVIDIA ) throw std::runtime_error( "hiprt_b200 supports NVIDIA devices only" );
+		m_info.device = input.device;
+		m_userCtx	  = input.ctxt;
+		bind();
+		cudaDeviceProp prop{};
+		checkCuda( cudaGetDeviceProperties( &prop, m_info.device ), "cudaGetDeviceProperties" );
+		m_info.smCount	 = uint32_t( prop.multiProcessorCount );
+		m_maxThreadsPerSm = uint32_t( prop.maxThreadsPerMultiProcessor > 0 ? prop.maxThreadsPerMultiProcessor : 2048 );
+		m_ccMajor = prop.major, m_ccMinor = prop.minor;
+	}
+
+	// Make the context's device current on the calling thread (builds may come from many host
+	// threads, each with its own stream: reference test/hiprtTest.cpp:1226-1352).
+	void bind() const
+	{
+		checkCuda( cudaSetDevice( m_info.device ), "cudaSetDevice" );
+		if ( m_userCtx ) compiler::setCurrentContext( m_userCtx );
+	}
+
+	const DeviceInfo& info() const { return m_info; }
+	uint32_t		  maxThreadsPerSm() const { return m_maxThreadsPerSm; }
+	int				  ccMajor() const { return m_ccMajor; }
+	int				  ccMinor() const { return m_ccMinor; }
+
+	void log( hiprtLogLevel level, const char* fmt, ... )
+	{
+		va_list args;
+		va_start( args, fmt );
+		char buf[1024];
+		vsnprintf( buf, sizeof( buf ), fmt, args );
+		va_end( args );
+		if ( level == hiprtLogLevelError )
+		{
+			std::lock_guard<std::mutex> lock( m_mutex );
+			m_lastError = buf;
+		}
+		if ( m_logMask & level ) fprintf( level == hiprtLogLevelInfo ? stdout : stderr, "[hiprt_b200] %s\n", buf );
+	}
+	void		setLogLevel( hiprtLogLevel mask ) { m_logMask = mask; }
+	const char* lastError() const { return m_lastError.c_str(); }
+
+	// ---- pooled device allocations ------------------------------------------------------------
+	std::vector<void*> allocatePool( const std::vector<size_t>& sizes )
+	{
+		size_t total = 0;
+		for ( size_t s : sizes )
+			total += s;
+		void*		base = nullptr;
+		cudaError_t e	 = cudaMalloc( &base, std::max<size_t>( total, 64 ) );
+		if ( e == cudaErrorMemoryAllocation ) throw OutOfDeviceMemory( "cudaMalloc: out of device memory" );
+		checkCuda( e, "cudaMalloc" );
+		std::vector<void*> out( sizes.size() );
+		uint8_t*		   p = static_cast<uint8_t*>( base );
+		for ( size_t i = 0; i < sizes.size(); ++i )
+		{
+			out[i] = p;
+			p += sizes[i];
+		}
+		std::lock_guard<std::mutex> lock( m_mutex );
+		m_pools[base] = Pool{ total, uint32_t( sizes.size() ) };
+		return out;
+	}
+
+	void releaseFromPool( void* member )
+	{
+		std::lock_guard<std::mutex> lock( m_mutex );
+		auto						it = m_pools.upper_bound( member );
+		if ( it == m_pools.begin() )
+		{
+			log( hiprtLogLevelWarn, "destroying an object that was not allocated by this context" );
+			return;
+		}
+		--it;
+		uint8_t* base = static_cast<uint8_t*>( it->first );
+		if ( static_cast<uint8_t*>( member ) >= base + std::max<size_t>( it->second.size, 64 ) )
+		{
+			log( hiprtLogLevelWarn, "destroying an object that was not allocated by this context" );
+			return;
+		}
+		if ( --it->second.members == 0 )
+		{
+			checkCuda( cudaFree( it->first ), "cudaFree" );
+			m_pools.erase( it );
+		}
+	}
+
+	std::string cacheDir;
+
+  private:
+	struct Pool
+	{
+		size_t	 size;
+		uint32_t members;
+	};
+	DeviceInfo			  m_info;
+	void*				  m_userCtx			= nullptr;
+	uint32_t			  m_maxThreadsPerSm = 2048;
+	int					  m_ccMajor = 10, m_ccMinor = 0;
+	hiprtLogLevel		  m_logMask = hiprtLogLevelNone;
+	std::string			  m_lastError;
+	std::map<void*, Pool> m_pools;
+	std::mutex			  m_mutex;
+};
+
+inline Context* ctx( hiprtContext c ) { return reinterpret_cast<Context*>( c ); }
+
+// Runs `fn` with the reference's error convention.
+template <typename Fn>
+hiprtError guarded( hiprtContext context, Fn&& fn )
+{
+	try
+	{
+		ctx( context )->bind();
+		fn();
+	}
+	catch ( const OutOfDeviceMemory& e )
+	{
+		ctx( context )->log( hiprtLogLevelError, "%s", e.what() );
+		return hiprtErrorOutOfDeviceMemory;
+	}
+	catch ( const std::bad_alloc& )
+	{
+		return hiprtErrorOutOfHostMemory;
+	}
+	catch ( const compiler::NotAvailable& e )
+	{
+		ctx( context )->log( hiprtLogLevelError, "%s", e.what() );
+		return hiprtErrorNotImplemented;
+	}
+	catch ( const std::exception& e )
+	{
+		ctx( context )->log( hiprtLogLevelError, "%s", e.what() );
+		return hiprtErrorInternal;
+	}
+	return hiprtSuccess;
+}
+
+bool usesBatch( size_t primCount, hiprtBuildOptions o )
+{
+	// reference: hiprt/impl/BvhCommon.h:155-166
+	return primCount <= o.batchBuildMaxPrimCount && ( o.buildFlags & 7 ) != hiprtBuildFlagBitCustomBvhImport;
+}
+
+void checkBuildFlags( Context* c, hiprtBuildOptions o )
+{
+	if ( ( o.buildFlags & 3 ) == hiprtBuildFlagBitCustomBvhImport ) throw compiler::NotAvailable( "custom BVH import is not implemented in this build" );
+	if ( ( o.buildFlags & 3 ) == hiprtBuildFlagBitPreferHighQualityBuild )
+		c->log( hiprtLogLevelInfo, "PreferHighQualityBuild is served by the balanced (H-PLOC) builder" );
+}
+} // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------
+hiprtError hiprtCreateContext( uint32_t hiprtApiVersion, const hiprtContextCreationInput& input, hiprtContext& contextOut )
+{
+	if ( hiprtApiVersion != HIPRT_API_VERSION ) return hiprtErrorInvalidApiVersion;
+	try
+	{
+		contextOut = reinterpret_cast<hiprtContext>( new Context( input ) );
+	}
+	catch ( const std::exception& e )
+	{
+		fprintf( stderr, "[hiprt_b200] hiprtCreateContext failed: %s\n", e.what() );
+		contextOut = nullptr;
+		return hiprtErrorInternal;
+	}
+	return hiprtSuccess;
+}
+
+hiprtError hiprtDestroyContext( hiprtContext context )
+{
+	if ( !context ) return hiprtErrorInvalidParameter;
+	delete ctx( context );
+	return hiprtSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------
+hiprtError hiprtCreateGeometry(
+	hiprtContext context, const hiprtGeometryBuildInput& buildInput, const hiprtBuildOptions buildOptions, hiprtGeometry& geometryOut )
+{
+	hiprtGeometry* addr = &geometryOut;
+	return hiprtCreateGeometries( context, 1, &buildInput, buildOptions, &addr );
+}
+
+hiprtError hiprtCreateGeometries(
+	hiprtContext				   context,
+	uint32_t					   numGeometries,
+	const hiprtGeometryBuildInput* buildInputs,
+	const hiprtBuildOptions		   buildOptions,
+	hiprtGeometry**				   geometriesOut )
+{
+	if ( !context || numGeometries == 0 || buildInputs == nullptr || geometriesOut == nullptr ) return hiprtErrorInvalidParameter;
+	for ( uint32_t i = 0; i < numGeometries; ++i )
+		if ( geometriesOut[i] == nullptr ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		checkBuildFlags( ctx( context ), buildOptions );
+		std::vector<size_t> sizes( numGeometries );
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+			sizes[i] = geometryStorageSize( buildInputs[i] );
+		const std::vector<void*> ptrs = ctx( context )->allocatePool( sizes );
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+			*geometriesOut[i] = reinterpret_cast<hiprtGeometry>( ptrs[i] );
+	} );
+}
+
+hiprtError hiprtDestroyGeometry( hiprtContext context, hiprtGeometry geometry ) { return hiprtDestroyGeometries( context, 1, &geometry ); }
+
+hiprtError hiprtDestroyGeometries( hiprtContext context, uint32_t numGeometries, hiprtGeometry* geometries )
+{
+	if ( !context || numGeometries == 0 || geometries == nullptr ) return hiprtErrorInvalidParameter;
+	for ( uint32_t i = 0; i < numGeometries; ++i )
+		if ( !geometries[i] ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+			ctx( context )->releaseFromPool( geometries[i] );
+	} );
+}
+
+hiprtError hiprtBuildGeometry(
+	hiprtContext				   context,
+	hiprtBuildOperation			   buildOperation,
+	const hiprtGeometryBuildInput& buildInput,
+	const hiprtBuildOptions		   buildOptions,
+	hiprtDevicePtr				   temporaryBuffer,
+	hiprtApiStream				   stream,
+	hiprtGeometry				   geometryOut )
+{
+	return hiprtBuildGeometries( context, buildOperation, 1, &buildInput, buildOptions, temporaryBuffer, stream, &geometryOut );
+}
+
+hiprtError hiprtBuildGeometries(
+	hiprtContext				   context,
+	hiprtBuildOperation			   buildOperation,
+	uint32_t					   numGeometries,
+	const hiprtGeometryBuildInput* buildInputs,
+	const hiprtBuildOptions		   buildOptions,
+	hiprtDevicePtr				   temporaryBuffer,
+	hiprtApiStream				   stream,
+	hiprtGeometry*				   geometriesOut )
+{
+	if ( !context || numGeometries == 0 || buildInputs == nullptr || geometriesOut == nullptr ) return hiprtErrorInvalidParameter;
+	for ( uint32_t i = 0; i < numGeometries; ++i )
+		if ( geometriesOut[i] == nullptr ) return hiprtErrorInvalidParameter;
+	if ( buildOperation != hiprtBuildOperationBuild && buildOperation != hiprtBuildOperationUpdate ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		Context* c = ctx( context );
+		checkBuildFlags( c, buildOptions );
+		cudaStream_t s = static_cast<cudaStream_t>( stream );
+		if ( buildOperation == hiprtBuildOperationUpdate )
+		{
+			for ( uint32_t i = 0; i < numGeometries; ++i )
+				updateGeometry( c->info(), buildInputs[i], buildOptions, temporaryBuffer, s, geometriesOut[i] );
+			return;
+		}
+		// inputs small enough for the batch builder are built together first (Context.cpp:153-168)
+		std::vector<hiprtGeometryBuildInput> batchInputs;
+		std::vector<void*>					 batchOut;
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+			if ( usesBatch( geometryPrimCount( buildInputs[i] ), buildOptions ) )
+			{
+				batchInputs.push_back( buildInputs[i] );
+				batchOut.push_back( geometriesOut[i] );
+			}
+		if ( !batchInputs.empty() )
+			buildGeometriesBatch( c->info(), batchInputs.data(), uint32_t( batchInputs.size() ), buildOptions, temporaryBuffer, s, batchOut.data() );
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+			if ( !usesBatch( geometryPrimCount( buildInputs[i] ), buildOptions ) )
+				buildGeometry( c->info(), buildInputs[i], buildOptions, temporaryBuffer, s, geometriesOut[i] );
+	} );
+}
+
+hiprtError hiprtGetGeometryBuildTemporaryBufferSize(
+	hiprtContext context, const hiprtGeometryBuildInput& buildInput, const hiprtBuildOptions buildOptions, size_t& sizeOut )
+{
+	return hiprtGetGeometriesBuildTemporaryBufferSize( context, 1, &buildInput, buildOptions, sizeOut );
+}
+
+hiprtError hiprtGetGeometriesBuildTemporaryBufferSize(
+	hiprtContext				   context,
+	uint32_t					   numGeometries,
+	const hiprtGeometryBuildInput* buildInputs,
+	const hiprtBuildOptions		   buildOptions,
+	size_t&						   sizeOut )
+{
+	if ( !context || numGeometries == 0 || buildInputs == nullptr ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		// non-batch builds run one after another on the stream: max; the batch needs its own slice
+		size_t	 size	   = 0;
+		uint32_t batchSize = 0;
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+		{
+			if ( usesBatch( geometryPrimCount( buildInputs[i] ), buildOptions ) )
+				++batchSize;
+			else
+				size = std::max( size, geometryTempSize( buildInputs[i], buildOptions ) );
+		}
+		if ( batchSize ) size = std::max( size, batchTempSize( batchSize ) );
+		sizeOut = size;
+	} );
+}
+
+hiprtError hiprtCompactGeometry( hiprtContext context, hiprtApiStream stream, hiprtGeometry geometryIn, hiprtGeometry& geometryOut )
+{
+	hiprtGeometry* addr = &geometryOut;
+	return hiprtCompactGeometries( context, 1, stream, &geometryIn, &addr );
+}
+
+hiprtError hiprtCompactGeometries(
+	hiprtContext context, uint32_t numGeometries, hiprtApiStream stream, hiprtGeometry* geometriesIn, hiprtGeometry** geometriesOut )
+{
+	if ( !context || numGeometries == 0 || geometriesIn == nullptr || geometriesOut == nullptr ) return hiprtErrorInvalidParameter;
+	for ( uint32_t i = 0; i < numGeometries; ++i )
+		if ( geometriesIn[i] == nullptr || geometriesOut[i] == nullptr ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		// reference: Context::compactGeometries (Context.cpp:292-355): read the headers back, allocate
+		// exactly what is used, copy box and leaf arrays, rebase the header pointers, free the inputs.
+		Context*				c = ctx( context );
+		cudaStream_t			s = static_cast<cudaStream_t>( stream );
+		std::vector<GeomHeader> headers( numGeometries );
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+			checkCuda( cudaMemcpyAsync( &headers[i], geometriesIn[i], sizeof( GeomHeader ), cudaMemcpyDeviceToHost, s ), "cudaMemcpyAsync" );
+		checkCuda( cudaStreamSynchronize( s ), "cudaStreamSynchronize" );
+		std::vector<size_t> sizes( numGeometries ), boxBytes( numGeometries ), leafBytes( numGeometries );
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+		{
+			const size_t leafSize = ( headers[i].geomType & 1u ) ? sizeof( TrianglePairNode ) : sizeof( CustomNode );
+			boxBytes[i]			  = RoundUp( size_t( headers[i].boxNodeCount ) * sizeof( Box4Node ), size_t( 64 ) );
+			leafBytes[i]		  = RoundUp( size_t( headers[i].primNodeCount ) * leafSize, size_t( 64 ) );
+			sizes[i]			  = 64 + boxBytes[i] + leafBytes[i];
+		}
+		const std::vector<void*> out = c->allocatePool( sizes );
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+		{
+			uint8_t*   dst = static_cast<uint8_t*>( out[i] );
+			GeomHeader h   = headers[i];
+			checkCuda( cudaMemcpyAsync( dst + 64, headers[i].boxNodes, boxBytes[i], cudaMemcpyDeviceToDevice, s ), "copy box nodes" );
+			checkCuda( cudaMemcpyAsync( dst + 64 + boxBytes[i], headers[i].primNodes, leafBytes[i], cudaMemcpyDeviceToDevice, s ), "copy leaves" );
+			h.boxNodes	= reinterpret_cast<Box4Node*>( dst + 64 );
+			h.primNodes = dst + 64 + boxBytes[i];
+			h.size		= sizes[i];
+			checkCuda( cudaMemcpyAsync( dst, &h, sizeof( GeomHeader ), cudaMemcpyHostToDevice, s ), "write header" );
+			*geometriesOut[i] = reinterpret_cast<hiprtGeometry>( dst );
+		}
+		checkCuda( cudaStreamSynchronize( s ), "cudaStreamSynchronize" );
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+			c->releaseFromPool( geometriesIn[i] );
+	} );
+}
+
+// ------------------------------------------------------------------------------------------------
+hiprtError
+hiprtCreateScene( hiprtContext context, const hiprtSceneBuildInput& buildInput, const hiprtBuildOptions buildOptions, hiprtScene& sceneOut )
+{
+	hiprtScene* addr = &sceneOut;
+	return hiprtCreateScenes( context, 1, &buildInput, buildOptions, &addr );
+}
+
+hiprtError hiprtCreateScenes(
+	hiprtContext context, uint32_t numScenes, const hiprtSceneBuildInput* buildInputs, const hiprtBuildOptions buildOptions, hiprtScene** scenesOut )
+{
+	if ( !context || numScenes == 0 || buildInputs == nullptr || scenesOut == nullptr ) return hiprtErrorInvalidParameter;
+	for ( uint32_t i = 0; i < numScenes; ++i )
+		if ( scenesOut[i] == nullptr ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		checkBuildFlags( ctx( context ), buildOptions );
+		std::vector<size_t> sizes( numScenes );
+		for ( uint32_t i = 0; i < numScenes; ++i )
+		{
+			// instance ids are 24 bits wide (reference: Context.cpp:366-373)
+			if ( buildInputs[i].instanceCount >= ( 1u << InstanceIDBits ) ) throw std::runtime_error( "too many instances (24-bit instance ids)" );
+			sizes[i] = sceneStorageSize( buildInputs[i] );
+		}
+		const std::vector<void*> ptrs = ctx( context )->allocatePool( sizes );
+		for ( uint32_t i = 0; i < numScenes; ++i )
+			*scenesOut[i] = reinterpret_cast<hiprtScene>( ptrs[i] );
+	} );
+}
+
+hiprtError hiprtDestroyScene( hiprtContext context, hiprtScene scene ) { return hiprtDestroyScenes( context, 1, &scene ); }
+
+hiprtError hiprtDestroyScenes( hiprtContext context, uint32_t numScenes, hiprtScene* scenes )
+{
+	if ( !context || numScenes == 0 || scenes == nullptr ) return hiprtErrorInvalidParameter;
+	for ( uint32_t i = 0; i < numScenes; ++i )
+		if ( !scenes[i] ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		for ( uint32_t i = 0; i < numScenes; ++i )
+			ctx( context )->releaseFromPool( scenes[i] );
+	} );
+}
+
+hiprtError hiprtBuildScene(
+	hiprtContext				context,
+	hiprtBuildOperation			buildOperation,
+	const hiprtSceneBuildInput& buildInput,
+	const hiprtBuildOptions		buildOptions,
+	hiprtDevicePtr				temporaryBuffer,
+	hiprtApiStream				stream,
+	hiprtScene					sceneOut )
+{
+	return hiprtBuildScenes( context, buildOperation, 1, &buildInput, buildOptions, temporaryBuffer, stream, &sceneOut );
+}
+
+hiprtError hiprtBuildScenes(
+	hiprtContext				context,
+	hiprtBuildOperation			buildOperation,
+	uint32_t					numScenes,
+	const hiprtSceneBuildInput* buildInputs,
+	const hiprtBuildOptions		buildOptions,
+	hiprtDevicePtr				temporaryBuffer,
+	hiprtApiStream				stream,
+	hiprtScene*					scenesOut )
+{
+	if ( !context || numScenes == 0 || buildInputs == nullptr || scenesOut == nullptr ) return hiprtErrorInvalidParameter;
+	for ( uint32_t i = 0; i < numScenes; ++i )
+		if ( scenesOut[i] == nullptr ) return hiprtErrorInvalidParameter;
+	if ( buildOperation != hiprtBuildOperationBuild && buildOperation != hiprtBuildOperationUpdate ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		Context* c = ctx( context );
+		checkBuildFlags( c, buildOptions );
+		cudaStream_t s	  = static_cast<cudaStream_t>( stream );
+		uint8_t*	 temp = static_cast<uint8_t*>( temporaryBuffer );
+		for ( uint32_t i = 0; i < numScenes; ++i )
+		{
+			// several scenes get disjoint slices of the temporary buffer (sizes add up: Context.cpp:598-629)
+			if ( buildOperation == hiprtBuildOperationUpdate )
+				updateScene( c->info(), buildInputs[i], buildOptions, temp, s, scenesOut[i] );
+			else
+				buildScene( c->info(), buildInputs[i], buildOptions, temp, s, scenesOut[i] );
+			temp += sceneTempSize( buildInputs[i], buildOptions );
+		}
+	} );
+}
+
+hiprtError hiprtGetSceneBuildTemporaryBufferSize(
+	hiprtContext context, const hiprtSceneBuildInput& buildInput, const hiprtBuildOptions buildOptions, size_t& sizeOut )
+{
+	return hiprtGetScenesBuildTemporaryBufferSize( context, 1, &buildInput, buildOptions, sizeOut );
+}
+
+hiprtError hiprtGetScenesBuildTemporaryBufferSize(
+	hiprtContext context, uint32_t numScenes, const hiprtSceneBuildInput* buildInputs, const hiprtBuildOptions buildOptions, size_t& sizeOut )
+{
+	if ( !context || numScenes == 0 || buildInputs == nullptr ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		size_t size = 0;
+		for ( uint32_t i = 0; i < numScenes; ++i )
+			size += sceneTempSize( buildInputs[i], buildOptions );
+		sizeOut = size;
+	} );
+}
+
+hiprtError hiprtCompactScene( hiprtContext context, hiprtApiStream stream, hiprtScene sceneIn, hiprtScene& sceneOut )
+{
+	hiprtScene* addr = &sceneOut;
+	return hiprtCompactScenes( context, 1, stream, &sceneIn, &addr );
+}
+
+hiprtError hiprtCompactScenes( hiprtContext context, uint32_t numScenes, hiprtApiStream stream, hiprtScene* scenesIn, hiprtScene** scenesOut )
+{
+	if ( !context || numScenes == 0 || scenesIn == nullptr || scenesOut == nullptr ) return hiprtErrorInvalidParameter;
+	for ( uint32_t i = 0; i < numScenes; ++i )
+		if ( scenesIn[i] == nullptr || scenesOut[i] == nullptr ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		Context*				 c = ctx( context );
+		cudaStream_t			 s = static_cast<cudaStream_t>( stream );
+		std::vector<SceneHeader> headers( numScenes );
+		for ( uint32_t i = 0; i < numScenes; ++i )
+			checkCuda( cudaMemcpyAsync( &headers[i], scenesIn[i], sizeof( SceneHeader ), cudaMemcpyDeviceToHost, s ), "cudaMemcpyAsync" );
+		checkCuda( cudaStreamSynchronize( s ), "cudaStreamSynchronize" );
+		std::vector<size_t> sizes( numScenes );
+		auto				up = []( size_t v ) { return RoundUp( v, size_t( 64 ) ); };
+		for ( uint32_t i = 0; i < numScenes; ++i )
+			sizes[i] = 64 + up( size_t( headers[i].boxNodeCount ) * sizeof( Box4Node ) ) + up( size_t( headers[i].primNodeCount ) * sizeof( InstanceNode ) ) +
+					   up( size_t( headers[i].primCount ) * sizeof( InstanceRecord ) ) + up( size_t( headers[i].frameCount ) * sizeof( SRTFrame ) );
+		const std::vector<void*> out = c->allocatePool( sizes );
+		for ( uint32_t i = 0; i < numScenes; ++i )
+		{
+			uint8_t*	dst = static_cast<uint8_t*>( out[i] );
+			SceneHeader h	= headers[i];
+			size_t		off = 64;
+			auto		copy = [&]( const void* src, size_t bytes ) {
+				   uint8_t* p = dst + off;
+				   if ( bytes ) checkCuda( cudaMemcpyAsync( p, src, bytes, cudaMemcpyDeviceToDevice, s ), "compact copy" );
+				   off += up( bytes );
+				   return p;
+			};
+			h.boxNodes	= reinterpret_cast<Box4Node*>( copy( headers[i].boxNodes, size_t( h.boxNodeCount ) * sizeof( Box4Node ) ) );
+			h.primNodes = reinterpret_cast<InstanceNode*>( copy( headers[i].primNodes, size_t( h.primNodeCount ) * sizeof( InstanceNode ) ) );
+			h.instances = reinterpret_cast<InstanceRecord*>( copy( headers[i].instances, size_t( h.primCount ) * sizeof( InstanceRecord ) ) );
+			h.frames	= reinterpret_cast<SRTFrame*>( copy( headers[i].frames, size_t( h.frameCount ) * sizeof( SRTFrame ) ) );
+			h.size		= sizes[i];
+			checkCuda( cudaMemcpyAsync( dst, &h, sizeof( SceneHeader ), cudaMemcpyHostToDevice, s ), "write header" );
+			*scenesOut[i] = reinterpret_cast<hiprtScene>( dst );
+		}
+		checkCuda( cudaStreamSynchronize( s ), "cudaStreamSynchronize" );
+		for ( uint32_t i = 0; i < numScenes; ++i )
+			c->releaseFromPool( scenesIn[i] );
+	} );
+}
+
+// ------------------------------------------------------------------------------------------------
+hiprtError hiprtCreateFuncTable( hiprtContext context, uint32_t numGeomTypes, uint32_t numRayTypes, hiprtFuncTable& funcTableOut )
+{
+	if ( !context ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		// device layout: header followed by numGeomTypes*numRayTypes data sets (Context.cpp:714-733)
+		const size_t bytes = sizeof( hiprtFuncTableHeader ) + size_t( numGeomTypes ) * numRayTypes * sizeof( hiprtFuncDataSet );
+		uint8_t*	 p	   = nullptr;
+		checkCuda( cudaMalloc( reinterpret_cast<void**>( &p ), bytes ), "cudaMalloc" );
+		checkCuda( cudaMemset( p, 0, bytes ), "cudaMemset" );
+		hiprtFuncTableHeader h{ numGeomTypes, numRayTypes, reinterpret_cast<hiprtFuncDataSet*>( p + sizeof( hiprtFuncTableHeader ) ) };
+		checkCuda( cudaMemcpy( p, &h, sizeof( h ), cudaMemcpyHostToDevice ), "cudaMemcpy" );
+		funcTableOut = reinterpret_cast<hiprtFuncTable>( p );
+	} );
+}
+
+hiprtError hiprtSetFuncTable( hiprtContext context, hiprtFuncTable funcTable, uint32_t geomType, uint32_t rayType, hiprtFuncDataSet set )
+{
+	if ( !context || !funcTable ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		hiprtFuncTableHeader h;
+		checkCuda( cudaMemcpy( &h, funcTable, sizeof( h ), cudaMemcpyDeviceToHost ), "cudaMemcpy" );
+		if ( geomType >= h.numGeomTypes || rayType >= h.numRayTypes ) throw std::runtime_error( "hiprtSetFuncTable: index out of range" );
+		checkCuda( cudaMemcpy( &h.funcDataSets[h.numGeomTypes * rayType + geomType], &set, sizeof( set ), cudaMemcpyHostToDevice ), "cudaMemcpy" );
+	} );
+}
+
+hiprtError hiprtDestroyFuncTable( hiprtContext context, hiprtFuncTable funcTable )
+{
+	if ( !context || !funcTable ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] { checkCuda( cudaFree( funcTable ), "cudaFree" ); } );
+}
+
+// ------------------------------------------------------------------------------------------------
+hiprtError hiprtCreateGlobalStackBuffer( hiprtContext context, const hiprtGlobalStackBufferInput& input, hiprtGlobalStackBuffer& stackBufferOut )
+{
+	if ( !context ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		// sizes as in the reference (Context.cpp:752-779); layout documented in hiprt_device.h
+		Context*	 c		   = ctx( context );
+		const size_t entrySize = input.entryType == hiprtStackEntryTypeInstance ? sizeof( hiprtInstanceStackEntry ) : sizeof( uint32_t );
+		hiprtGlobalStackBuffer b{ input.stackSize, 0, nullptr };
+		size_t				   bytes = 0, zeroBytes = 0;
+		if ( input.type == hiprtStackTypeDynamic )
+		{
+			b.stackCount = c->info().smCount * c->maxThreadsPerSm();
+			zeroBytes	 = size_t( b.stackCount / 32 ) * sizeof( uint32_t ); // lock table
+			bytes		 = zeroBytes + size_t( b.stackCount ) * input.stackSize * entrySize;
+		}
+		else
+		{
+			b.stackCount = input.threadCount;
+			bytes		 = size_t( input.stackSize ) * input.threadCount * entrySize;
+		}
+		cudaError_t e = cudaMalloc( &b.stackData, std::max<size_t>( bytes, 64 ) );
+		if ( e == cudaErrorMemoryAllocation ) throw OutOfDeviceMemory( "cudaMalloc: out of device memory" );
+		checkCuda( e, "cudaMalloc" );
+		if ( zeroBytes ) checkCuda( cudaMemset( b.stackData, 0, zeroBytes ), "cudaMemset" );
+		stackBufferOut = b;
+	} );
+}
+
+hiprtError hiprtDestroyGlobalStackBuffer( hiprtContext context, hiprtGlobalStackBuffer stackBuffer )
+{
+	if ( !context ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] { checkCuda( cudaFree( stackBuffer.stackData ), "cudaFree" ); } );
+}
+
+// ------------------------------------------------------------------------------------------------
+// Serialisation: the storage buffer with the header's pointers rebased to offsets
+// (reference: Context.cpp:787-853).
+hiprtError hiprtSaveGeometry( hiprtContext context, hiprtGeometry geometry, const char* filename )
+{
+	if ( !context || !geometry || !filename ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		GeomHeader h;
+		checkCuda( cudaMemcpy( &h, geometry, sizeof( h ), cudaMemcpyDeviceToHost ), "cudaMemcpy" );
+		std::vector<uint8_t> buf( h.size );
+		checkCuda( cudaMemcpy( buf.data(), geometry, h.size, cudaMemcpyDeviceToHost ), "cudaMemcpy" );
+		const uintptr_t base = reinterpret_cast<uintptr_t>( geometry );
+		h.boxNodes			 = reinterpret_cast<Box4Node*>( reinterpret_cast<uintptr_t>( h.boxNodes ) - base );
+		h.primNodes			 = reinterpret_cast<void*>( reinterpret_cast<uintptr_t>( h.primNodes ) - base );
+		memcpy( buf.data(), &h, sizeof( h ) );
+		std::ofstream f( filename, std::ios::binary );
+		if ( !f ) throw std::runtime_error( std::string( "cannot open " ) + filename );
+		f.write( reinterpret_cast<const char*>( buf.data() ), std::streamsize( buf.size() ) );
+	} );
+}
+
+hiprtError hiprtLoadGeometry( hiprtContext context, hiprtGeometry& geometryOut, const char* filename )
+{
+	if ( !context || !filename ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		std::ifstream f( filename, std::ios::binary );
+		if ( !f ) throw std::runtime_error( std::string( "cannot open " ) + filename );
+		GeomHeader h;
+		f.read( reinterpret_cast<char*>( &h ), sizeof( h ) );
+		if ( !f || h.rtip != 0 ) throw std::runtime_error( "not a geometry saved by an RTIP-0 (software traversal) build" );
+		std::vector<uint8_t> buf( h.size );
+		f.seekg( 0 );
+		f.read( reinterpret_cast<char*>( buf.data() ), std::streamsize( buf.size() ) );
+		if ( !f ) throw std::runtime_error( "truncated geometry file" );
+		const std::vector<void*> out = ctx( context )->allocatePool( { size_t( h.size ) } );
+		const uintptr_t			 base = reinterpret_cast<uintptr_t>( out[0] );
+		h.boxNodes					  = reinterpret_cast<Box4Node*>( reinterpret_cast<uintptr_t>( h.boxNodes ) + base );
+		h.primNodes					  = reinterpret_cast<void*>( reinterpret_cast<uintptr_t>( h.primNodes ) + base );
+		memcpy( buf.data(), &h, sizeof( h ) );
+		checkCuda( cudaMemcpy( out[0], buf.data(), buf.size(), cudaMemcpyHostToDevice ), "cudaMemcpy" );
+		geometryOut = reinterpret_cast<hiprtGeometry>( out[0] );
+	} );
+}
+
+hiprtError hiprtSaveScene( hiprtContext context, hiprtScene, const char* ) { return context ? hiprtErrorNotImplemented : hiprtErrorInvalidParameter; }
+hiprtError hiprtLoadScene( hiprtContext context, hiprtScene&, const char* ) { return context ? hiprtErrorNotImplemented : hiprtErrorInvalidParameter; }
+
+// ------------------------------------------------------------------------------------------------
+static void exportRootBox( const Box4Node* deviceRoot, hiprtFloat3& lo, hiprtFloat3& hi )
+{
+	Box4Node root;
+	checkCuda( cudaMemcpy( &root, deviceRoot, sizeof( root ), cudaMemcpyDeviceToHost ), "cudaMemcpy" );
+	lo = { FltMax, FltMax, FltMax };
+	hi = { -FltMax, -FltMax, -FltMax };
+	for ( int s = 0; s < 4; ++s )
+	{
+		if ( root.child[s] == InvalidValue ) continue;
+		lo = { std::min( lo.x, root.box[s].lo.x ), std::min( lo.y, root.box[s].lo.y ), std::min( lo.z, root.box[s].lo.z ) };
+		hi = { std::max( hi.x, root.box[s].hi.x ), std::max( hi.y, root.box[s].hi.y ), std::max( hi.z, root.box[s].hi.z ) };
+	}
+}
+
+hiprtError hiprtExportGeometryAabb( hiprtContext context, hiprtGeometry geometry, hiprtFloat3& aabbMinOut, hiprtFloat3& aabbMaxOut )
+{
+	if ( !context || !geometry ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		GeomHeader h;
+		checkCuda( cudaMemcpy( &h, geometry, sizeof( h ), cudaMemcpyDeviceToHost ), "cudaMemcpy" );
+		exportRootBox( h.boxNodes, aabbMinOut, aabbMaxOut );
+	} );
+}
+
+hiprtError hiprtExportSceneAabb( hiprtContext context, hiprtScene scene, hiprtFloat3& aabbMinOut, hiprtFloat3& aabbMaxOut )
+{
+	if ( !context || !scene ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		SceneHeader h;
+		checkCuda( cudaMemcpy( &h, scene, sizeof( h ), cudaMemcpyDeviceToHost ), "cudaMemcpy" );
+		exportRootBox( h.boxNodes, aabbMinOut, aabbMaxOut );
+	} );
+}
+
+// ------------------------------------------------------------------------------------------------
+hiprtError hiprtBuildTraceKernels(
+	hiprtContext	  context,
+	uint32_t		  numFunctions,
+	const char**	  funcNames,
+	const char*		  src,
+	const char*		  moduleName,
+	uint32_t		  numHeaders,
+	const char**	  headers,
+	const char**	  includeNames,
+	uint32_t		  numOptions,
+	const char**	  options,
+	uint32_t		  numGeomTypes,
+	uint32_t		  numRayTypes,
+	hiprtFuncNameSet* funcNameSets,
+	hiprtApiFunction* functionsOut,
+	hiprtApiModule*	  moduleOut,
+	bool			  cache )
+{
+	if ( !context || numFunctions == 0 || funcNames == nullptr || src == nullptr || functionsOut == nullptr ) return hiprtErrorInvalidParameter;
+	(void)cache; // compiled modules are cached in memory by source hash
+	return guarded( context, [&] {
+		Context* c = ctx( context );
+		compiler::buildTraceKernels(
+			c->ccMajor(), c->ccMinor(), numFunctions, funcNames, src, moduleName ? moduleName : "hiprt_user_module", numHeaders, headers,
+			includeNames, numOptions, options, numGeomTypes, numRayTypes, funcNameSets, functionsOut, moduleOut );
+	} );
+}
+
+hiprtError hiprtBuildTraceKernelsFromBitcode(
+	hiprtContext context, uint32_t, const char**, const char*, const char*, size_t, uint32_t, uint32_t, hiprtFuncNameSet*, hiprtApiFunction*, bool )
+{
+	// AMD bitcode linking has no CUDA counterpart here; user kernels go through hiprtBuildTraceKernels.
+	return context ? hiprtErrorNotImplemented : hiprtErrorInvalidParameter;
+}
+
+hiprtError hiprtSetCacheDirPath( hiprtContext context, const char* path )
+{
+	if ( !context || !path ) return hiprtErrorInvalidParameter;
+	ctx( context )->cacheDir = path;
+	return hiprtSuccess;
+}
+
+hiprtError hiprtSetLogLevel( hiprtContext context, hiprtLogLevel level )
+{
+	if ( !context ) return hiprtErrorInvalidParameter;
+	ctx( context )->setLogLevel( level );
+	return hiprtSuccess;
+}
+
+// ================================================================================================
+// hiprt_b200 additions
+hiprtError hiprtB200TraceGeometry(
+	hiprtContext context, hiprtGeometry geometry, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtApiStream stream )
+{
+	if ( !context || !geometry || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		traceGeometry( geometry, rays, numRays, hits, type, static_cast<cudaStream_t>( stream ) );
+		checkCuda( cudaGetLastError(), "trace launch" );
+	} );
+}
+
+hiprtError hiprtB200TraceScene(
+	hiprtContext	   context,
+	hiprtScene		   scene,
+	const hiprtRay*	   rays,
+	uint32_t		   numRays,
+	hiprtHit*		   hits,
+	hiprtTraversalType type,
+	hiprtRayMask	   mask,
+	hiprtApiStream	   stream )
+{
+	if ( !context || !scene || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		traceScene( scene, rays, numRays, hits, type, mask, static_cast<cudaStream_t>( stream ) );
+		checkCuda( cudaGetLastError(), "trace launch" );
+	} );
+}
+
+static void traceHost(
+	hiprtGeometry geometry, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t s )
+{
+	hiprtRay* dRays = nullptr;
+	hiprtHit* dHits = nullptr;
+	checkCuda( cudaMallocAsync( reinterpret_cast<void**>( &dRays ), size_t( numRays ) * sizeof( hiprtRay ), s ), "cudaMallocAsync" );
+	checkCuda( cudaMallocAsync( reinterpret_cast<void**>( &dHits ), size_t( numRays ) * sizeof( hiprtHit ), s ), "cudaMallocAsync" );
+	checkCuda( cudaMemcpyAsync( dRays, hostRays, size_t( numRays ) * sizeof( hiprtRay ), cudaMemcpyHostToDevice, s ), "H2D rays" );
+	if ( geometry )
+		traceGeometry( geometry, dRays, numRays, dHits, type, s );
+	else
+		traceScene( scene, dRays, numRays, dHits, type, mask, s );
+	checkCuda( cudaGetLastError(), "trace launch" );
+	checkCuda( cudaMemcpyAsync( hostHits, dHits, size_t( numRays ) * sizeof( hiprtHit ), cudaMemcpyDeviceToHost, s ), "D2H hits" );
+	checkCuda( cudaFreeAsync( dRays, s ), "cudaFreeAsync" );
+	checkCuda( cudaFreeAsync( dHits, s ), "cudaFreeAsync" );
+	checkCuda( cudaStreamSynchronize( s ), "cudaStreamSynchronize" );
+}
+
+hiprtError hiprtB200TraceGeometryHost(
+	hiprtContext context, hiprtGeometry geometry, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtApiStream stream )
+{
+	if ( !context || !geometry || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] { traceHost( geometry, nullptr, hostRays, numRays, hostHits, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ) ); } );
+}
+
+hiprtError hiprtB200TraceSceneHost(
+	hiprtContext	   context,
+	hiprtScene		   scene,
+	const hiprtRay*	   hostRays,
+	uint32_t		   numRays,
+	hiprtHit*		   hostHits,
+	hiprtTraversalType type,
+	hiprtRayMask	   mask,
+	hiprtApiStream	   stream )
+{
+	if ( !context || !scene || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] { traceHost( nullptr, scene, hostRays, numRays, hostHits, type, mask, static_cast<cudaStream_t>( stream ) ); } );
+}
+
+hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount, size_t* offsetsOut, uint32_t numOffsets )
+{
+	if ( !offsetsOut || numOffsets < 14 ) return hiprtErrorInvalidParameter;
+	const TempLayout L = tempLayout( primCount, pairedTriangleCount );
+	const size_t	 v[14] = { L.control, L.pairs,	  L.pairScan,	L.primRefs,	  L.keys[0], L.vals[0], L.keys[1],
+							   L.vals[1], L.sortScratch, L.sortedRefs, L.scratch, L.flags,	 L.taskQueue, L.total };
+	memcpy( offsetsOut, v, sizeof( v ) );
+	return hiprtSuccess;
+}
+
+uint32_t hiprtB200GetDeviceHeaders( const char*** namesOut, const char*** sourcesOut ) { return compiler::deviceHeaders( namesOut, sourcesOut ); }
+
+const char* hiprtB200GetLastErrorString( hiprtContext context ) { return context ? ctx( context )->lastError() : ""; }
+
+hiprtError hiprtB200CopyToHost( hiprtContext context, void* hostDst, const void* deviceSrc, size_t bytes )
+{
+	if ( !context || !hostDst || !deviceSrc ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		checkCuda( cudaDeviceSynchronize(), "cudaDeviceSynchronize" );
+		checkCuda( cudaMemcpy( hostDst, deviceSrc, bytes, cudaMemcpyDeviceToHost ), "cudaMemcpy" );
+	} );
+}
+
+} // extern "C"

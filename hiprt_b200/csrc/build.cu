@@ -1,0 +1,205 @@
+// Host orchestration of the builders: temporary-buffer layout, launch sequences.
+// (kernels: build_kernels.cuh; reference host side: hiprt/impl/LbvhBuilder.{h,cpp},
+// PlocBuilder.{h,cpp}, BatchBuilder.{h,cpp}, Context.cpp:144-290.)
+#include "build_kernels.cuh"
+
+namespace hiprt
+{
+TempLayout tempLayout( size_t n, size_t pairTriangles )
+{
+	TempLayout L{};
+	size_t	   off = 0;
+	auto	   take = [&]( size_t bytes ) {
+		  const size_t o = off;
+		  off += alignUp( bytes );
+		  return o;
+	};
+	L.control	  = take( sizeof( BuildControl ) );
+	L.pairs		  = take( pairTriangles * sizeof( uint2 ) );
+	L.pairScan	  = take( DivideRoundUp( pairTriangles, size_t( PairBlock ) ) * sizeof( uint32_t ) );
+	L.primRefs	  = take( n * 32 );
+	L.keys[0]	  = take( n * 4 );
+	L.vals[0]	  = take( n * 4 );
+	L.keys[1]	  = take( n * 4 );
+	L.vals[1]	  = take( n * 4 );
+	L.sortScratch = take( rsort::scratchWords( uint32_t( n ) ) * 4 );
+	L.sortedRefs  = take( n * 32 );
+	L.scratch	  = take( n * 32 );
+	L.flags		  = take( n * 4 );
+	L.taskQueue	  = L.keys[1]; // 8 B x maxBox(n) <= 8 B x n: reuses the second key/value buffer
+	L.total		  = off;
+	return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t geometryPrimCount( const hiprtGeometryBuildInput& input )
+{
+	if ( input.type == hiprtPrimitiveTypeTriangleMesh )
+	{
+		const auto& m = input.primitive.triangleMesh;
+		if ( m.trianglePairCount > 0 ) return m.trianglePairCount;
+		if ( m.triangleCount == 0 || m.triangleIndices == nullptr ) return m.vertexCount / 3;
+		return m.triangleCount;
+	}
+	if ( input.type == hiprtPrimitiveTypeAABBList ) return input.primitive.aabbList.aabbCount;
+	throw std::runtime_error( "unsupported primitive type" );
+}
+
+static bool wantsPairing( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
+{
+	if ( input.type != hiprtPrimitiveTypeTriangleMesh ) return false;
+	const auto& m = input.primitive.triangleMesh;
+	// reference: TriangleMesh::pairable() (TriangleMesh.h:246) and LbvhBuilder.h:186-189
+	return m.triangleIndices != nullptr && m.triangleCount > 2 && m.trianglePairCount == 0 &&
+		   !( options.buildFlags & hiprtBuildFlagBitDisableTrianglePairing );
+}
+
+size_t geometryStorageSize( const hiprtGeometryBuildInput& input )
+{
+	const size_t n		  = geometryPrimCount( input );
+	const size_t leafSize = input.type == hiprtPrimitiveTypeTriangleMesh ? sizeof( TrianglePairNode ) : sizeof( CustomNode );
+	return alignUp( sizeof( GeomHeader ) ) + alignUp( maxBoxNodeCount( n ) * sizeof( Box4Node ) ) + alignUp( n * leafSize );
+}
+
+size_t geometryTempSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
+{
+	const size_t n = geometryPrimCount( input );
+	return tempLayout( n, wantsPairing( input, options ) ? n : 0 ).total;
+}
+
+// Sort + emit + collapse for primitives whose 32-byte box records are already in temp.
+template <typename Source>
+static void runLbvh(
+	const DeviceInfo& dev,
+	Source			  src,
+	uint32_t		  nMax,
+	uint8_t*		  temp,
+	const TempLayout& L,
+	cudaStream_t	  stream,
+	uint32_t*		  boxNodeCounter,
+	uint32_t*		  primNodeCounter,
+	Box4Node*		  boxNodes,
+	void*			  leafNodes )
+{
+	BuildControl* ctl		 = reinterpret_cast<BuildControl*>( temp + L.control );
+	void*		  primRefs	 = temp + L.primRefs;
+	uint32_t*	  keys[2]	 = { reinterpret_cast<uint32_t*>( temp + L.keys[0] ), reinterpret_cast<uint32_t*>( temp + L.keys[1] ) };
+	uint32_t*	  vals[2]	 = { reinterpret_cast<uint32_t*>( temp + L.vals[0] ), reinterpret_cast<uint32_t*>( temp + L.vals[1] ) };
+	uint32_t*	  sortScr	 = reinterpret_cast<uint32_t*>( temp + L.sortScratch );
+	void*		  sortedRefs = temp + L.sortedRefs;
+	void*		  scratch	 = temp + L.scratch;
+	uint32_t*	  flags		 = reinterpret_cast<uint32_t*>( temp + L.flags );
+	uint64_t*	  taskQueue	 = reinterpret_cast<uint64_t*>( temp + L.taskQueue );
+	const uint32_t maxBox	 = uint32_t( maxBoxNodeCount( nMax ) );
+
+	const uint32_t streamGrid = std::min<uint32_t>( DivideRoundUp( nMax, 256u ), dev.smCount * 8 );
+	HIPRT_CUDA_CHECK( cudaMemsetAsync( sortScr, 0, rsort::scratchWords( nMax ) * 4, stream ) );
+	mortonKernel<<<streamGrid, 256, 0, stream>>>( ctl, primRefs, keys[0], vals[0], sortScr );
+
+	const uint32_t tiles = rsort::tileCount( nMax );
+	for ( int pass = 0; pass < rsort::Passes; ++pass )
+	{
+		const int in = pass & 1, out = in ^ 1;
+		rsort::onesweepPass<<<tiles, rsort::Block, sizeof( rsort::Smem ), stream>>>(
+			keys[in], vals[in], keys[out], vals[out], &ctl->primCount, nMax, sortScr, pass );
+	}
+	static_assert( rsort::Passes % 2 == 0, "sorted pairs must end up in buffer 0" );
+
+	// keys[1]/vals[1] are dead now: they become the collapse task queue
+	HIPRT_CUDA_CHECK( cudaMemsetAsync( taskQueue, 0xFF, size_t( maxBox ) * 8, stream ) );
+	HIPRT_CUDA_CHECK( cudaMemsetAsync( flags, 0xFF, size_t( nMax ) * 4, stream ) );
+	emitTopologyKernel<Source::LeafType><<<DivideRoundUp( nMax, 256u ), 256, 0, stream>>>(
+		ctl, keys[0], vals[0], primRefs, sortedRefs, scratch, flags, taskQueue );
+
+	const uint32_t warpsNeeded = DivideRoundUp( maxBox, 8u );
+	const uint32_t blocks	   = std::max( 1u, std::min( DivideRoundUp( warpsNeeded, CollapseBlock / 32 ), dev.smCount * 16 ) );
+	collapsePackKernel<Source><<<blocks, CollapseBlock, 0, stream>>>(
+		src, ctl, boxNodeCounter, primNodeCounter, scratch, sortedRefs, taskQueue, maxBox, boxNodes, leafNodes );
+	HIPRT_CUDA_CHECK( cudaGetLastError() );
+}
+
+void buildGeometry(
+	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* tempBuffer, cudaStream_t stream, void* storage )
+{
+	const uint32_t nMax = uint32_t( geometryPrimCount( input ) );
+	if ( nMax == 0 ) throw std::runtime_error( "empty geometry" );
+	const bool		 pairing = wantsPairing( input, options );
+	const TempLayout L		 = tempLayout( nMax, pairing ? nMax : 0 );
+	uint8_t*		 temp	 = static_cast<uint8_t*>( tempBuffer );
+	uint8_t*		 out	 = static_cast<uint8_t*>( storage );
+
+	GeomHeader* header	  = reinterpret_cast<GeomHeader*>( out );
+	Box4Node*	boxNodes  = reinterpret_cast<Box4Node*>( out + alignUp( sizeof( GeomHeader ) ) );
+	void*		leafNodes = out + alignUp( sizeof( GeomHeader ) ) + alignUp( maxBoxNodeCount( nMax ) * sizeof( Box4Node ) );
+	BuildControl* ctl	  = reinterpret_cast<BuildControl*>( temp + L.control );
+
+	const bool	   isMesh	= input.type == hiprtPrimitiveTypeTriangleMesh;
+	const uint32_t geomType = ( input.geomType << 1 ) | ( isMesh ? 1u : 0u );
+	initGeometryKernel<<<1, 1, 0, stream>>>( ctl, header, boxNodes, leafNodes, geometryStorageSize( input ), nMax, geomType );
+
+	const uint32_t streamGrid = std::min<uint32_t>( DivideRoundUp( nMax, 256u ), dev.smCount * 8 );
+	if ( isMesh )
+	{
+		const auto&		   m = input.primitive.triangleMesh;
+		TriangleMeshSource src{};
+		src.vertices	   = static_cast<const uint8_t*>( m.vertices );
+		src.vertexStride   = m.vertexStride;
+		src.triangles	   = ( m.triangleCount == 0 ) ? nullptr : static_cast<const uint8_t*>( m.triangleIndices );
+		src.triangleStride = m.triangleStride;
+		src.pairs		   = m.trianglePairCount > 0 ? static_cast<const uint2*>( m.trianglePairIndices ) : nullptr;
+		if ( nMax == 1 )
+		{
+			singletonKernel<TriangleMeshSource><<<1, 1, 0, stream>>>( src, &header->primNodeCount, boxNodes, leafNodes );
+			HIPRT_CUDA_CHECK( cudaGetLastError() );
+			return;
+		}
+		if ( pairing )
+		{
+			uint2*	  pairs = reinterpret_cast<uint2*>( temp + L.pairs );
+			uint32_t* scan	= reinterpret_cast<uint32_t*>( temp + L.pairScan );
+			const uint32_t tiles = DivideRoundUp( nMax, PairBlock );
+			HIPRT_CUDA_CHECK( cudaMemsetAsync( scan, 0, size_t( tiles ) * 4, stream ) );
+			pairTrianglesKernel<<<tiles, PairBlock, 0, stream>>>( src, nMax, pairs, scan, ctl );
+			src.pairs = pairs;
+		}
+		primBoxesKernel<TriangleMeshSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
+		runLbvh( dev, src, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
+	}
+	else
+	{
+		const auto&	   a = input.primitive.aabbList;
+		AabbListSource src{ static_cast<const uint8_t*>( a.aabbs ), a.aabbStride };
+		if ( nMax == 1 )
+		{
+			singletonKernel<AabbListSource><<<1, 1, 0, stream>>>( src, &header->primNodeCount, boxNodes, leafNodes );
+			HIPRT_CUDA_CHECK( cudaGetLastError() );
+			return;
+		}
+		primBoxesKernel<AabbListSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
+		runLbvh( dev, src, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// not yet implemented in this revision
+size_t sceneStorageSize( const hiprtSceneBuildInput& ) { throw std::runtime_error( "scene build: not implemented yet" ); }
+size_t sceneTempSize( const hiprtSceneBuildInput&, hiprtBuildOptions ) { throw std::runtime_error( "scene build: not implemented yet" ); }
+void   buildScene( const DeviceInfo&, const hiprtSceneBuildInput&, hiprtBuildOptions, void*, cudaStream_t, void* )
+{
+	throw std::runtime_error( "scene build: not implemented yet" );
+}
+void updateGeometry( const DeviceInfo&, const hiprtGeometryBuildInput&, hiprtBuildOptions, void*, cudaStream_t, void* )
+{
+	throw std::runtime_error( "geometry update: not implemented yet" );
+}
+void updateScene( const DeviceInfo&, const hiprtSceneBuildInput&, hiprtBuildOptions, void*, cudaStream_t, void* )
+{
+	throw std::runtime_error( "scene update: not implemented yet" );
+}
+size_t batchTempSize( uint32_t ) { return 64; }
+void   buildGeometriesBatch(
+	  const DeviceInfo&, const hiprtGeometryBuildInput*, uint32_t, hiprtBuildOptions, void*, cudaStream_t, void* const* )
+{
+	throw std::runtime_error( "batch build: not implemented yet" );
+}
+} // namespace hiprt

@@ -1,0 +1,455 @@
+// LBVH fast builder + collapse to 4-wide nodes + leaf packing, hand-written for sm_100a.
+//
+// Reference path this replaces: hiprt/impl/LbvhBuilder.h:133-430 with
+// the kernels PairTriangles / ComputeCentroidBox / ComputeMortonCodes (BvhBuilderKernels.h:
+// 373-548), Orochi onesweep sort, EmitTopologyAndFitBounds (LbvhBuilderKernels.h:67-134),
+// Collapse / CompactTasks / PackLeaves (BvhBuilderKernels.h:1088-1479).
+//
+// B200 design: the whole build is 10 launches on the caller's stream and never
+// synchronises with the host (the reference blocks 4-5 times to read counters back):
+//   init -> pair (single pass, decoupled look-back scan => deterministic pair order)
+//        -> prim boxes + scene box (vertices gathered once, 32-byte box records kept)
+//        -> Morton codes fused with the digit histograms of all sort passes
+//        -> 4 x onesweep pass
+//        -> emit topology + refit (bottom-up, one flag exchange per internal node)
+//        -> collapse + pack (persistent in-order work queue; box nodes are written as whole
+//           128-byte lines, leaves are packed by the task that creates their parent, so the
+//           reference's CompactTasks and PackLeaves passes disappear).
+// The primitive count after pairing lives in device memory (BuildControl::primCount); grids
+// are sized from the host-side upper bound and kernels trim themselves.
+#pragma once
+#include "builders.h"
+#include "prim_sources.cuh"
+#include "radix_sort.cuh"
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+
+namespace hiprt
+{
+#define HIPRT_CUDA_CHECK( expr )                                                                                  \
+	do                                                                                                            \
+	{                                                                                                             \
+		cudaError_t e_ = ( expr );                                                                                \
+		if ( e_ != cudaSuccess )                                                                                  \
+			throw std::runtime_error( std::string( "CUDA error: " ) + cudaGetErrorString( e_ ) + " at " #expr ); \
+	} while ( 0 )
+
+static inline size_t alignUp( size_t v ) { return RoundUp( v, size_t( DefaultAlignment ) ); }
+
+constexpr uint32_t PairBlock = 256; // triangles per pairing tile
+
+// ------------------------------------------------------------------------------------------------
+__global__ void initGeometryKernel(
+	BuildControl* ctl, GeomHeader* header, Box4Node* boxNodes, void* primNodes, size_t size, uint32_t primCount, uint32_t geomType )
+{
+	ctl->sceneBox		 = Box{ { FltMax, FltMax, FltMax }, { -FltMax, -FltMax, -FltMax } };
+	ctl->primCount		 = primCount;
+	ctl->rootNode		 = InvalidValue;
+	ctl->queueHead		 = 0;
+	ctl->pairTileCounter = 0;
+	header->boxNodes	  = boxNodes;
+	header->primNodes	  = primNodes;
+	header->size		  = size;
+	header->referenceCount = 0;
+	header->boxNodeCount  = 1;
+	header->primNodeCount = 0;
+	header->geomType	  = geomType;
+	header->rtip		  = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Triangle pairing: greedy inside each group of 32 consecutive triangles (reference
+// BvhBuilderKernels.h:373-420). Output order = group order (the reference's order across warps
+// is atomic arrival order); made deterministic with a single-pass scan over 256-triangle tiles.
+constexpr uint32_t ScanAgg	= 1u << 30;
+constexpr uint32_t ScanIncl = 2u << 30;
+
+__global__ void __launch_bounds__( PairBlock )
+	pairTrianglesKernel( TriangleMeshSource mesh, uint32_t triCount, uint2* pairs, uint32_t* scanState, BuildControl* ctl )
+{
+	__shared__ uint32_t sTile;
+	__shared__ uint32_t sWarpCount[PairBlock / 32];
+	__shared__ uint32_t sBase;
+	const uint32_t		lane = laneId(), warp = threadIdx.x >> 5;
+	if ( threadIdx.x == 0 ) sTile = atomicAdd( &ctl->pairTileCounter, 1u );
+	__syncthreads();
+	const uint32_t tile	 = sTile;
+	const uint32_t index = tile * PairBlock + threadIdx.x;
+	const bool	   valid = index < triCount;
+	uint3		   idx	 = make_uint3( 0, 0, 0 );
+	if ( valid ) idx = mesh.indices( index );
+
+	uint32_t active	 = __ballot_sync( FullMask, valid );
+	uint32_t partner = InvalidValue; // set on the first triangle of each emitted pair
+	while ( active )
+	{
+		const uint32_t a = __ffs( active ) - 1;
+		active &= active - 1;
+		const uint3 ia		 = make_uint3( __shfl_sync( FullMask, idx.x, a ), __shfl_sync( FullMask, idx.y, a ), __shfl_sync( FullMask, idx.z, a ) );
+		uint3		m;
+		const bool	pairable = ( ( active >> lane ) & 1u ) && TriangleMeshSource::mapIndices( ia, idx, m );
+		const uint32_t cand	 = __ballot_sync( FullMask, pairable );
+		uint32_t	   b	 = a;
+		if ( cand )
+		{
+			b = __ffs( cand ) - 1;
+			active &= ~( 1u << b );
+		}
+		if ( lane == a ) partner = tile * PairBlock + ( warp << 5 ) + b;
+	}
+	const bool	   emit		= valid && partner != InvalidValue;
+	const uint32_t emitMask = __ballot_sync( FullMask, emit );
+	if ( lane == 0 ) sWarpCount[warp] = __popc( emitMask );
+	__syncthreads();
+	uint32_t warpOffset = 0, blockTotal = 0;
+#pragma unroll
+	for ( uint32_t w = 0; w < PairBlock / 32; ++w )
+	{
+		if ( w < warp ) warpOffset += sWarpCount[w];
+		blockTotal += sWarpCount[w];
+	}
+	if ( threadIdx.x == 0 )
+	{
+		// decoupled look-back over preceding tiles
+		volatile uint32_t* st = scanState;
+		uint32_t		   prefix = 0;
+		if ( tile == 0 )
+			st[0] = ScanIncl | blockTotal;
+		else
+		{
+			st[tile] = ScanAgg | blockTotal;
+			int t	 = int( tile ) - 1;
+			while ( true )
+			{
+				const uint32_t v = st[t];
+				if ( ( v >> 30 ) == 0 ) continue;
+				prefix += v & ( ScanAgg - 1 );
+				if ( v & ScanIncl ) break;
+				--t;
+			}
+			st[tile] = ScanIncl | ( prefix + blockTotal );
+		}
+		sBase = prefix;
+		if ( tile == DivideRoundUp( triCount, PairBlock ) - 1 ) ctl->primCount = prefix + blockTotal;
+	}
+	__syncthreads();
+	if ( emit ) pairs[sBase + warpOffset + __popc( emitMask & laneMaskLt() )] = make_uint2( index, partner );
+}
+
+// ------------------------------------------------------------------------------------------------
+// Primitive boxes (kept as 32-byte records so vertices are gathered exactly once before the
+// leaves are packed) + scene box by warp shuffle reduction and 6 atomics per block.
+template <typename Source>
+__global__ void __launch_bounds__( 256 ) primBoxesKernel( Source src, BuildControl* ctl, void* primRefs )
+{
+	const uint32_t n	= ctl->primCount;
+	DBox		   mine = emptyBox();
+	for ( uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x )
+	{
+		const DBox b = src.box( p );
+		storeRec( primRefs, p, b, p, 0u );
+		mine = uniteBox( mine, b );
+	}
+	mine = warpUniteBox( mine );
+	__shared__ DBox sBox[8];
+	if ( laneId() == 0 ) sBox[threadIdx.x >> 5] = mine;
+	__syncthreads();
+	if ( threadIdx.x < 32 )
+	{
+		DBox b = threadIdx.x < ( blockDim.x >> 5 ) ? sBox[threadIdx.x] : emptyBox();
+		b	   = warpUniteBox( b );
+		if ( threadIdx.x == 0 && b.lo.x <= b.hi.x )
+		{
+			atomicMinF( &ctl->sceneBox.lo.x, b.lo.x );
+			atomicMinF( &ctl->sceneBox.lo.y, b.lo.y );
+			atomicMinF( &ctl->sceneBox.lo.z, b.lo.z );
+			atomicMaxF( &ctl->sceneBox.hi.x, b.hi.x );
+			atomicMaxF( &ctl->sceneBox.hi.y, b.hi.y );
+			atomicMaxF( &ctl->sceneBox.hi.z, b.hi.z );
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Morton codes (key = code, value = primitive index) fused with the digit histograms of all
+// four sort passes (reference: ComputeMortonCodes BvhBuilderKernels.h:508-525 + Orochi GHistogram).
+__global__ void __launch_bounds__( 256 )
+	mortonKernel( const BuildControl* ctl, const void* primRefs, uint32_t* keys, uint32_t* vals, uint32_t* sortScratch )
+{
+	__shared__ uint32_t sHist[rsort::Passes * rsort::Radix];
+	for ( int i = threadIdx.x; i < rsort::Passes * rsort::Radix; i += blockDim.x )
+		sHist[i] = 0;
+	__syncthreads();
+	const uint32_t n   = ctl->primCount;
+	const float3   lo  = make_float3( ctl->sceneBox.lo.x, ctl->sceneBox.lo.y, ctl->sceneBox.lo.z );
+	const float3   ext = make_float3( ctl->sceneBox.hi.x - lo.x, ctl->sceneBox.hi.y - lo.y, ctl->sceneBox.hi.z - lo.z );
+	const MortonLayout L = mortonLayout( ext );
+	for ( uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x )
+	{
+		const Rec32	 r = loadRec( primRefs, p );
+		const float3 c = make_float3(
+			( r.box.hi.x + r.box.lo.x ) * 0.5f, ( r.box.hi.y + r.box.lo.y ) * 0.5f, ( r.box.hi.z + r.box.lo.z ) * 0.5f );
+		const float3 pos = make_float3( __fdividef( c.x - lo.x, ext.x ), __fdividef( c.y - lo.y, ext.y ), __fdividef( c.z - lo.z, ext.z ) );
+		const uint32_t key = mortonCode( L, pos );
+		keys[p]			   = key;
+		vals[p]			   = p;
+		rsort::histogramKey( sHist, key );
+	}
+	__syncthreads();
+	for ( int i = threadIdx.x; i < rsort::Passes * rsort::Radix; i += blockDim.x )
+		if ( sHist[i] ) atomicAdd( &sortScratch[i], sHist[i] );
+}
+
+// ------------------------------------------------------------------------------------------------
+// LBVH topology + refit, bottom-up (reference: LbvhBuilderKernels.h:44-134, MortonCode.h:279-285).
+// Internal node id = position of the split gap; the first child to arrive parks its far range
+// end in flags[parent], the second one unites the boxes and climbs. The climbing thread keeps
+// its own box in registers and reads only the sibling's record (through L2: it was written by
+// another SM in this launch).
+__device__ __forceinline__ uint64_t gapDelta( const uint32_t* keys, uint32_t a, uint32_t n )
+{
+	// delta between sorted positions a and a+1; the ends of the array compare as +infinity
+	if ( a >= n - 1 ) return ~0ull; // also catches a == uint32(-1)
+	const uint32_t k0 = keys[a], k1 = keys[a + 1];
+	return ( uint64_t( k0 ^ k1 ) << 32 ) | uint64_t( a ^ ( a + 1 ) );
+}
+
+template <uint32_t LeafType>
+__global__ void __launch_bounds__( 256 ) emitTopologyKernel(
+	BuildControl*	ctl,
+	const uint32_t* sortedKeys,
+	const uint32_t* sortedVals,
+	const void*		primRefs,
+	void*			sortedRefs,
+	void*			scratch,
+	uint32_t*		flags,
+	uint64_t*		taskQueue )
+{
+	const uint32_t n = ctl->primCount;
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( k >= n ) return;
+	const uint32_t prim = sortedVals[k];
+	DBox		   box	= loadRec( primRefs, prim ).box;
+	storeRec( sortedRefs, k, box, prim, 0u );
+
+	uint32_t i = k, j = k + 1; // covered leaf range [i, j)
+	uint32_t self = makeNodeIndex( k, LeafType );
+	uint32_t* scratchWords = reinterpret_cast<uint32_t*>( scratch );
+	while ( true )
+	{
+		const bool	   left	  = ( i == 0 ) || ( j != n && gapDelta( sortedKeys, j - 1, n ) < gapDelta( sortedKeys, i - 1, n ) );
+		const uint32_t parent = left ? j - 1 : i - 1;
+		scratchWords[size_t( parent ) * 8 + ( left ? 6 : 7 )] = self;
+		__threadfence();
+		const uint32_t other = atomicExch( &flags[parent], left ? i : j );
+		if ( other == InvalidValue ) return; // first to arrive: the sibling finishes the node
+		__threadfence();
+		if ( left )
+			j = other;
+		else
+			i = other;
+		// sibling record: its index was stored in the parent's other child slot
+		const uint32_t sib	  = __ldcg( &scratchWords[size_t( parent ) * 8 + ( left ? 7 : 6 )] );
+		const Rec32	   sibRec = isBoxIndex( sib ) ? loadRecCg( scratch, nodeAddr( sib ) ) : loadRecCg( sortedRefs, nodeAddr( sib ) );
+		box					  = uniteBox( box, sibRec.box );
+		// write the node's box (children words are already in place)
+		float4* dst = reinterpret_cast<float4*>( scratch ) + 2 * size_t( parent );
+		dst[0]		= make_float4( box.lo.x, box.lo.y, box.lo.z, box.hi.x );
+		reinterpret_cast<float2*>( dst + 1 )[0] = make_float2( box.hi.y, box.hi.z );
+		self									= makeNodeIndex( parent, BoxType );
+		if ( i == 0 && j == n )
+		{
+			ctl->rootNode = parent;
+			taskQueue[0]  = ( uint64_t( InvalidValue ) << 32 ) | self; // root task: {binary node, parent box}
+			return;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Collapse the binary tree into 4-wide nodes and pack the leaves (reference: Collapse + openNodes
+// BvhBuilderKernels.h:137-193,1088-1258; PackLeaves :1441-1479).
+// A task = (binary node, parent box address); the task's index in the queue IS the address of
+// the Box4Node it produces. Four lanes cooperate on a task (one per child slot). Warps claim 8
+// consecutive task slots at a time in queue order, so the producer of any slot is always held
+// by an already-running warp: the kernel is persistent and deadlock-free at any occupancy.
+// A slot is processed as soon as its task arrives; termination = every leaf has been packed.
+constexpr uint32_t CollapseBlock = 128;
+
+template <typename Source>
+__global__ void __launch_bounds__( CollapseBlock ) collapsePackKernel(
+	Source		  src,
+	BuildControl* ctl,
+	uint32_t*	  boxNodeCounter,  // header field: number of box nodes allocated (starts at 1 = root)
+	uint32_t*	  primNodeCounter, // header field: number of leaf nodes allocated (starts at 0)
+	const void*	  scratch,
+	const void*	  sortedRefs,
+	uint64_t*	  taskQueue,
+	uint32_t	  maxBoxNodes,
+	Box4Node*	  boxNodes,
+	void*		  leafNodes )
+{
+	__shared__ __align__( 16 ) uint32_t sNode[CollapseBlock / 32][8][32]; // one 128-byte line per 4-lane group
+	const uint32_t n	= ctl->primCount;
+	const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
+	const uint32_t group = lane >> 2, slot = lane & 3u;
+	const uint32_t groupMask = 0xFu << ( group * 4 );
+
+	uint32_t idlePolls = 0; // safety net: a corrupted tree must not hang the device
+	while ( true )
+	{
+		uint32_t base = 0;
+		if ( lane == 0 ) base = atomicAdd( &ctl->queueHead, 8u );
+		base				   = __shfl_sync( FullMask, base, 0 );
+		const uint32_t taskIdx = base + group;
+		bool		   done	   = taskIdx >= maxBoxNodes; // such a slot can never be produced
+		uint64_t	   task	   = ~0ull;
+
+		while ( !__all_sync( FullMask, done ) )
+		{
+			bool ready = false;
+			if ( !done )
+			{
+				task  = ldVolatile( taskQueue + taskIdx );
+				ready = task != ~0ull;
+			}
+			if ( !__any_sync( FullMask, ready ) )
+			{
+				// nothing arrived: stop once every leaf is packed (no task can appear any more)
+				uint32_t packed = 0;
+				if ( lane == 0 ) packed = ldVolatile( primNodeCounter );
+				if ( __shfl_sync( FullMask, packed, 0 ) >= n ) return;
+				if ( ++idlePolls > ( 1u << 22 ) )
+				{
+					if ( lane == 0 ) ctl->pad[1] = 1; // build error flag
+					return;
+				}
+				continue;
+			}
+			idlePolls = 0;
+
+			// ---- process the ready groups in lockstep; other lanes idle through the collectives
+			const uint32_t binIndex	  = uint32_t( task );
+			const uint32_t parentAddr = uint32_t( task >> 32 );
+			uint32_t	   child	  = InvalidValue;
+			DBox		   cbox		  = emptyBox();
+			uint32_t	   w0 = 0, w1 = 0; // children of an internal child / primIndex of a leaf child
+			uint32_t	   count = 2;
+			if ( ready && slot < 2 )
+			{
+				const uint32_t* binWords = reinterpret_cast<const uint32_t*>( scratch ) + size_t( nodeAddr( binIndex ) ) * 8;
+				child					 = binWords[6 + slot];
+				const Rec32 rec = isBoxIndex( child ) ? loadRec( scratch, nodeAddr( child ) ) : loadRec( sortedRefs, nodeAddr( child ) );
+				cbox = rec.box, w0 = rec.a, w1 = rec.b;
+			}
+			// open the internal child with the largest area (lowest slot on ties) until 4 children
+#pragma unroll
+			for ( int it = 0; it < 2; ++it )
+			{
+				float area = -FltMax;
+				if ( ready && slot < count && isBoxIndex( child ) ) area = boxArea( cbox );
+				float best = fmaxf( area, __shfl_xor_sync( FullMask, area, 1 ) );
+				best	   = fmaxf( best, __shfl_xor_sync( FullMask, best, 2 ) );
+				const bool	   open	   = ready && best >= 0.0f;
+				const uint32_t isBest  = __ballot_sync( FullMask, open && area == best ) & groupMask;
+				const uint32_t srcLane = isBest ? __ffs( isBest ) - 1 : lane;
+				const uint32_t c0 = __shfl_sync( FullMask, w0, srcLane ), c1 = __shfl_sync( FullMask, w1, srcLane );
+				if ( open )
+				{
+					const uint32_t openSlot = srcLane & 3u;
+					uint32_t	   take		= InvalidValue;
+					if ( slot == openSlot ) take = c0;
+					if ( slot == count ) take = c1;
+					if ( take != InvalidValue )
+					{
+						child			= take;
+						const Rec32 rec = isBoxIndex( child ) ? loadRec( scratch, nodeAddr( child ) ) : loadRec( sortedRefs, nodeAddr( child ) );
+						cbox = rec.box, w0 = rec.a, w1 = rec.b;
+					}
+					++count;
+				}
+			}
+
+			const bool	   active	= ready && slot < count;
+			const bool	   internal = active && isBoxIndex( child );
+			const bool	   leaf		= active && !internal;
+			// warp-aggregated allocation of box nodes (= task slots) and leaf nodes
+			const uint32_t imask = __ballot_sync( FullMask, internal );
+			const uint32_t lmask = __ballot_sync( FullMask, leaf );
+			uint32_t	   ibase = 0, lbase = 0;
+			if ( lane == 0 )
+			{
+				if ( imask ) ibase = atomicAdd( boxNodeCounter, __popc( imask ) );
+				if ( lmask ) lbase = atomicAdd( primNodeCounter, __popc( lmask ) );
+			}
+			ibase			  = __shfl_sync( FullMask, ibase, 0 );
+			lbase			  = __shfl_sync( FullMask, lbase, 0 );
+			uint32_t outChild = InvalidValue;
+			if ( internal )
+			{
+				const uint32_t addr = ibase + __popc( imask & laneMaskLt() );
+				taskQueue[addr]		= ( uint64_t( taskIdx ) << 32 ) | child; // single 8-byte store: arrives whole
+				outChild			= makeNodeIndex( addr, BoxType );
+			}
+			if ( leaf )
+			{
+				const uint32_t addr = lbase + __popc( lmask & laneMaskLt() );
+				src.writeLeaf( leafNodes, addr, w0 );
+				outChild = makeNodeIndex( addr, Source::LeafType );
+			}
+
+			// ---- assemble the 128-byte node in shared memory, write it as whole 16-byte words
+			if ( ready )
+			{
+				uint32_t* nodeWords = sNode[warp][group];
+				nodeWords[slot]		= outChild;
+				const DBox b		= active ? cbox : emptyBox();
+				float*	   bw		= reinterpret_cast<float*>( nodeWords ) + 4 + 6 * slot;
+				bw[0] = b.lo.x, bw[1] = b.lo.y, bw[2] = b.lo.z, bw[3] = b.hi.x, bw[4] = b.hi.y, bw[5] = b.hi.z;
+				if ( slot == 0 )
+				{
+					nodeWords[28] = taskIdx == 0 ? InvalidValue : parentAddr;
+					nodeWords[29] = 0;
+					nodeWords[30] = count;
+					nodeWords[31] = 0;
+				}
+			}
+			__syncwarp();
+			if ( ready )
+			{
+				const uint4* srcWords = reinterpret_cast<const uint4*>( sNode[warp][group] );
+				uint4*		 dst	  = reinterpret_cast<uint4*>( boxNodes + taskIdx );
+				dst[slot]			  = srcWords[slot];
+				dst[slot + 4]		  = srcWords[slot + 4];
+				done				  = true;
+			}
+			__syncwarp();
+		}
+	}
+}
+
+// A single primitive: root with one child (reference: SingletonConstruction BvhBuilderKernels.h:296-331).
+template <typename Source>
+__global__ void singletonKernel( Source src, uint32_t* primNodeCounter, Box4Node* boxNodes, void* leafNodes )
+{
+	const DBox b = src.box( 0 );
+	src.writeLeaf( leafNodes, 0, 0 );
+	Box4Node node;
+	for ( int s = 0; s < 4; ++s )
+	{
+		node.child[s] = InvalidValue;
+		node.box[s]	  = Box{ { FltMax, FltMax, FltMax }, { -FltMax, -FltMax, -FltMax } };
+	}
+	node.child[0]	   = makeNodeIndex( 0, Source::LeafType );
+	node.box[0]		   = Box{ { b.lo.x, b.lo.y, b.lo.z }, { b.hi.x, b.hi.y, b.hi.z } };
+	node.parentAddr	   = InvalidValue;
+	node.updateCounter = 0;
+	node.childCount	   = 1;
+	node.pad		   = 0;
+	boxNodes[0]		   = node;
+	*primNodeCounter   = 1;
+}
+
+} // namespace hiprt

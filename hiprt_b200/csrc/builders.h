@@ -1,0 +1,74 @@
+// Host-side entry points of the CUDA builders (implemented in build_lbvh.cu & friends).
+// The API shim (api.cpp) validates arguments and calls these; nothing here synchronises
+// with the host: every build is a fixed sequence of launches on the caller's stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <hiprt/hiprt_b200_layout.h>
+#include <hiprt/hiprt_types.h>
+
+namespace hiprt
+{
+struct DeviceInfo
+{
+	int		 device	 = 0;
+	uint32_t smCount = 148;
+};
+
+// ---- sizes -------------------------------------------------------------------------------------
+size_t geometryPrimCount( const hiprtGeometryBuildInput& input ); // triangles (or pairs if given) / AABBs
+size_t geometryStorageSize( const hiprtGeometryBuildInput& input );
+size_t geometryTempSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options );
+size_t sceneStorageSize( const hiprtSceneBuildInput& input );
+size_t sceneTempSize( const hiprtSceneBuildInput& input, hiprtBuildOptions options );
+
+// ---- builds (asynchronous on `stream`) -----------------------------------------------------------
+void buildGeometry(
+	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage );
+void buildScene(
+	const DeviceInfo& dev, const hiprtSceneBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage );
+// refit in place (hiprtBuildOperationUpdate)
+void updateGeometry(
+	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage );
+void updateScene(
+	const DeviceInfo& dev, const hiprtSceneBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage );
+// many small geometries in one launch (one CTA per geometry)
+size_t batchTempSize( uint32_t numGeometries );
+void   buildGeometriesBatch(
+	  const DeviceInfo&				 dev,
+	  const hiprtGeometryBuildInput* inputs,
+	  uint32_t						 numGeometries,
+	  hiprtBuildOptions				 options,
+	  void*							 temp,
+	  cudaStream_t					 stream,
+	  void* const*					 storages );
+
+// ---- introspection for the parity tests: where the intermediate arrays of the last build of
+// `primCount` primitives live inside the caller's temporary buffer (byte offsets).
+struct TempLayout
+{
+	size_t control;	   // BuildControl
+	size_t pairs;	   // uint2[triangles]          (triangle meshes that are paired)
+	size_t pairScan;   // look-back words of the pairing scan
+	size_t primRefs;   // 32 B x N  {box, primIndex} in input order
+	size_t keys[2];	   // u32 x N ping-pong
+	size_t vals[2];	   // u32 x N ping-pong
+	size_t sortScratch;
+	size_t sortedRefs; // 32 B x N  {box, primIndex} in sorted order
+	size_t scratch;	   // 32 B x N  binary nodes
+	size_t flags;	   // u32 x N
+	size_t taskQueue;  // u64 x maxBoxNodes (aliases keys/vals)
+	size_t total;
+};
+TempLayout tempLayout( size_t primCount, size_t triangleCountForPairing );
+
+struct BuildControl
+{
+	Box		 sceneBox;		 // union of primitive boxes (atomics)
+	uint32_t primCount;		 // N after pairing
+	uint32_t rootNode;		 // binary root id
+	uint32_t queueHead;		 // collapse: next task to claim
+	uint32_t pairTileCounter;
+	uint32_t pad[6];
+};
+static_assert( sizeof( BuildControl ) == 64, "BuildControl is one 64-byte line" );
+} // namespace hiprt

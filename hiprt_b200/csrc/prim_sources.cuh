@@ -1,0 +1,134 @@
+// Primitive containers of the builders: what a "primitive" is (triangle pair, custom AABB,
+// instance), how its box is fetched and how its leaf node is written.
+// Reference counterparts: TriangleMesh.h:56-287, AabbList.h:31-60, InstanceList.h:31-235.
+#pragma once
+#include "device_util.cuh"
+
+namespace hiprt
+{
+// ------------------------------------------------------------------------------------------------
+struct TriangleMeshSource
+{
+	static constexpr uint32_t LeafType = TriangleType;
+	static constexpr uint32_t LeafSize = sizeof( TrianglePairNode );
+
+	const uint8_t* vertices;
+	const uint8_t* triangles; // null: triangle t uses vertices 3t..3t+2
+	const uint2*   pairs;	  // null: primitive p is the lone triangle p
+	uint32_t	   vertexStride;
+	uint32_t	   triangleStride;
+
+	__device__ __forceinline__ float3 vertex( uint32_t i ) const
+	{
+		const float* p = reinterpret_cast<const float*>( vertices + size_t( i ) * vertexStride );
+		return make_float3( __ldg( p ), __ldg( p + 1 ), __ldg( p + 2 ) );
+	}
+	__device__ __forceinline__ uint3 indices( uint32_t t ) const
+	{
+		if ( triangles == nullptr ) return make_uint3( 3 * t, 3 * t + 1, 3 * t + 2 );
+		const uint32_t* p = reinterpret_cast<const uint32_t*>( triangles + size_t( t ) * triangleStride );
+		return make_uint3( __ldg( p ), __ldg( p + 1 ), __ldg( p + 2 ) );
+	}
+	__device__ __forceinline__ uint2 pairOf( uint32_t p ) const { return pairs ? pairs[p] : make_uint2( p, p ); }
+
+	__device__ __forceinline__ DBox box( uint32_t p ) const
+	{
+		const uint2 pr = pairOf( p );
+		const uint3 i0 = indices( pr.x );
+		DBox		b  = emptyBox();
+		growBox( b, vertex( i0.x ) );
+		growBox( b, vertex( i0.y ) );
+		growBox( b, vertex( i0.z ) );
+		if ( pr.x != pr.y )
+		{
+			const uint3 i1 = indices( pr.y );
+			growBox( b, vertex( i1.x ) );
+			growBox( b, vertex( i1.y ) );
+			growBox( b, vertex( i1.z ) );
+		}
+		return b;
+	}
+
+	// For each index of b its position in a (3 = absent); pairable iff at most one is absent
+	// (TriangleMesh.h:32-50).
+	static __device__ __forceinline__ bool mapIndices( const uint3 a, const uint3 b, uint3& m )
+	{
+		m.x = b.x == a.z ? 2u : ( b.x == a.y ? 1u : ( b.x == a.x ? 0u : 3u ) );
+		m.y = b.y == a.z ? 2u : ( b.y == a.y ? 1u : ( b.y == a.x ? 0u : 3u ) );
+		m.z = b.z == a.z ? 2u : ( b.z == a.y ? 1u : ( b.z == a.x ? 0u : 3u ) );
+		return ( m.x == 3u ) + ( m.y == 3u ) + ( m.z == 3u ) <= 1;
+	}
+
+	// 64-byte pair leaf: triangle 0 rotated so that its unshared vertex comes first, the shared
+	// edge is (v1,v2) and v3 is the unshared vertex of triangle 1 (TriangleMesh.h:89-157).
+	__device__ __forceinline__ void writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t p ) const
+	{
+		const uint2 pr	  = pairOf( p );
+		uint3		i0	  = indices( pr.x );
+		uint32_t	flags = DefaultTriangleFlags;
+		uint32_t	i3	  = 0;
+		if ( pr.x != pr.y )
+		{
+			uint3 i1 = indices( pr.y );
+			uint3 m;
+			mapIndices( i1, i0, m );
+			uint3 f0 = make_uint3( 1, 2, 0 );
+			if ( m.y == 3u )
+			{
+				m  = make_uint3( m.y, m.z, m.x );
+				i0 = make_uint3( i0.y, i0.z, i0.x );
+				f0 = make_uint3( f0.z, f0.x, f0.y );
+			}
+			else if ( m.z == 3u )
+			{
+				m  = make_uint3( m.z, m.x, m.y );
+				i0 = make_uint3( i0.z, i0.x, i0.y );
+				f0 = make_uint3( f0.y, f0.z, f0.x );
+			}
+			const bool keep = ( m.y == 0u && m.z == 2u ) || ( m.y == 2u && m.z == 1u ) || ( m.y == 1u && m.z == 0u );
+			const bool flip = !keep;
+			uint3	   f1	= flip ? make_uint3( 2, 1, 0 ) : make_uint3( 0, 1, 2 );
+			if ( ( m.y == 2u && m.z == 1u ) || ( m.y == 1u && m.z == 2u ) )
+			{
+				i1 = make_uint3( i1.y, i1.z, i1.x );
+				f1 = make_uint3( f1.z, f1.x, f1.y );
+			}
+			else if ( ( m.y == 2u && m.z == 0u ) || ( m.y == 0u && m.z == 2u ) )
+			{
+				i1 = make_uint3( i1.z, i1.x, i1.y );
+				f1 = make_uint3( f1.y, f1.z, f1.x );
+			}
+			flags = ( uint32_t( flip ) << 13 ) | ( f1.y << 10 ) | ( f1.x << 8 ) | ( f0.y << 2 ) | f0.x;
+			i3	  = i1.z;
+		}
+		const float3 v0 = vertex( i0.x ), v1 = vertex( i0.y ), v2 = vertex( i0.z );
+		const float3 v3 = ( pr.x != pr.y ) ? vertex( i3 ) : v2;
+		float4*		 dst = reinterpret_cast<float4*>( static_cast<TrianglePairNode*>( leafArray ) + leafAddr );
+		dst[0]			 = make_float4( v0.x, v0.y, v0.z, v1.x );
+		dst[1]			 = make_float4( v1.y, v1.z, v2.x, v2.y );
+		dst[2]			 = make_float4( v2.z, v3.x, v3.y, v3.z );
+		dst[3]			 = make_float4( 0.0f, __uint_as_float( pr.x ), __uint_as_float( pr.y ), __uint_as_float( flags ) );
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+struct AabbListSource
+{
+	static constexpr uint32_t LeafType = CustomType;
+	static constexpr uint32_t LeafSize = sizeof( CustomNode );
+
+	const uint8_t* aabbs;
+	uint32_t	   stride; // 24 (2 x float3) or 32 (2 x float4); max starts at stride/2
+
+	__device__ __forceinline__ DBox box( uint32_t p ) const
+	{
+		const float* lo = reinterpret_cast<const float*>( aabbs + size_t( p ) * stride );
+		const float* hi = reinterpret_cast<const float*>( aabbs + size_t( p ) * stride + ( stride >> 1 ) );
+		return DBox{ make_float3( __ldg( lo ), __ldg( lo + 1 ), __ldg( lo + 2 ) ), make_float3( __ldg( hi ), __ldg( hi + 1 ), __ldg( hi + 2 ) ) };
+	}
+	__device__ __forceinline__ void writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t p ) const
+	{
+		static_cast<CustomNode*>( leafArray )[leafAddr].primIndex = p;
+	}
+};
+} // namespace hiprt

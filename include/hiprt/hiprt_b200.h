@@ -1,0 +1,74 @@
+// hiprt_b200 -- C-ABI entry points this build adds next to the reference API (hiprt/hiprt.h).
+//
+// The reference has no host-side "trace" call: users launch their own kernels that include
+// hiprt_device.h (reference: test/kernels/HiprtTestKernel.h:102-116 `TraceKernel` is the
+// canonical rays-in/hits-out kernel). For the benchmark, the parity tests and bindings from
+// other languages we export that kernel as a library call; it is built from the same
+// hiprt_device.h traversal objects a user kernel would use.
+#pragma once
+#include <hiprt/hiprt.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// rays/hits are DEVICE pointers (hiprtRay[numRays], hiprtHit[numRays]); asynchronous on `stream`.
+// traversalType: hiprtTraversalTerminateAtClosestHit or hiprtTraversalTerminateAtAnyHit (first hit found).
+HIPRT_API hiprtError hiprtB200TraceGeometry(
+	hiprtContext	   context,
+	hiprtGeometry	   geometry,
+	const hiprtRay*	   rays,
+	uint32_t		   numRays,
+	hiprtHit*		   hits,
+	hiprtTraversalType traversalType,
+	hiprtApiStream	   stream );
+
+HIPRT_API hiprtError hiprtB200TraceScene(
+	hiprtContext	   context,
+	hiprtScene		   scene,
+	const hiprtRay*	   rays,
+	uint32_t		   numRays,
+	hiprtHit*		   hits,
+	hiprtTraversalType traversalType,
+	hiprtRayMask	   mask,
+	hiprtApiStream	   stream );
+
+// Same with HOST buffers: copies the rays to the device, traces, copies the hits back and
+// synchronises the stream (the end-to-end path measured by bench.py's "e2e").
+HIPRT_API hiprtError hiprtB200TraceGeometryHost(
+	hiprtContext	   context,
+	hiprtGeometry	   geometry,
+	const hiprtRay*	   hostRays,
+	uint32_t		   numRays,
+	hiprtHit*		   hostHits,
+	hiprtTraversalType traversalType,
+	hiprtApiStream	   stream );
+
+HIPRT_API hiprtError hiprtB200TraceSceneHost(
+	hiprtContext	   context,
+	hiprtScene		   scene,
+	const hiprtRay*	   hostRays,
+	uint32_t		   numRays,
+	hiprtHit*		   hostHits,
+	hiprtTraversalType traversalType,
+	hiprtRayMask	   mask,
+	hiprtApiStream	   stream );
+
+// Byte offsets of the builder's intermediate arrays inside the caller's temporary buffer
+// (parity tests read sorted Morton keys, binary nodes etc. from there). 16 size_t values,
+// see hiprt_b200/csrc/builders.h TempLayout.
+HIPRT_API hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount, size_t* offsetsOut, uint32_t numOffsets );
+
+// The device-side API header tree (hiprt_device.h and what it includes) as embedded strings,
+// for callers that NVRTC-compile their own kernels. Returns the number of headers.
+HIPRT_API uint32_t hiprtB200GetDeviceHeaders( const char*** namesOut, const char*** sourcesOut );
+
+HIPRT_API const char* hiprtB200GetLastErrorString( hiprtContext context );
+
+// Synchronous device-to-host copy of raw bytes (lets bindings without a CUDA runtime of their
+// own inspect built structures through the handle).
+HIPRT_API hiprtError hiprtB200CopyToHost( hiprtContext context, void* hostDst, const void* deviceSrc, size_t bytes );
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,178 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on identical inputs."""
+import numpy as np
+import pytest
+
+from hiprt_b200 import api, scenes
+from oracle import binding as orc
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def to_dev(ctx, a, dtype=None):
+    t = ctx.torch
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)
+    return t.from_numpy(a).to(ctx.device)
+
+
+def compare_hits(got, ref, rel=1e-5):
+    """primID exact; t / uv within `rel` relative. Returns the number of exact-tie disagreements."""
+    same = got["primID"] == ref["primID"]
+    hit = ref["primID"] != orc.INVALID
+    ties = 0
+    if not same.all():
+        bad = ~same
+        # tie-aware: different primitives are tolerated only at (nearly) the same distance
+        both_hit = (got["primID"][bad] != orc.INVALID) & (ref["primID"][bad] != orc.INVALID)
+        assert both_hit.all(), f"{(~both_hit).sum()} rays hit in one implementation only"
+        dt = np.abs(got["t"][bad] - ref["t"][bad]) / np.maximum(np.abs(ref["t"][bad]), 1e-20)
+        assert (dt <= rel).all(), f"{(dt > rel).sum()} primID mismatches away from ties (max rel dt {dt.max():.3g})"
+        ties = int(bad.sum())
+    ok = same & hit
+    dt = np.abs(got["t"][ok] - ref["t"][ok]) / np.maximum(np.abs(ref["t"][ok]), 1e-20)
+    assert dt.size == 0 or dt.max() <= rel, f"t differs: max rel {dt.max():.3g}"
+    duv = np.abs(got["uv"][ok] - ref["uv"][ok])
+    assert duv.size == 0 or duv.max() <= rel, f"uv differs: max abs {duv.max():.3g}"
+    return ties
+
+
+def check_build_against_oracle(ctx, geom, og, expect_same_keys=False):
+    """Binary topology and the canonicalised wide structure must be bit-exact for identical sorted keys."""
+    n = og.prim_count
+    hdr = geom.header()
+    assert int(hdr["primNodeCount"]) == n
+    skeys = geom.temp_array("keys0", np.uint32, n)
+    svals = geom.temp_array("vals0", np.uint32, n)
+    # sorted, stable, a permutation
+    assert np.all(skeys[1:] >= skeys[:-1])
+    eq = skeys[1:] == skeys[:-1]
+    assert np.all(svals[1:][eq] > svals[:-1][eq]), "sort is not stable"
+    assert np.array_equal(np.sort(svals), np.arange(n, dtype=np.uint32))
+    # Morton codes: report mismatches against the IEEE oracle (the GPU uses fast division like the reference)
+    keys_by_prim = np.empty(n, np.uint32)
+    keys_by_prim[svals] = skeys
+    mismatch = float((keys_by_prim != og.keys).mean())
+    if expect_same_keys:
+        assert mismatch == 0.0
+    assert mismatch < 1e-3, f"Morton mismatch fraction {mismatch}"
+    # topology on identical keys
+    og.rebuild_from_sorted(skeys, svals)
+    if n > 1:
+        gscratch = geom.temp_array("scratch", api.SCRATCH_DTYPE, n - 1)
+        oscratch = og.scratch
+        assert np.array_equal(gscratch["child0"], oscratch["child0"])
+        assert np.array_equal(gscratch["child1"], oscratch["child1"])
+        assert np.array_equal(gscratch["box"].view(np.uint32), oscratch["box"].view(np.uint32))
+    boxes, leaves = geom.nodes()
+    cb, cl = orc.canonicalize(boxes.view(orc.BOX4_DTYPE), leaves.view(orc.TRIPAIR_DTYPE))
+    ob, ol = og.box_nodes, og.leaves
+    assert len(cb) == len(ob) == int(hdr["boxNodeCount"])
+    assert cb.tobytes() == ob.tobytes(), "wide nodes differ from the oracle"
+    assert cl.tobytes() == ol.tobytes(), "leaf nodes differ from the oracle"
+    return mismatch
+
+
+def test_c1_cornell_box_hits_match_oracle(ctx):
+    verts, _, _ = H.cornell_box()
+    idx = np.arange(96, dtype=np.uint32).reshape(-1, 3)
+    geom = ctx.build(to_dev(ctx, verts), to_dev(ctx, idx))
+    og = orc.Geometry(verts, idx)
+    check_build_against_oracle(ctx, geom, og)
+    rays = scenes.cornell_rays(512, 512)
+    got = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays)))
+    ref = og.trace(rays, tie_mode=1)
+    assert np.array_equal(got["primID"], ref["primID"])
+    assert np.array_equal(got["t"].view(np.uint32), ref["t"].view(np.uint32))
+    assert np.array_equal(got["uv"].view(np.uint32), ref["uv"].view(np.uint32))
+    assert np.array_equal(got["normal"].view(np.uint32), ref["normal"].view(np.uint32))
+    # and the end-to-end host-buffer call returns the same thing
+    got2 = ctx.trace_host(geom, rays)
+    assert got2.tobytes() == got.tobytes()
+    geom.destroy()
+
+
+def test_anyhit_agrees_with_closest_on_occlusion(ctx):
+    verts, _, _ = H.cornell_box()
+    idx = np.arange(96, dtype=np.uint32).reshape(-1, 3)
+    geom = ctx.build(to_dev(ctx, verts), to_dev(ctx, idx))
+    rays = scenes.cornell_rays(256, 256)
+    d = ctx.rays_to_device(rays)
+    closest = ctx.hits_to_host(ctx.trace(geom, d))
+    anyhit = ctx.hits_to_host(ctx.trace(geom, d, kind=api.ANY_HIT))
+    assert np.array_equal(closest["primID"] != api.INVALID, anyhit["primID"] != api.INVALID)
+    geom.destroy()
+
+
+@pytest.mark.parametrize("n_tris", [1, 2, 3, 5, 33, 1000, 100_000])
+def test_soup_build_and_hits(ctx, n_tris):
+    verts = scenes.random_soup(n_tris, seed=n_tris)
+    geom = ctx.build(to_dev(ctx, verts))
+    og = orc.Geometry(verts)
+    check_build_against_oracle(ctx, geom, og)
+    rays = scenes.random_rays(20000, verts.min(0), verts.max(0), seed=3)
+    got = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays)))
+    ref = og.trace(rays, tie_mode=1)
+    compare_hits(got, ref)
+    geom.destroy()
+
+
+@pytest.mark.parametrize("shape", [(3, 1), (16, 16), (300, 300)])
+def test_indexed_mesh_pairing_topology_hits(ctx, shape):
+    verts, idx = scenes.sphere_mesh(*shape)
+    geom = ctx.build(to_dev(ctx, verts), to_dev(ctx, idx))
+    og = orc.Geometry(verts, idx)
+    n = og.prim_count
+    # deterministic pairing: identical pair list, in group order
+    L = api.temp_layout(len(idx), len(idx))
+    ctx.torch.cuda.synchronize()
+    pairs = geom.temp[L["pairs"]: L["pairs"] + n * 8].cpu().numpy().view(np.uint32).reshape(-1, 2)
+    assert int(geom.header()["primNodeCount"]) == n
+    assert np.array_equal(pairs, og.pairs)
+    check_build_against_oracle(ctx, geom, og)
+    rays = scenes.pinhole_rays(256, 256, (0, 0, 3), (0, 0, 0))
+    got = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays)))
+    ref = og.trace(rays, tie_mode=1)
+    compare_hits(got, ref)
+    geom.destroy()
+
+
+def test_planar_grid_uses_2d_morton(ctx):
+    verts, idx = scenes.grid_mesh(64, 48)
+    geom = ctx.build(to_dev(ctx, verts), to_dev(ctx, idx))
+    og = orc.Geometry(verts, idx)
+    check_build_against_oracle(ctx, geom, og)
+    rays = H.ortho_rays(128, 128)
+    got = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays)))
+    compare_hits(got, og.trace(rays, tie_mode=1))
+    geom.destroy()
+
+
+def test_identical_triangles_all_equal_morton_codes(ctx):
+    # reference test PlocFallback / degenerate input: every primitive has the same code
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    verts = np.tile(tri, (5000, 1))
+    geom = ctx.build(to_dev(ctx, verts))
+    og = orc.Geometry(verts)
+    check_build_against_oracle(ctx, geom, og)
+    rays = scenes.make_rays([[0.2, 0.2, -1.0]], [[0, 0, 1.0]])
+    got = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays)))
+    assert got["primID"][0] == 0 and got["t"][0] == 1.0  # min (t, primID)
+    geom.destroy()
+
+
+def test_disable_pairing_flag(ctx):
+    verts, idx = scenes.sphere_mesh(32, 16)
+    geom = ctx.build(to_dev(ctx, verts), to_dev(ctx, idx), flags=api.FAST_BUILD | api.DISABLE_PAIRING)
+    og = orc.Geometry(verts, idx, allow_pairing=False)
+    assert int(geom.header()["primNodeCount"]) == len(idx) == og.prim_count
+    check_build_against_oracle(ctx, geom, og)
+    geom.destroy()
