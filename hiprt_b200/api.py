@@ -237,7 +237,10 @@ class Context:
             self.h = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: ctypes may already be gone
+            pass
 
     def _check(self, code, what, ctx=True):
         if code != SUCCESS:

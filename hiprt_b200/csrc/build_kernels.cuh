@@ -303,6 +303,7 @@ __global__ void __launch_bounds__( CollapseBlock ) collapsePackKernel(
 		uint32_t base = 0;
 		if ( lane == 0 ) base = atomicAdd( &ctl->queueHead, 8u );
 		base				   = __shfl_sync( FullMask, base, 0 );
+		if ( base >= maxBoxNodes ) return; // the queue is exhausted: every slot is owned by some warp
 		const uint32_t taskIdx = base + group;
 		bool		   done	   = taskIdx >= maxBoxNodes; // such a slot can never be produced
 		uint64_t	   task	   = ~0ull;

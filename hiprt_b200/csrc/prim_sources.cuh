@@ -3,6 +3,7 @@
 // Reference counterparts: TriangleMesh.h:56-287, AabbList.h:31-60, InstanceList.h:31-235.
 #pragma once
 #include "device_util.cuh"
+#include "transform_util.cuh"
 
 namespace hiprt
 {
@@ -129,6 +130,84 @@ struct AabbListSource
 	__device__ __forceinline__ void writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t p ) const
 	{
 		static_cast<CustomNode*>( leafArray )[leafAddr].primIndex = p;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------
+// Instances of a scene. Box = union over the (up to 4) child boxes of the referenced structure's
+// root node of the box of their 8 transformed corners (reference: InstanceList.h:104-121,
+// Transform.h:496-517); leaf = 64-byte InstanceNode holding the world->object matrix
+// (BvhNode.h:1142-1182). Frames have been converted to SRT form by initSceneKernel.
+struct InstanceSource
+{
+	static constexpr uint32_t LeafType = InstanceType;
+	static constexpr uint32_t LeafSize = sizeof( InstanceNode );
+
+	const hiprtInstance*		instances;
+	const hiprtTransformHeader* headers; // null: frame k belongs to instance k
+	const SRTFrame*				frames;	 // converted frames inside the scene storage
+	const uint32_t*				masks;	 // null: all ones
+	uint32_t					frameCount;
+
+	__device__ __forceinline__ hiprtTransformHeader header( uint32_t p ) const
+	{
+		return headers ? headers[p] : hiprtTransformHeader{ p, 1u };
+	}
+	__device__ __forceinline__ DFrame frame( uint32_t index ) const
+	{
+		return ( frameCount == 0 || frames == nullptr ) ? identityFrame() : loadFrame( frames, index );
+	}
+
+	__device__ __forceinline__ DBox box( uint32_t p ) const
+	{
+		const hiprtTransformHeader h = header( p );
+		// both header kinds start with the box-node pointer (Header.h:33-60)
+		const Box4Node* root = *reinterpret_cast<Box4Node* const*>( instances[p].geometry );
+		const float4*	q	 = reinterpret_cast<const float4*>( root );
+		const float4	q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4], q5 = q[5], q6 = q[6];
+		const float		b[24]	   = { q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w,
+									   q4.x, q4.y, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, q6.x, q6.y, q6.z, q6.w };
+		const uint32_t	child[4]   = { __float_as_uint( q0.x ), __float_as_uint( q0.y ), __float_as_uint( q0.z ), __float_as_uint( q0.w ) };
+		const uint32_t	childCount = reinterpret_cast<const uint32_t*>( root )[30];
+		DBox			out		   = emptyBox();
+		const uint32_t	nFrames	   = max( h.frameCount, 1u );
+		for ( uint32_t f = 0; f < nFrames; ++f ) // animated instances: union over the key frames
+		{
+			const DFrame fr	   = frame( h.frameIndex + f );
+			const bool	 ident = frameIsIdentity( fr );
+#pragma unroll
+			for ( uint32_t c = 0; c < 4; ++c )
+			{
+				if ( c >= childCount || child[c] == InvalidValue ) continue;
+				const float3 lo = make_float3( b[6 * c], b[6 * c + 1], b[6 * c + 2] ), hi = make_float3( b[6 * c + 3], b[6 * c + 4], b[6 * c + 5] );
+#pragma unroll
+				for ( uint32_t k = 0; k < 8; ++k )
+				{
+					const float3 corner = make_float3( ( k & 4 ) ? hi.x : lo.x, ( k & 2 ) ? hi.y : lo.y, ( k & 1 ) ? hi.z : lo.z );
+					growBox( out, ident ? corner : frameTransformPoint( fr, corner ) );
+				}
+			}
+		}
+		return out;
+	}
+
+	__device__ __forceinline__ void writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t p ) const
+	{
+		const hiprtTransformHeader h	= header( p );
+		const hiprtInstance		   inst = instances[p];
+		const DFrame			   fr	= frame( h.frameIndex );
+		const bool				   ident = frameIsIdentity( fr );
+		float					   m[3][4] = { { 1, 0, 0, 0 }, { 0, 1, 0, 0 }, { 0, 0, 1, 0 } };
+		if ( !ident ) frameInverseMatrix( fr, m );
+		const uint32_t mask = masks ? masks[p] : FullRayMask;
+		// bits: primIndex:24 | type:1 | static:1 | identity:1
+		const uint32_t bits = ( p & 0xFFFFFFu ) | ( uint32_t( inst.type == hiprtInstanceTypeScene ) << 24 ) | ( 1u << 25 ) | ( uint32_t( ident ) << 26 );
+		const uint64_t ptr	= reinterpret_cast<uint64_t>( inst.geometry );
+		float4*		   dst	= reinterpret_cast<float4*>( static_cast<InstanceNode*>( leafArray ) + leafAddr );
+		dst[0]				= make_float4( m[0][0], m[0][1], m[0][2], m[0][3] );
+		dst[1]				= make_float4( m[1][0], m[1][1], m[1][2], m[1][3] );
+		dst[2]				= make_float4( m[2][0], m[2][1], m[2][2], m[2][3] );
+		dst[3] = make_float4( __uint_as_float( uint32_t( ptr ) ), __uint_as_float( uint32_t( ptr >> 32 ) ), __uint_as_float( mask ), __uint_as_float( bits ) );
 	}
 };
 } // namespace hiprt
