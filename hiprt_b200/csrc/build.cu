@@ -182,11 +182,67 @@ void buildGeometry(
 
 // ------------------------------------------------------------------------------------------------
 // not yet implemented in this revision
-size_t sceneStorageSize( const hiprtSceneBuildInput& ) { throw std::runtime_error( "scene build: not implemented yet" ); }
-size_t sceneTempSize( const hiprtSceneBuildInput&, hiprtBuildOptions ) { throw std::runtime_error( "scene build: not implemented yet" ); }
-void   buildScene( const DeviceInfo&, const hiprtSceneBuildInput&, hiprtBuildOptions, void*, cudaStream_t, void* )
+// ------------------------------------------------------------------------------------------------
+// Scene (top-level) build: primitives are instances (reference: LbvhBuilder.cpp:126-164 with
+// InstanceList<Frame>, InitSceneData BvhBuilderKernels.h:224-294). Storage layout:
+// [SceneHeader][Box4Node x maxBox][InstanceNode x I][InstanceRecord x I][SRTFrame x F].
+struct SceneLayout
 {
-	throw std::runtime_error( "scene build: not implemented yet" );
+	size_t boxNodes, primNodes, instances, frames, total;
+};
+
+static SceneLayout sceneLayout( const hiprtSceneBuildInput& input )
+{
+	SceneLayout	 L{};
+	const size_t n = input.instanceCount;
+	L.boxNodes	   = alignUp( sizeof( SceneHeader ) );
+	L.primNodes	   = L.boxNodes + alignUp( maxBoxNodeCount( n ) * sizeof( Box4Node ) );
+	L.instances	   = L.primNodes + alignUp( n * sizeof( InstanceNode ) );
+	L.frames	   = L.instances + alignUp( n * sizeof( InstanceRecord ) );
+	L.total		   = L.frames + alignUp( size_t( input.frameCount ) * sizeof( SRTFrame ) );
+	return L;
+}
+
+size_t sceneStorageSize( const hiprtSceneBuildInput& input ) { return sceneLayout( input ).total; }
+size_t sceneTempSize( const hiprtSceneBuildInput& input, hiprtBuildOptions ) { return tempLayout( input.instanceCount, 0 ).total; }
+
+void buildScene(
+	const DeviceInfo& dev, const hiprtSceneBuildInput& input, hiprtBuildOptions options, void* tempBuffer, cudaStream_t stream, void* storage )
+{
+	(void)options;
+	const uint32_t n = input.instanceCount;
+	if ( n == 0 ) throw std::runtime_error( "empty scene" );
+	if ( input.instances == nullptr ) throw std::runtime_error( "scene without instances" );
+	const SceneLayout S	   = sceneLayout( input );
+	const TempLayout  L	   = tempLayout( n, 0 );
+	uint8_t*		  temp = static_cast<uint8_t*>( tempBuffer );
+	uint8_t*		  out  = static_cast<uint8_t*>( storage );
+	SceneHeader*	  header	= reinterpret_cast<SceneHeader*>( out );
+	Box4Node*		  boxNodes	= reinterpret_cast<Box4Node*>( out + S.boxNodes );
+	InstanceNode*	  instNodes = reinterpret_cast<InstanceNode*>( out + S.primNodes );
+	InstanceRecord*	  records	= reinterpret_cast<InstanceRecord*>( out + S.instances );
+	SRTFrame*		  frames	= reinterpret_cast<SRTFrame*>( out + S.frames );
+	BuildControl*	  ctl		= reinterpret_cast<BuildControl*>( temp + L.control );
+
+	InstanceSource src{};
+	src.instances  = static_cast<const hiprtInstance*>( input.instances );
+	src.headers	   = static_cast<const hiprtTransformHeader*>( input.instanceTransformHeaders );
+	src.frames	   = ( input.frameCount > 0 && input.instanceFrames != nullptr ) ? frames : nullptr;
+	src.masks	   = static_cast<const uint32_t*>( input.instanceMasks );
+	src.frameCount = input.frameCount;
+
+	const uint32_t work = std::max( n, input.frameCount );
+	initSceneKernel<<<DivideRoundUp( work, 256u ), 256, 0, stream>>>(
+		ctl, header, boxNodes, instNodes, records, frames, S.total, src, n, input.instanceFrames, input.frameType == hiprtFrameTypeMatrix );
+	if ( n == 1 )
+	{
+		singletonKernel<InstanceSource><<<1, 1, 0, stream>>>( src, &header->primNodeCount, boxNodes, instNodes );
+		HIPRT_CUDA_CHECK( cudaGetLastError() );
+		return;
+	}
+	const uint32_t streamGrid = std::min<uint32_t>( DivideRoundUp( n, 256u ), dev.smCount * 8 );
+	primBoxesKernel<InstanceSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
+	runLbvh( dev, src, n, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
 }
 void updateGeometry( const DeviceInfo&, const hiprtGeometryBuildInput&, hiprtBuildOptions, void*, cudaStream_t, void* )
 {

@@ -59,6 +59,60 @@ __global__ void initGeometryKernel(
 	header->rtip		  = 0;
 }
 
+// Scene header + per-instance records + API frames converted to the internal SRT form
+// (reference: InitSceneData BvhBuilderKernels.h:224-266, frame conversion Transform.h:134-176).
+__global__ void __launch_bounds__( 256 ) initSceneKernel(
+	BuildControl*	ctl,
+	SceneHeader*	header,
+	Box4Node*		boxNodes,
+	InstanceNode*	instNodes,
+	InstanceRecord* records,
+	SRTFrame*		frames,
+	size_t			size,
+	InstanceSource	src,
+	uint32_t		instanceCount,
+	const void*		apiFrames,
+	bool			matrixFrames )
+{
+	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( index < instanceCount )
+	{
+		const hiprtInstance		   inst = src.instances[index];
+		const hiprtTransformHeader h	= src.header( index );
+		uint4					   rec;
+		rec.x					  = h.frameIndex;
+		rec.y					  = ( h.frameCount & 0x7FFFFFFFu ) | ( uint32_t( inst.type == hiprtInstanceTypeScene ) << 31 );
+		const uint64_t ptr		  = reinterpret_cast<uint64_t>( inst.geometry );
+		rec.z = uint32_t( ptr ), rec.w = uint32_t( ptr >> 32 );
+		reinterpret_cast<uint4*>( records )[index] = rec;
+	}
+	if ( index < src.frameCount && apiFrames != nullptr )
+	{
+		const DFrame f = matrixFrames ? frameFromMatrix( static_cast<const hiprtFrameMatrix*>( apiFrames )[index] )
+									  : frameFromSRT( static_cast<const hiprtFrameSRT*>( apiFrames )[index] );
+		storeFrame( frames, index, f );
+	}
+	if ( index == 0 )
+	{
+		ctl->sceneBox		 = Box{ { FltMax, FltMax, FltMax }, { -FltMax, -FltMax, -FltMax } };
+		ctl->primCount		 = instanceCount;
+		ctl->rootNode		 = InvalidValue;
+		ctl->queueHead		 = 0;
+		ctl->pairTileCounter = 0;
+		header->boxNodes	   = boxNodes;
+		header->primNodes	   = instNodes;
+		header->instances	   = records;
+		header->frames		   = frames;
+		header->size		   = size;
+		header->referenceCount = 0;
+		header->primCount	   = instanceCount;
+		header->primNodeCount  = 0;
+		header->boxNodeCount   = 1;
+		header->frameCount	   = src.frameCount;
+		header->rtip		   = 0;
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // Triangle pairing: greedy inside each group of 32 consecutive triangles (reference
 // BvhBuilderKernels.h:373-420). Output order = group order (the reference's order across warps

@@ -746,6 +746,314 @@ void traceAll( const BvhView& bvh, const hiprtRay& ray, std::vector<hiprtHit>& h
 		stack.pop_back();
 	}
 }
+// ---------------------------------------------------------------------------------------------
+// Scene (top level): instance transforms (Transform.h:41-240, Quaternion.h:30-140,
+// QrDecomposition.h:30-135), instance boxes (InstanceList.h:104-121, Transform.h:460-517),
+// instance leaves (BvhNode.h:1109-1182), two-level traversal (hiprt_device_impl.h:959-1204).
+struct Quat
+{
+	float x, y, z, w;
+};
+struct Frame
+{
+	Quat  rot{ 0, 0, 0, 1 };
+	V3	  scale{ 1, 1, 1 }, shear{ 0, 0, 0 }, trans{ 0, 0, 0 };
+	float time = 0;
+	bool  identity() const
+	{
+		return scale.x == 1 && scale.y == 1 && scale.z == 1 && shear.x == 0 && shear.y == 0 && shear.z == 0 && trans.x == 0 &&
+			   trans.y == 0 && trans.z == 0 && rot.w == 1;
+	}
+};
+
+inline float hypot3( V3 a )
+{
+	const float x = fabsf( a.x ), y = fabsf( a.y ), z = fabsf( a.z );
+	const float d = x < y ? ( y < z ? z : y ) : ( x < z ? z : x );
+	return d != 0.0f ? d * sqrtf( ( x / d ) * ( x / d ) + ( y / d ) * ( y / d ) + ( z / d ) * ( z / d ) ) : 0.0f;
+}
+inline Quat qmul( Quat a, Quat b )
+{
+	const V3 av = mk( a.x, a.y, a.z ), bv = mk( b.x, b.y, b.z );
+	const V3 c	= cross( av, bv ) + bv * a.w + av * b.w;
+	return Quat{ c.x, c.y, c.z, a.w * b.w - dot( av, bv ) };
+}
+inline V3 qrotate( Quat q, V3 p )
+{
+	const Quat r = qmul( qmul( q, Quat{ p.x, p.y, p.z, 0 } ), Quat{ -q.x, -q.y, -q.z, q.w } );
+	return mk( r.x, r.y, r.z );
+}
+inline Quat qFromAxisAngle( const float aa[4] )
+{
+	if ( aa[3] == 0.0f ) return Quat{ 0, 0, 0, 1 };
+	const V3	axis = mk( aa[0], aa[1], aa[2] );
+	const float len	 = hypot3( axis );
+	const float s	 = sinf( aa[3] / 2.0f );
+	return Quat{ axis.x / len * s, axis.y / len * s, axis.z / len * s, cosf( aa[3] / 2.0f ) };
+}
+inline Quat qFromMatrix( const float R[3][3] )
+{
+	const float tr = R[0][0] + R[1][1] + R[2][2];
+	if ( tr > 0.0f )
+	{
+		const float S = sqrtf( tr + 1.0f ) * 2.0f;
+		return Quat{ ( R[2][1] - R[1][2] ) / S, ( R[0][2] - R[2][0] ) / S, ( R[1][0] - R[0][1] ) / S, 0.25f * S };
+	}
+	if ( R[0][0] > R[1][1] && R[0][0] > R[2][2] )
+	{
+		const float S = sqrtf( 1.0f + R[0][0] - R[1][1] - R[2][2] ) * 2.0f;
+		return Quat{ 0.25f * S, ( R[0][1] + R[1][0] ) / S, ( R[0][2] + R[2][0] ) / S, ( R[2][1] - R[1][2] ) / S };
+	}
+	if ( R[1][1] > R[2][2] )
+	{
+		const float S = sqrtf( 1.0f + R[1][1] - R[0][0] - R[2][2] ) * 2.0f;
+		return Quat{ ( R[0][1] + R[1][0] ) / S, 0.25f * S, ( R[1][2] + R[2][1] ) / S, ( R[0][2] - R[2][0] ) / S };
+	}
+	const float S = sqrtf( 1.0f + R[2][2] - R[0][0] - R[1][1] ) * 2.0f;
+	return Quat{ ( R[0][2] + R[2][0] ) / S, ( R[1][2] + R[2][1] ) / S, 0.25f * S, ( R[1][0] - R[0][1] ) / S };
+}
+inline void qToMatrix( Quat q, float R[3][3] )
+{
+	const float x2 = q.x * q.x, y2 = q.y * q.y, z2 = q.z * q.z;
+	R[0][0] = 1.0f - 2.0f * y2 - 2.0f * z2;
+	R[0][1] = 2.0f * q.x * q.y - 2.0f * q.w * q.z;
+	R[0][2] = 2.0f * q.x * q.z + 2.0f * q.w * q.y;
+	R[1][0] = 2.0f * q.x * q.y + 2.0f * q.w * q.z;
+	R[1][1] = 1.0f - 2.0f * x2 - 2.0f * z2;
+	R[1][2] = 2.0f * q.y * q.z - 2.0f * q.w * q.x;
+	R[2][0] = 2.0f * q.x * q.z - 2.0f * q.w * q.y;
+	R[2][1] = 2.0f * q.y * q.z + 2.0f * q.w * q.x;
+	R[2][2] = 1.0f - 2.0f * x2 - 2.0f * y2;
+}
+// modified Gram-Schmidt on columns, det(Q) forced positive
+void qrDecompose( const float A[3][3], float Q[3][3], float R[3][3] )
+{
+	for ( int i = 0; i < 3; ++i )
+		for ( int j = 0; j < 3; ++j )
+			Q[i][j] = A[i][j], R[i][j] = 0.0f;
+	for ( int c = 0; c < 3; ++c )
+	{
+		for ( int p = 0; p < c; ++p )
+		{
+			const float w = Q[0][p] * Q[0][c] + Q[1][p] * Q[1][c] + Q[2][p] * Q[2][c];
+			R[p][c]		  = w;
+			for ( int r = 0; r < 3; ++r )
+				Q[r][c] -= w * Q[r][p];
+		}
+		float w = hypot3( mk( Q[0][c], Q[1][c], Q[2][c] ) );
+		R[c][c] = w;
+		if ( w != 0.0f )
+		{
+			w = 1.0f / w;
+			for ( int r = 0; r < 3; ++r )
+				Q[r][c] *= w;
+		}
+		else
+			Q[0][c] = 1.0f;
+	}
+	const float d = Q[0][0] * Q[1][1] * Q[2][2] + Q[0][1] * Q[1][2] * Q[2][0] + Q[1][0] * Q[2][1] * Q[0][2] - Q[0][2] * Q[1][1] * Q[2][0] -
+					Q[0][1] * Q[1][0] * Q[2][2] - Q[1][2] * Q[2][1] * Q[0][0];
+	if ( d < 0.0f )
+		for ( int k = 0; k < 3; ++k )
+			Q[k][0] = -Q[k][0], R[0][k] = -R[0][k];
+}
+
+Frame frameFromMatrix( const float* m16 ) // hiprtFrameMatrix: 3x4 row-major + time
+{
+	const float( *m )[4] = reinterpret_cast<const float( * )[4]>( m16 );
+	Frame f;
+	const bool ident = m[0][0] == 1 && m[1][1] == 1 && m[2][2] == 1 && m[0][1] == 0 && m[0][2] == 0 && m[0][3] == 0 && m[1][0] == 0 &&
+					   m[1][2] == 0 && m[1][3] == 0 && m[2][0] == 0 && m[2][1] == 0 && m[2][3] == 0;
+	if ( !ident )
+	{
+		float A[3][3], Q[3][3], R[3][3];
+		for ( int i = 0; i < 3; ++i )
+			for ( int j = 0; j < 3; ++j )
+				A[i][j] = m[i][j];
+		qrDecompose( A, Q, R );
+		f.trans = mk( m[0][3], m[1][3], m[2][3] );
+		f.rot	= qFromMatrix( Q );
+		f.scale = mk( R[0][0], R[1][1], R[2][2] );
+		f.shear = mk( R[0][1], R[0][2], R[1][2] );
+	}
+	f.time = m16[12];
+	return f;
+}
+
+Frame frameFromSRT( const float* s12 ) // hiprtFrameSRT: rotation(4) scale(3) translation(3) time + pad
+{
+	Frame f;
+	f.rot	= qFromAxisAngle( s12 );
+	f.scale = mk( s12[4], s12[5], s12[6] );
+	f.trans = mk( s12[7], s12[8], s12[9] );
+	f.time	= s12[10];
+	return f;
+}
+
+V3 frameTransform( const Frame& f, V3 p )
+{
+	if ( f.identity() ) return p;
+	V3 r = p * f.scale;
+	r	 = r + mk( p.y * f.shear.x + p.z * f.shear.y, p.z * f.shear.z, 0.0f );
+	r	 = qrotate( f.rot, r );
+	return r + f.trans;
+}
+
+void frameInverseMatrix( const Frame& f, float out[3][4] )
+{
+	float Q[3][3];
+	qToMatrix( f.rot, Q );
+	float Ri[3][3] = {};
+	Ri[0][0]	   = 1.0f / f.scale.x;
+	Ri[1][1]	   = 1.0f / f.scale.y;
+	Ri[2][2]	   = 1.0f / f.scale.z;
+	Ri[0][1]	   = -f.shear.x / ( f.scale.x * f.scale.y );
+	Ri[0][2]	   = ( f.shear.x * f.shear.z - f.shear.y * f.scale.y ) / ( f.scale.x * f.scale.y * f.scale.z );
+	Ri[1][2]	   = -f.shear.z / ( f.scale.y * f.scale.z );
+	for ( int i = 0; i < 3; ++i )
+	{
+		for ( int j = 0; j < 3; ++j )
+			out[i][j] = dot( mk( Ri[i][0], Ri[i][1], Ri[i][2] ), mk( Q[j][0], Q[j][1], Q[j][2] ) );
+		out[i][3] = -dot( mk( out[i][0], out[i][1], out[i][2] ), f.trans );
+	}
+}
+
+struct SceneObj
+{
+	uint32_t				  count = 0;
+	std::vector<Geometry*>	  geoms; // per instance
+	std::vector<Frame>		  frames;
+	std::vector<uint32_t>	  masks;
+	std::vector<Box>		  primBoxes, sortedBoxes;
+	std::vector<uint32_t>	  keys, sortedKeys, sortedVals;
+	std::vector<ScratchNode>  scratch;
+	uint32_t				  root = InvalidValue;
+	Wide					  wide;
+	std::vector<InstanceNode> leaves; // packed order
+	std::vector<uint32_t>	  leafGeom; // geometry slot per packed leaf
+	Box						  sceneBox;
+};
+
+Box instanceBox( const Geometry& g, const Frame& f )
+{
+	const Box4Node& root = g.wide.boxes[0];
+	Box				out	 = emptyBox();
+	for ( uint32_t c = 0; c < root.childCount; ++c )
+	{
+		const Box& b = root.box[c];
+		for ( int k = 0; k < 8; ++k )
+			out = grow( out, frameTransform( f, mk( ( k & 4 ) ? b.hi.x : b.lo.x, ( k & 2 ) ? b.hi.y : b.lo.y, ( k & 1 ) ? b.hi.z : b.lo.z ) ) );
+	}
+	return out;
+}
+
+hiprtRay toObjectSpace( const InstanceNode& n, const hiprtRay& ray )
+{
+	hiprtRay out;
+	const V3 o = ray.origin, d = ray.direction;
+	out.origin = mk( dot( mk( n.invMatrix[0][0], n.invMatrix[0][1], n.invMatrix[0][2] ), o ),
+					 dot( mk( n.invMatrix[1][0], n.invMatrix[1][1], n.invMatrix[1][2] ), o ),
+					 dot( mk( n.invMatrix[2][0], n.invMatrix[2][1], n.invMatrix[2][2] ), o ) ) +
+				 mk( n.invMatrix[0][3], n.invMatrix[1][3], n.invMatrix[2][3] );
+	out.direction = mk( dot( mk( n.invMatrix[0][0], n.invMatrix[0][1], n.invMatrix[0][2] ), d ),
+						dot( mk( n.invMatrix[1][0], n.invMatrix[1][1], n.invMatrix[1][2] ), d ),
+						dot( mk( n.invMatrix[2][0], n.invMatrix[2][1], n.invMatrix[2][2] ), d ) );
+	out.minT	  = ray.minT;
+	out.maxT	  = ray.maxT;
+	return out;
+}
+
+// Closest hit through a two-level structure with the order-independent rule min (t, instanceID, primID)
+// (tieMode 1) or the reference's visiting-order rule (tieMode 0).
+hiprtHit traceSceneClosest( const SceneObj& s, const hiprtRay& worldRay, uint32_t rayMask, int tieMode )
+{
+	hiprtRay			  ray  = worldRay;
+	V3					  invD = mk( 1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z );
+	hiprtHit			  best;
+	std::vector<uint32_t> stack;
+	stack.push_back( InvalidValue );
+	uint32_t		node	 = RootIndex;
+	const Geometry* geom	 = nullptr;
+	uint32_t		instance = InvalidValue;
+	auto			pop		 = [&]() {
+		   uint32_t n = stack.back();
+		   stack.pop_back();
+		   while ( n == InvalidValue && !stack.empty() )
+		   {
+			   // leave the instance: world ray again, distance kept
+			   const float maxT = ray.maxT;
+			   ray				= worldRay;
+			   ray.maxT			= maxT;
+			   invD				= mk( 1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z );
+			   geom				= nullptr;
+			   instance			= InvalidValue;
+			   n				= stack.back();
+			   stack.pop_back();
+		   }
+		   return n;
+	};
+	while ( node != InvalidValue )
+	{
+		if ( isBoxIndex( node ) )
+		{
+			const Box4Node* boxes = geom ? geom->wide.boxes.data() : s.wide.boxes.data();
+			uint32_t		res[4];
+			orderChildren( boxes[nodeAddr( node )], ray.origin, invD, ray.maxT, res );
+			for ( int k = 3; k >= 1; --k )
+				if ( res[k] != InvalidValue ) stack.push_back( res[k] );
+			node = res[0] != InvalidValue ? res[0] : pop();
+			continue;
+		}
+		if ( !geom )
+		{
+			const uint32_t		addr = nodeAddr( node );
+			const InstanceNode& in	 = s.leaves[addr];
+			if ( in.mask & rayMask )
+			{
+				const float maxT = ray.maxT;
+				if ( !in.identity ) ray = toObjectSpace( in, ray );
+				ray.maxT = maxT;
+				invD	 = mk( 1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z );
+				geom	 = s.geoms[s.leafGeom[addr]];
+				instance = in.primIndex;
+				stack.push_back( InvalidValue );
+				node = RootIndex;
+				continue;
+			}
+			node = pop();
+			continue;
+		}
+		const TrianglePairNode& leaf = geom->leaves[nodeAddr( node )];
+		hiprtHit				cand[2];
+		bool					ok[2];
+		for ( uint32_t which = 0; which < 2; ++which )
+		{
+			ok[which]				= hitPairTriangle( leaf, which, ray, cand[which] );
+			cand[which].instanceID = instance;
+		}
+		if ( tieMode == 0 )
+		{
+			int pick = ok[0] ? 0 : -1;
+			if ( ok[1] && ( !ok[0] || cand[0].t > cand[1].t ) ) pick = 1;
+			if ( pick >= 0 ) best = cand[pick];
+		}
+		else
+		{
+			for ( uint32_t which = 0; which < 2; ++which )
+			{
+				const hiprtHit& c = cand[which];
+				if ( !ok[which] ) continue;
+				bool better = !best.hasHit() || c.t < best.t;
+				if ( !better && c.t == best.t )
+					better = c.instanceID != best.instanceID ? c.instanceID < best.instanceID : c.primID < best.primID;
+				if ( better ) best = c;
+			}
+		}
+		if ( best.hasHit() ) ray.maxT = best.t;
+		node = pop();
+	}
+	return best;
+}
 } // namespace
 
 // =================================================================================================
@@ -959,6 +1267,126 @@ uint32_t orc_canonicalize(
 	}
 	*leafCountOut = leafCount;
 	return uint32_t( order.size() );
+}
+
+// ---- scenes -------------------------------------------------------------------------------------
+// One frame per instance (frame k belongs to instance k). frameType 0: hiprtFrameSRT (12 floats),
+// 1: hiprtFrameMatrix (16 floats). geometryOfInstance[k] indexes `geometries`.
+void* orc_scene_create(
+	void* const*	geometries,
+	uint32_t		geometryCount,
+	const uint32_t* geometryOfInstance,
+	const float*	frames,
+	int				frameType,
+	const uint32_t* masks,
+	uint32_t		instanceCount )
+{
+	(void)geometryCount;
+	SceneObj* s = new SceneObj;
+	s->count	= instanceCount;
+	s->geoms.resize( instanceCount );
+	s->frames.resize( instanceCount );
+	s->masks.resize( instanceCount );
+	s->primBoxes.resize( instanceCount );
+	for ( uint32_t k = 0; k < instanceCount; ++k )
+	{
+		s->geoms[k]	 = static_cast<Geometry*>( geometries[geometryOfInstance[k]] );
+		s->frames[k] = frames ? ( frameType == 1 ? frameFromMatrix( frames + 16 * size_t( k ) ) : frameFromSRT( frames + 12 * size_t( k ) ) ) : Frame();
+		s->masks[k]	 = masks ? masks[k] : FullRayMask;
+		s->primBoxes[k] = instanceBox( *s->geoms[k], s->frames[k] );
+	}
+	// same LBVH pipeline as geometries, leaves are instances
+	s->sceneBox = emptyBox();
+	for ( uint32_t k = 0; k < instanceCount; ++k )
+		s->sceneBox = unite( s->sceneBox, s->primBoxes[k] );
+	const V3 ext = s->sceneBox.hi - s->sceneBox.lo;
+	s->keys.resize( instanceCount );
+	for ( uint32_t k = 0; k < instanceCount; ++k )
+	{
+		const V3 c = ( s->primBoxes[k].hi + s->primBoxes[k].lo ) * 0.5f;
+		const V3 d = c - s->sceneBox.lo;
+		s->keys[k] = extendedMorton( mk( d.x / ext.x, d.y / ext.y, d.z / ext.z ), ext );
+	}
+	s->sortedVals.resize( instanceCount );
+	std::iota( s->sortedVals.begin(), s->sortedVals.end(), 0u );
+	std::stable_sort( s->sortedVals.begin(), s->sortedVals.end(), [&]( uint32_t a, uint32_t b ) { return s->keys[a] < s->keys[b]; } );
+	s->sortedKeys.resize( instanceCount );
+	s->sortedBoxes.resize( instanceCount );
+	for ( uint32_t k = 0; k < instanceCount; ++k )
+	{
+		s->sortedKeys[k]  = s->keys[s->sortedVals[k]];
+		s->sortedBoxes[k] = s->primBoxes[s->sortedVals[k]];
+	}
+	if ( instanceCount == 1 )
+	{
+		Box4Node node;
+		memset( &node, 0, sizeof( node ) );
+		node.parentAddr = InvalidValue;
+		node.childCount = 1;
+		for ( int k = 0; k < 4; ++k )
+			node.child[k] = InvalidValue, node.box[k] = emptyBox();
+		node.child[0] = makeNodeIndex( 0, InstanceType );
+		node.box[0]	  = s->primBoxes[0];
+		s->wide.boxes.assign( 1, node );
+		s->wide.leafRefs.assign( 1, 0 );
+	}
+	else
+	{
+		s->root = buildTopology( s->sortedKeys.data(), instanceCount, s->sortedBoxes.data(), InstanceType, s->scratch );
+		collapse( s->scratch, s->sortedBoxes.data(), instanceCount, s->root, InstanceType, s->wide );
+	}
+	for ( uint32_t ref : s->wide.leafRefs )
+	{
+		const uint32_t k = instanceCount == 1 ? 0 : s->sortedVals[ref];
+		InstanceNode   n;
+		memset( &n, 0, sizeof( n ) );
+		const bool ident = s->frames[k].identity();
+		float	   m[3][4] = { { 1, 0, 0, 0 }, { 0, 1, 0, 0 }, { 0, 0, 1, 0 } };
+		if ( !ident ) frameInverseMatrix( s->frames[k], m );
+		memcpy( n.invMatrix, m, sizeof( m ) );
+		n.geometry	= nullptr;
+		n.mask		= s->masks[k];
+		n.primIndex = k;
+		n.type		= 0;
+		n.isStatic	= 1;
+		n.identity	= ident ? 1 : 0;
+		s->leaves.push_back( n );
+		s->leafGeom.push_back( k );
+	}
+	return s;
+}
+
+void orc_scene_destroy( void* h ) { delete static_cast<SceneObj*>( h ); }
+
+uint32_t orc_scene_count( void* h, int what )
+{
+	SceneObj& s = *static_cast<SceneObj*>( h );
+	return what == 0 ? s.count : what == 1 ? uint32_t( s.wide.boxes.size() ) : uint32_t( s.leaves.size() );
+}
+
+// what: 0 primBoxes 1 keys 2 boxNodes 3 instance leaves (64 B, geometry pointer zeroed) 4 sortedKeys 5 sortedVals
+void orc_scene_read( void* h, int what, void* out )
+{
+	SceneObj& s	 = *static_cast<SceneObj*>( h );
+	auto	  cp = [&]( const void* p, size_t bytes ) {
+		 if ( bytes ) memcpy( out, p, bytes );
+	};
+	switch ( what )
+	{
+	case 0: cp( s.primBoxes.data(), s.primBoxes.size() * sizeof( Box ) ); break;
+	case 1: cp( s.keys.data(), s.keys.size() * 4 ); break;
+	case 2: cp( s.wide.boxes.data(), s.wide.boxes.size() * sizeof( Box4Node ) ); break;
+	case 3: cp( s.leaves.data(), s.leaves.size() * sizeof( InstanceNode ) ); break;
+	case 4: cp( s.sortedKeys.data(), s.sortedKeys.size() * 4 ); break;
+	case 5: cp( s.sortedVals.data(), s.sortedVals.size() * 4 ); break;
+	}
+}
+
+void orc_scene_trace( void* h, const hiprtRay* rays, uint32_t n, hiprtHit* hits, uint32_t rayMask, int tieMode )
+{
+	SceneObj& s = *static_cast<SceneObj*>( h );
+	for ( uint32_t i = 0; i < n; ++i )
+		hits[i] = traceSceneClosest( s, rays[i], rayMask, tieMode );
 }
 
 } // extern "C"
