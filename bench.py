@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Headline benchmark: BASELINE.json's metric -- Mrays/s (closest-hit primary + any-hit secondary
+rays) and BVH build Mtris/s -- on config C2 (1M-triangle tessellated sphere, PreferFastBuild LBVH,
+1920x1080 primary + shadow rays), one process per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...             # the reference's CPU arm (Embree 4.3
+                                                              # bundled with the reference, all host threads)
+
+A "step" is one frame: every primary ray traced closest-hit plus one shadow ray per hit pixel
+traced any-hit, rays resident in HBM (`value`), or pushed from / pulled back to pinned host
+memory through the C-ABI's host-buffer entry point (`e2e`). The BVH build is timed separately
+over the same number of steps (`build`). Multi-GPU: the BVH is replicated (every rank builds
+it), every rank traces its own frame-sized ray batch (weak scaling), no data-path collective.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 1920, 1080
+WORKLOADS = {
+    # name: (mesh factory, camera eye, look-at, light)
+    "c2_sphere_1M": dict(mesh=("sphere", 1000, 500), eye=(0.0, 0.0, 3.0), look=(0.0, 0.0, 0.0), light=(2.0, 4.0, 3.0), flags="fast"),
+    "c3_terrain_10M": dict(mesh=("terrain", 2236), eye=(0.5, 0.6, -0.6), look=(0.5, 0.0, 0.5), light=(2.0, 4.0, 3.0), flags="fast"),
+    "small_sphere_40k": dict(mesh=("sphere", 200, 100), eye=(0.0, 0.0, 3.0), look=(0.0, 0.0, 0.0), light=(2.0, 4.0, 3.0), flags="fast"),
+}
+METRIC = "Mrays/s (primary closest-hit + shadow any-hit, 1920x1080); build Mtris/s under 'build'"
+BYTES_PER_RAY = 80  # algorithmic HBM traffic of a traced ray: 32 B hiprtRay in + 48 B hiprtHit out
+
+
+def make_mesh(spec):
+    from hiprt_b200 import scenes
+
+    if spec[0] == "sphere":
+        return scenes.sphere_mesh(spec[1], spec[2])
+    if spec[0] == "terrain":
+        return scenes.terrain_mesh(spec[1])
+    raise ValueError(spec)
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, device_index):
+        self.samples, self.reasons, self.proc = [], set(), None
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={device_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            p = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append((float(p[0]), float(p[1])))
+                for n, v in zip(names, p[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples), "reasons": sorted(self.reasons), "samples": len(sm)}
+
+
+def embree_arm(verts, idx, primary, light, steps, warmup, threads):
+    """Reference CPU arm: Embree 4.3 build (LOW = Morton, the counterpart of PreferFastBuild) and
+    rtcIntersect1/rtcOccluded1 over all host threads. Falls back to the single-threaded oracle port."""
+    from hiprt_b200 import scenes
+    from oracle import embree_binding as emb
+
+    if not emb.available():
+        return None
+    build_ms = []
+    for _ in range(max(2, min(steps, 5))):
+        s = emb.EmbreeScene(verts, idx, quality=0, threads=threads)
+        build_ms.append(s.build_ms)
+        s.release()
+    scene = emb.EmbreeScene(verts, idx, quality=0, threads=threads)
+    hits, _ = scene.trace(primary, kind=2)
+    shadow, _ = scenes.shadow_rays(primary, hits, light)
+    times = []
+    for it in range(warmup + steps):
+        _, ms_p = scene.trace(primary, kind=2, want_hits=False)
+        _, ms_s = scene.trace(shadow, kind=1, want_hits=False)
+        if it >= warmup:
+            times.append(ms_p + ms_s)
+    n_rays = len(primary) + len(shadow)
+    ms = float(np.mean(times))
+    return {"mrays": n_rays / ms / 1e3, "ms": ms, "rays": n_rays, "build_ms": float(min(build_ms[1:])),
+            "build_mtris": len(idx) / float(min(build_ms[1:])) / 1e3, "hits": hits}
+
+
+def oracle_port_arm(verts, idx, primary, sample=65536):
+    from oracle import binding as orc
+
+    t0 = time.perf_counter()
+    g = orc.Geometry(verts, idx)
+    build_s = time.perf_counter() - t0
+    step = max(1, len(primary) // sample)
+    rays = primary[::step]
+    t0 = time.perf_counter()
+    g.trace(rays, tie_mode=1)
+    trace_s = time.perf_counter() - t0
+    return {"mrays": len(rays) / trace_s / 1e6, "rays": len(rays), "build_mtris": len(idx) / build_s / 1e6}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_sphere_1M", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-hiprt-reference", action="store_true", help="also time the reference's own GPU kernels (oracle/_ref)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    wl = WORKLOADS[args.workload]
+    host_threads = os.cpu_count() or 1
+
+    from hiprt_b200 import scenes
+
+    verts, idx = make_mesh(wl["mesh"])
+    n_tris = len(idx)
+
+    # ------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        primary = scenes.pinhole_rays(WIDTH, HEIGHT, wl["eye"], wl["look"])
+        r = embree_arm(verts, idx, primary, wl["light"], args.steps, args.warmup, host_threads)
+        kind = "reference"
+        if r is None:
+            r = oracle_port_arm(verts, idx, primary)
+            r["ms"] = r["rays"] / r["mrays"] / 1e3
+            kind, host_threads_used, sample = "port", 1, f"{r['rays']} primary rays (every k-th pixel), single thread"
+        else:
+            host_threads_used, sample = host_threads, f"full frame: {r['rays']} rays/step (primary + shadow), {args.steps} steps; build = best of 4 x rtcCommitScene(LOW)"
+        line = {
+            "impl": "reference", "metric": METRIC, "value": round(r["mrays"], 3), "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(r["ms"], 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "triangles": n_tris, "rays_per_step": r["rays"], "resolution": [WIDTH, HEIGHT],
+                       "engine": "Embree 4.3.0 (contrib/embree of the reference), build quality LOW" if kind == "reference" else "oracle port"},
+            "build": {"mtris_per_s": round(r["build_mtris"], 3)},
+            "cpu_baseline": {"value": round(r["mrays"], 3), "unit": "Mrays/s", "cores": host_threads_used, "kind": kind, "sample": sample},
+            "e2e": {"value": round(r["mrays"], 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------
+    import torch
+
+    from hiprt_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    ctx = api.Context(local_rank)
+    dev = ctx.device
+    flags = api.FAST_BUILD
+
+    d_verts = torch.from_numpy(verts).to(dev)
+    d_idx = torch.from_numpy(idx.view(np.int32)).to(dev)
+    inp = ctx.mesh_input(d_verts, d_idx)
+    temp = ctx.alloc_temp(ctx.geometry_temp_size(inp, flags))
+    geom_h = ctx.create_geometry(inp, flags)
+    ctx.build_geometry(inp, geom_h, temp, flags)
+    geom = api.Geometry(ctx, geom_h, inp, temp, flags)
+    torch.cuda.synchronize()
+
+    # every rank traces its own frame (weak scaling): the camera is nudged per rank
+    eye = np.array(wl["eye"], np.float64) + np.array([0.01 * rank, 0.005 * rank, 0.0])
+    primary = scenes.pinhole_rays(WIDTH, HEIGHT, eye, wl["look"])
+    d_primary = ctx.rays_to_device(primary)
+    hits0 = ctx.hits_to_host(ctx.trace(geom, d_primary))
+    shadow, _ = scenes.shadow_rays(primary, hits0, wl["light"])
+    d_shadow = ctx.rays_to_device(shadow)
+    n_primary, n_shadow = len(primary), len(shadow)
+    n_rays = n_primary + n_shadow
+    d_hits_p = torch.empty((n_primary, 12), dtype=torch.int32, device=dev)
+    d_hits_s = torch.empty((n_shadow, 12), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 256 MiB > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        ctx.trace(geom, d_primary, d_hits_p, api.CLOSEST_HIT)
+        ctx.trace(geom, d_shadow, d_hits_s, api.ANY_HIT)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    t_wall0 = time.perf_counter()
+    step_ms, prim_ms = [], []
+    for _ in range(args.steps):
+        flush.fill_(1)  # cold L2 for every step
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        ctx.trace(geom, d_primary, d_hits_p, api.CLOSEST_HIT)
+        e1.record()
+        ctx.trace(geom, d_shadow, d_hits_s, api.ANY_HIT)
+        e2.record()
+        e2.synchronize()
+        prim_ms.append(e0.elapsed_time(e1))
+        step_ms.append(e0.elapsed_time(e2))
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    total_ms = float(np.sum(step_ms))
+
+    # ---- build: K full builds of the same mesh (includes every internal launch, excludes allocation)
+    ctx.enable_build_profile(True)
+    build_ms, phases = [], {}
+    for it in range(args.warmup + args.steps):
+        flush.fill_(1)
+        e0, e1 = ev(), ev()
+        e0.record()
+        ctx.build_geometry(inp, geom_h, temp, flags)
+        e1.record()
+        e1.synchronize()
+        if it >= args.warmup:
+            build_ms.append(e0.elapsed_time(e1))
+            for name, ms in ctx.build_profile():
+                phases.setdefault(name, []).append(ms)
+    ctx.enable_build_profile(False)
+    clocks = sampler.stop()
+    build_total_ms = float(np.sum(build_ms))
+
+    # ---- end to end through the C-ABI with host buffers (pinned), H2D + D2H inside the timed region
+    pin = lambda a: torch.from_numpy(a.view(np.uint8).reshape(-1)).pin_memory().numpy().view(a.dtype)
+    h_primary, h_shadow = pin(primary), pin(shadow)
+    h_hits_p = pin(np.zeros(n_primary, api.HIT_DTYPE))
+    h_hits_s = pin(np.zeros(n_shadow, api.HIT_DTYPE))
+    e2e_ms = []
+    for it in range(3 + args.steps):
+        t0 = time.perf_counter()
+        ctx.trace_host(geom, h_primary, h_hits_p, api.CLOSEST_HIT)
+        ctx.trace_host(geom, h_shadow, h_hits_s, api.ANY_HIT)
+        if it >= 3:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    assert np.array_equal(h_hits_p["primID"], hits0["primID"]), "host-buffer path disagrees with the device path"
+    e2e_total_ms = float(np.sum(e2e_ms))
+
+    # ---- max over ranks
+    if world > 1:
+        t = torch.tensor([total_ms, build_total_ms, e2e_total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, build_total_ms, e2e_total_ms = [float(x) for x in t.tolist()]
+        cnt = torch.tensor([n_rays], dtype=torch.float64, device=dev)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        rays_all = float(cnt.item())
+    else:
+        rays_all = float(n_rays)
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        ms_per_step = total_ms / args.steps
+        value = rays_all * args.steps / total_ms / 1e3  # Mrays/s, whole job
+        prim_ms_avg = float(np.mean(prim_ms))
+        achieved = n_primary * BYTES_PER_RAY / (prim_ms_avg * 1e-3) / 1e9
+        build_ms_avg = build_total_ms / args.steps
+        # build passes against the HBM roofline: algorithmic bytes per primitive pair
+        n_prims = int(geom.header()["primNodeCount"])
+        algo = {"pair": 32 * n_prims, "boxes": 96 * n_prims, "morton+histogram": 32 * n_prims, "sort": 64 * n_prims,
+                "emit+refit": 128 * n_prims, "collapse+pack": (123 + 152) * n_prims}
+        build_roofline = {}
+        for name, v in phases.items():
+            ms = float(np.mean(v))
+            gbs = algo.get(name, 0) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            build_roofline[name] = {"ms": round(ms, 4), "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "triangles": n_tris, "primitives_after_pairing": n_prims, "build": "PreferFastBuild (LBVH)",
+                       "resolution": [WIDTH, HEIGHT], "rays_per_step_per_gpu": n_rays, "primary_rays": n_primary, "shadow_rays": n_shadow,
+                       "l2": "256 MiB flush write before every timed step", "bvh": "replicated per GPU", "sharding": "one frame-sized ray batch per GPU"},
+            "build": {"mtris_per_s": round(n_tris * world * args.steps / build_total_ms / 1e3, 2), "ms_per_build": round(build_ms_avg, 4),
+                      "bytes_per_triangle_model": round(sum(algo.values()) / n_tris, 1),
+                      "achieved_gbs": round(sum(algo.values()) / (build_ms_avg * 1e-3) / 1e9, 1),
+                      "frac_of_hbm_peak": round(sum(algo.values()) / (build_ms_avg * 1e-3) / 1e9 / peak, 4), "phases": build_roofline},
+            "roofline": {"kernel": "traceGeometryKernel<closest> (primary rays)", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                         "note": "80 B/ray compulsory I/O; traversal is L2/latency bound, see DESIGN.md and profiles/"},
+            "e2e": {"value": round(rays_all * args.steps / e2e_total_ms / 1e3, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n_rays,
+                    "d2h_bytes_per_step": 48 * n_rays, "api": "hiprtB200TraceGeometryHost (pinned host buffers)"},
+            "gpu_launches": args.steps * 2 + args.steps * (10 if n_prims != n_tris else 9),
+            "clocks": clocks,
+            "wall_s_timed_region": round(wall_s, 3),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = embree_arm(verts, idx, primary, wl["light"], min(args.steps, 10), 2, host_threads)
+            if r is not None:
+                line["cpu_baseline"] = {"value": round(r["mrays"], 3), "unit": "Mrays/s", "cores": host_threads, "kind": "reference",
+                                        "sample": f"full frame ({r['rays']} rays/step) x {min(args.steps, 10)} steps on Embree 4.3 bundled with the reference",
+                                        "build_mtris_per_s": round(r["build_mtris"], 3)}
+                # cross-check against Embree: same primitive away from ties
+                agree = float((r["hits"]["primID"] == hits0["primID"]).mean())
+                line["cpu_baseline"]["primID_agreement_with_gpu"] = round(agree, 6)
+            else:
+                r = oracle_port_arm(verts, idx, primary)
+                line["cpu_baseline"] = {"value": round(r["mrays"], 4), "unit": "Mrays/s", "cores": 1, "kind": "port",
+                                        "sample": f"{r['rays']} primary rays (every k-th pixel) through the oracle", "build_mtris_per_s": round(r["build_mtris"], 4)}
+        if world == 1 and args.with_hiprt_reference:
+            try:
+                from oracle import ref_binding as ref
+
+                rg = ref.RefGeometry(verts, idx, build_flags=0, reps=6)
+                _, ms_p = rg.trace(primary, kind=2, reps=6)
+                _, ms_s = rg.trace(shadow, kind=1, reps=6)
+                line["hiprt_reference_gpu"] = {"mrays_per_s": round(n_rays / (ms_p + ms_s) / 1e3, 2), "build_mtris_per_s": round(n_tris / rg.build_ms / 1e3, 2),
+                                               "build_ms": round(rg.build_ms, 4), "note": "unmodified HIPRT v3.1.0 kernels via Orochi/CUDA on this GPU (oracle/_ref)"}
+            except Exception as e:  # the reference is optional infrastructure
+                line["hiprt_reference_gpu"] = {"unavailable": str(e)[:200]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

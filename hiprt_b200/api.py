@@ -168,6 +168,8 @@ SIGNATURES = {
     "hiprtB200GetDeviceHeaders": [_P(_P(C.c_char_p)), _P(_P(C.c_char_p))],
     "hiprtB200GetLastErrorString": [_vp],
     "hiprtB200CopyToHost": [_vp, _vp, _vp, _sz],
+    "hiprtB200EnableBuildProfile": [_vp, C.c_int],
+    "hiprtB200GetBuildProfile": [_vp, _P(_u32), _P(C.c_char_p), _P(C.c_float), _u32],
 }
 HIPRT_API_FUNCTIONS = [n for n in SIGNATURES if not n.startswith("hiprtB200")]
 
@@ -297,6 +299,17 @@ class Context:
 
     def destroy_geometry(self, geom):
         self._check(lib().hiprtDestroyGeometry(self.h, geom), "hiprtDestroyGeometry")
+
+    def enable_build_profile(self, on=True):
+        self._check(lib().hiprtB200EnableBuildProfile(self.h, int(on)), "hiprtB200EnableBuildProfile")
+
+    def build_profile(self):
+        """[(phase name, milliseconds)] of the most recent build (needs enable_build_profile)."""
+        n = C.c_uint32()
+        names = (C.c_char_p * 20)()
+        ms = (C.c_float * 20)()
+        self._check(lib().hiprtB200GetBuildProfile(self.h, C.byref(n), names, ms, 20), "hiprtB200GetBuildProfile")
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
 
     def alloc_temp(self, nbytes):
         return self.torch.empty(max(int(nbytes), 64), dtype=self.torch.uint8, device=self.device)

@@ -50,7 +50,28 @@ class Context
 		m_info.smCount	 = uint32_t( prop.multiProcessorCount );
 		m_maxThreadsPerSm = uint32_t( prop.maxThreadsPerMultiProcessor > 0 ? prop.maxThreadsPerMultiProcessor : 2048 );
 		m_ccMajor = prop.major, m_ccMinor = prop.minor;
+		m_info.profile = &m_profile;
 	}
+
+	~Context()
+	{
+		if ( m_profileEventsCreated )
+			for ( auto& e : m_profile.events )
+				cudaEventDestroy( e );
+	}
+
+	void enableProfile( bool on )
+	{
+		if ( on && !m_profileEventsCreated )
+		{
+			for ( auto& e : m_profile.events )
+				checkCuda( cudaEventCreate( &e ), "cudaEventCreate" );
+			m_profileEventsCreated = true;
+		}
+		m_profile.enabled = on;
+		m_profile.count	  = 0;
+	}
+	BuildProfile& profile() { return m_profile; }
 
 	// Make the context's device current on the calling thread (builds may come from many host
 	// threads, each with its own stream: reference test/hiprtTest.cpp:1226-1352).
@@ -136,6 +157,8 @@ class Context
 		uint32_t members;
 	};
 	DeviceInfo			  m_info;
+	BuildProfile		  m_profile;
+	bool				  m_profileEventsCreated = false;
 	void*				  m_userCtx			= nullptr;
 	uint32_t			  m_maxThreadsPerSm = 2048;
 	int					  m_ccMajor = 10, m_ccMinor = 0;
@@ -825,6 +848,33 @@ hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount,
 uint32_t hiprtB200GetDeviceHeaders( const char*** namesOut, const char*** sourcesOut ) { return compiler::deviceHeaders( namesOut, sourcesOut ); }
 
 const char* hiprtB200GetLastErrorString( hiprtContext context ) { return context ? ctx( context )->lastError() : ""; }
+
+hiprtError hiprtB200EnableBuildProfile( hiprtContext context, int enable )
+{
+	if ( !context ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] { ctx( context )->enableProfile( enable != 0 ); } );
+}
+
+hiprtError hiprtB200GetBuildProfile( hiprtContext context, uint32_t* phaseCountOut, const char** phaseNamesOut, float* phaseMsOut, uint32_t maxPhases )
+{
+	if ( !context || !phaseCountOut ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		BuildProfile& p = ctx( context )->profile();
+		uint32_t	  n = 0;
+		if ( p.count > 1 )
+		{
+			checkCuda( cudaEventSynchronize( p.events[p.count - 1] ), "cudaEventSynchronize" );
+			for ( int i = 1; i < p.count && n < maxPhases; ++i, ++n )
+			{
+				float ms = 0.0f;
+				checkCuda( cudaEventElapsedTime( &ms, p.events[i - 1], p.events[i] ), "cudaEventElapsedTime" );
+				if ( phaseNamesOut ) phaseNamesOut[n] = p.names[i];
+				if ( phaseMsOut ) phaseMsOut[n] = ms;
+			}
+		}
+		*phaseCountOut = n;
+	} );
+}
 
 hiprtError hiprtB200CopyToHost( hiprtContext context, void* hostDst, const void* deviceSrc, size_t bytes )
 {

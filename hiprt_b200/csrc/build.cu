@@ -95,6 +95,7 @@ static void runLbvh(
 	const uint32_t streamGrid = std::min<uint32_t>( DivideRoundUp( nMax, 256u ), dev.smCount * 8 );
 	HIPRT_CUDA_CHECK( cudaMemsetAsync( sortScr, 0, rsort::scratchWords( nMax ) * 4, stream ) );
 	mortonKernel<<<streamGrid, 256, 0, stream>>>( ctl, primRefs, keys[0], vals[0], sortScr );
+	dev.mark( "morton+histogram", stream );
 
 	const uint32_t tiles = rsort::tileCount( nMax );
 	for ( int pass = 0; pass < rsort::Passes; ++pass )
@@ -104,17 +105,20 @@ static void runLbvh(
 			keys[in], vals[in], keys[out], vals[out], &ctl->primCount, nMax, sortScr, pass );
 	}
 	static_assert( rsort::Passes % 2 == 0, "sorted pairs must end up in buffer 0" );
+	dev.mark( "sort", stream );
 
 	// keys[1]/vals[1] are dead now: they become the collapse task queue
 	HIPRT_CUDA_CHECK( cudaMemsetAsync( taskQueue, 0xFF, size_t( maxBox ) * 8, stream ) );
 	HIPRT_CUDA_CHECK( cudaMemsetAsync( flags, 0xFF, size_t( nMax ) * 4, stream ) );
 	emitTopologyKernel<Source::LeafType><<<DivideRoundUp( nMax, 256u ), 256, 0, stream>>>(
 		ctl, keys[0], vals[0], primRefs, sortedRefs, scratch, flags, taskQueue );
+	dev.mark( "emit+refit", stream );
 
 	const uint32_t warpsNeeded = DivideRoundUp( maxBox, 8u );
 	const uint32_t blocks	   = std::max( 1u, std::min( DivideRoundUp( warpsNeeded, CollapseBlock / 32 ), dev.smCount * 16 ) );
 	collapsePackKernel<Source><<<blocks, CollapseBlock, 0, stream>>>(
 		src, ctl, boxNodeCounter, primNodeCounter, scratch, sortedRefs, taskQueue, maxBox, boxNodes, leafNodes );
+	dev.mark( "collapse+pack", stream );
 	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
 
@@ -135,6 +139,7 @@ void buildGeometry(
 
 	const bool	   isMesh	= input.type == hiprtPrimitiveTypeTriangleMesh;
 	const uint32_t geomType = ( input.geomType << 1 ) | ( isMesh ? 1u : 0u );
+	dev.beginProfile( stream );
 	initGeometryKernel<<<1, 1, 0, stream>>>( ctl, header, boxNodes, leafNodes, geometryStorageSize( input ), nMax, geomType );
 
 	const uint32_t streamGrid = std::min<uint32_t>( DivideRoundUp( nMax, 256u ), dev.smCount * 8 );
@@ -161,8 +166,10 @@ void buildGeometry(
 			HIPRT_CUDA_CHECK( cudaMemsetAsync( scan, 0, size_t( tiles ) * 4, stream ) );
 			pairTrianglesKernel<<<tiles, PairBlock, 0, stream>>>( src, nMax, pairs, scan, ctl );
 			src.pairs = pairs;
+			dev.mark( "pair", stream );
 		}
 		primBoxesKernel<TriangleMeshSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
+		dev.mark( "boxes", stream );
 		runLbvh( dev, src, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
 	}
 	else

@@ -8,10 +8,37 @@
 
 namespace hiprt
 {
+// Optional per-phase timing of a build (the reference has a compile-time Timer around every
+// phase, hiprt/impl/Timer.h:41, LbvhBuilder.h:411-429). Events are recorded on the build stream,
+// nothing synchronises until the profile is read.
+struct BuildProfile
+{
+	static constexpr int MaxMarks = 20;
+	cudaEvent_t			 events[MaxMarks];
+	const char*			 names[MaxMarks]; // names[i] = phase that ENDS at events[i]; events[0] is the start
+	int					 count	 = 0;
+	bool				 enabled = false;
+};
+
 struct DeviceInfo
 {
-	int		 device	 = 0;
-	uint32_t smCount = 148;
+	int			  device  = 0;
+	uint32_t	  smCount = 148;
+	BuildProfile* profile = nullptr;
+
+	void mark( const char* phaseJustFinished, cudaStream_t stream ) const
+	{
+		if ( !profile || !profile->enabled || profile->count >= BuildProfile::MaxMarks ) return;
+		profile->names[profile->count] = phaseJustFinished;
+		cudaEventRecord( profile->events[profile->count], stream );
+		++profile->count;
+	}
+	void beginProfile( cudaStream_t stream ) const
+	{
+		if ( !profile || !profile->enabled ) return;
+		profile->count = 0;
+		mark( "start", stream );
+	}
 };
 
 // ---- sizes -------------------------------------------------------------------------------------

@@ -65,6 +65,12 @@ HIPRT_API uint32_t hiprtB200GetDeviceHeaders( const char*** namesOut, const char
 
 HIPRT_API const char* hiprtB200GetLastErrorString( hiprtContext context );
 
+// Per-phase timing of the most recent build on this context (CUDA events on the build stream;
+// the reference's counterpart is its compile-time Timer, hiprt/impl/Timer.h:41).
+HIPRT_API hiprtError hiprtB200EnableBuildProfile( hiprtContext context, int enable );
+HIPRT_API hiprtError hiprtB200GetBuildProfile(
+	hiprtContext context, uint32_t* phaseCountOut, const char** phaseNamesOut, float* phaseMsOut, uint32_t maxPhases );
+
 // Synchronous device-to-host copy of raw bytes (lets bindings without a CUDA runtime of their
 // own inspect built structures through the handle).
 HIPRT_API hiprtError hiprtB200CopyToHost( hiprtContext context, void* hostDst, const void* deviceSrc, size_t bytes );
