@@ -92,6 +92,10 @@ class SceneBuildInput(C.Structure):
                 ("frameCount", C.c_uint32), ("frameType", C.c_int), ("_pad", C.c_uint8 * 12)]
 
 
+class Instance(C.Structure):
+    _fields_ = [("type", C.c_uint32), ("_pad", C.c_uint32), ("pointer", C.c_void_p)]
+
+
 class FuncDataSet(C.Structure):
     _fields_ = [("intersectFuncData", C.c_void_p), ("filterFuncData", C.c_void_p)]
 
@@ -322,6 +326,54 @@ class Context:
         self.build_geometry(inp, g, temp, flags)
         return Geometry(self, g, inp, temp, flags)
 
+    # ---- scenes -------------------------------------------------------------------------------
+    def build_scene(self, instance_handles, frames=None, frame_type=FRAME_MATRIX, masks=None, flags=FAST_BUILD,
+                    instance_types=None, transform_headers=None, stream=None):
+        """Create + build a scene. instance_handles: device handles (Geometry/Scene wrappers or raw pointers), one per
+        instance; frames: host float32 [F,16] (hiprtFrameMatrix) or [F,12] (hiprtFrameSRT), frame k -> instance k unless
+        transform_headers (uint32 [I,2] = frameIndex, frameCount) is given; masks: uint32 [I]."""
+        t = self.torch
+        n = len(instance_handles)
+        inst = np.zeros(n, np.dtype([("type", "<u4"), ("_pad", "<u4"), ("pointer", "<u8")]))
+        for k, h in enumerate(instance_handles):
+            h = h.h if hasattr(h, "h") else h
+            inst["pointer"][k] = int(h.value if hasattr(h, "value") else h)
+        if instance_types is not None:
+            inst["type"] = np.asarray(instance_types, np.uint32)
+        d_inst = t.from_numpy(inst.view(np.uint8).reshape(-1)).to(self.device)
+        inp = SceneBuildInput()
+        inp.instances = d_inst.data_ptr()
+        inp.instanceCount = n
+        keep = [d_inst]
+        if frames is not None:
+            f = np.ascontiguousarray(frames, np.float32).reshape(-1, 16 if frame_type == FRAME_MATRIX else 12)
+            d_frames = t.from_numpy(f).to(self.device)
+            inp.instanceFrames = d_frames.data_ptr()
+            inp.frameCount = len(f)
+            keep.append(d_frames)
+        inp.frameType = frame_type
+        if masks is not None:
+            d_masks = t.from_numpy(np.ascontiguousarray(masks, np.uint32).view(np.int32)).to(self.device)
+            inp.instanceMasks = d_masks.data_ptr()
+            keep.append(d_masks)
+        if transform_headers is not None:
+            d_hdr = t.from_numpy(np.ascontiguousarray(transform_headers, np.uint32).view(np.int32)).to(self.device)
+            inp.instanceTransformHeaders = d_hdr.data_ptr()
+            keep.append(d_hdr)
+        opts = BuildOptions(flags, 0)
+        sz = C.c_size_t()
+        self._check(lib().hiprtGetSceneBuildTemporaryBufferSize(self.h, C.byref(inp), opts, C.byref(sz)), "hiprtGetSceneBuildTemporaryBufferSize")
+        temp = self.alloc_temp(sz.value)
+        s = C.c_void_p()
+        self._check(lib().hiprtCreateScene(self.h, C.byref(inp), opts, C.byref(s)), "hiprtCreateScene")
+        self._check(lib().hiprtBuildScene(self.h, BUILD, C.byref(inp), opts, _ptr(temp), _stream_handle(stream), s), "hiprtBuildScene")
+        keep.append(list(instance_handles))
+        return Scene(self, s, keep, inp, temp, flags)
+
+    def rebuild_scene(self, scene, op=BUILD, stream=None):
+        self._check(lib().hiprtBuildScene(self.h, op, C.byref(scene.inp), BuildOptions(scene.flags, 0), _ptr(scene.temp),
+                                          _stream_handle(stream), scene.h), "hiprtBuildScene")
+
     # ---- tracing ------------------------------------------------------------------------------
     def trace(self, geom_or_scene, rays, hits=None, kind=CLOSEST_HIT, mask=0xFFFFFFFF, stream=None):
         """rays: uint8/float32 device tensor holding hiprtRay[n]; returns device tensor of hiprtHit[n] (as [n,12] int32)."""
@@ -409,5 +461,21 @@ class Geometry:
 
 
 class Scene:
-    def __init__(self, ctx, handle, keep):
-        self.ctx, self.h, self.keep = ctx, handle, keep
+    def __init__(self, ctx, handle, keep, inp=None, temp=None, flags=FAST_BUILD):
+        self.ctx, self.h, self.keep, self.inp, self.temp, self.flags = ctx, handle, keep, inp, temp, flags
+
+    def header(self):
+        self.ctx.torch.cuda.synchronize()
+        return self.ctx.read_device(self.h.value, 64).view(SCENE_HEADER_DTYPE)[0]
+
+    def nodes(self):
+        """(box nodes, instance leaves) copied to the host."""
+        h = self.header()
+        boxes = self.ctx.read_device(h["boxNodes"], int(h["boxNodeCount"]) * 128).view(BOX4_DTYPE)
+        leaves = self.ctx.read_device(h["primNodes"], int(h["primNodeCount"]) * 64).view(INSTANCE_NODE_DTYPE)
+        return boxes, leaves
+
+    def destroy(self):
+        if self.h is not None:
+            self.ctx._check(lib().hiprtDestroyScene(self.ctx.h, self.h), "hiprtDestroyScene")
+            self.h = None

@@ -26,6 +26,7 @@ TempLayout tempLayout( size_t n, size_t pairTriangles )
 	L.sortedRefs  = take( n * 32 );
 	L.scratch	  = take( n * 32 );
 	L.flags		  = take( n * 4 );
+	L.clusterIds  = take( n * 4 ); // balanced builder only
 	L.taskQueue	  = L.keys[1]; // 8 B x maxBox(n) <= 8 B x n: reuses the second key/value buffer
 	L.total		  = off;
 	return L;
@@ -43,6 +44,14 @@ size_t geometryPrimCount( const hiprtGeometryBuildInput& input )
 	}
 	if ( input.type == hiprtPrimitiveTypeAABBList ) return input.primitive.aabbList.aabbCount;
 	throw std::runtime_error( "unsupported primitive type" );
+}
+
+// PreferBalancedBuild -> H-PLOC; PreferHighQualityBuild is served by the same builder (the SBVH
+// builder is out of scope: SURVEY.md section 2 row 14); anything else -> LBVH (Context.cpp:174-198).
+static bool usesBalancedBuilder( hiprtBuildOptions options )
+{
+	const uint32_t kind = options.buildFlags & 3u;
+	return kind == hiprtBuildFlagBitPreferBalancedBuild || kind == hiprtBuildFlagBitPreferHighQualityBuild;
 }
 
 static bool wantsPairing( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
@@ -72,6 +81,7 @@ template <typename Source>
 static void runLbvh(
 	const DeviceInfo& dev,
 	Source			  src,
+	bool			  balanced,
 	uint32_t		  nMax,
 	uint8_t*		  temp,
 	const TempLayout& L,
@@ -110,9 +120,19 @@ static void runLbvh(
 	// keys[1]/vals[1] are dead now: they become the collapse task queue
 	HIPRT_CUDA_CHECK( cudaMemsetAsync( taskQueue, 0xFF, size_t( maxBox ) * 8, stream ) );
 	HIPRT_CUDA_CHECK( cudaMemsetAsync( flags, 0xFF, size_t( nMax ) * 4, stream ) );
-	emitTopologyKernel<Source::LeafType><<<DivideRoundUp( nMax, 256u ), 256, 0, stream>>>(
-		ctl, keys[0], vals[0], primRefs, sortedRefs, scratch, flags, taskQueue );
-	dev.mark( "emit+refit", stream );
+	if ( balanced )
+	{
+		uint32_t* clusterIds = reinterpret_cast<uint32_t*>( temp + L.clusterIds );
+		hplocKernel<Source::LeafType><<<DivideRoundUp( nMax, PlocBlock ), PlocBlock, 0, stream>>>(
+			ctl, keys[0], vals[0], primRefs, sortedRefs, scratch, flags, clusterIds, &ctl->nodeCounter, taskQueue );
+		dev.mark( "hploc", stream );
+	}
+	else
+	{
+		emitTopologyKernel<Source::LeafType><<<DivideRoundUp( nMax, 256u ), 256, 0, stream>>>(
+			ctl, keys[0], vals[0], primRefs, sortedRefs, scratch, flags, taskQueue );
+		dev.mark( "emit+refit", stream );
+	}
 
 	const uint32_t warpsNeeded = DivideRoundUp( maxBox, 8u );
 	const uint32_t blocks	   = std::max( 1u, std::min( DivideRoundUp( warpsNeeded, CollapseBlock / 32 ), dev.smCount * 16 ) );
@@ -127,8 +147,9 @@ void buildGeometry(
 {
 	const uint32_t nMax = uint32_t( geometryPrimCount( input ) );
 	if ( nMax == 0 ) throw std::runtime_error( "empty geometry" );
-	const bool		 pairing = wantsPairing( input, options );
-	const TempLayout L		 = tempLayout( nMax, pairing ? nMax : 0 );
+	const bool		 pairing  = wantsPairing( input, options );
+	const bool		 balanced = usesBalancedBuilder( options );
+	const TempLayout L		  = tempLayout( nMax, pairing ? nMax : 0 );
 	uint8_t*		 temp	 = static_cast<uint8_t*>( tempBuffer );
 	uint8_t*		 out	 = static_cast<uint8_t*>( storage );
 
@@ -170,7 +191,7 @@ void buildGeometry(
 		}
 		primBoxesKernel<TriangleMeshSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
 		dev.mark( "boxes", stream );
-		runLbvh( dev, src, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
+		runLbvh( dev, src, balanced, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
 	}
 	else
 	{
@@ -183,7 +204,7 @@ void buildGeometry(
 			return;
 		}
 		primBoxesKernel<AabbListSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
-		runLbvh( dev, src, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
+		runLbvh( dev, src, balanced, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
 	}
 }
 
@@ -216,8 +237,8 @@ size_t sceneTempSize( const hiprtSceneBuildInput& input, hiprtBuildOptions ) { r
 void buildScene(
 	const DeviceInfo& dev, const hiprtSceneBuildInput& input, hiprtBuildOptions options, void* tempBuffer, cudaStream_t stream, void* storage )
 {
-	(void)options;
-	const uint32_t n = input.instanceCount;
+	const bool	   balanced = usesBalancedBuilder( options );
+	const uint32_t n		= input.instanceCount;
 	if ( n == 0 ) throw std::runtime_error( "empty scene" );
 	if ( input.instances == nullptr ) throw std::runtime_error( "scene without instances" );
 	const SceneLayout S	   = sceneLayout( input );
@@ -249,7 +270,7 @@ void buildScene(
 	}
 	const uint32_t streamGrid = std::min<uint32_t>( DivideRoundUp( n, 256u ), dev.smCount * 8 );
 	primBoxesKernel<InstanceSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
-	runLbvh( dev, src, n, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
+	runLbvh( dev, src, balanced, n, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
 }
 void updateGeometry( const DeviceInfo&, const hiprtGeometryBuildInput&, hiprtBuildOptions, void*, cudaStream_t, void* )
 {

@@ -49,6 +49,7 @@ __global__ void initGeometryKernel(
 	ctl->rootNode		 = InvalidValue;
 	ctl->queueHead		 = 0;
 	ctl->pairTileCounter = 0;
+	ctl->nodeCounter	 = 0;
 	header->boxNodes	  = boxNodes;
 	header->primNodes	  = primNodes;
 	header->size		  = size;
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__( 256 ) initSceneKernel(
 		ctl->rootNode		 = InvalidValue;
 		ctl->queueHead		 = 0;
 		ctl->pairTileCounter = 0;
+	ctl->nodeCounter	 = 0;
 		header->boxNodes	   = boxNodes;
 		header->primNodes	   = instNodes;
 		header->instances	   = records;
@@ -323,6 +325,169 @@ __global__ void __launch_bounds__( 256 ) emitTopologyKernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// Balanced builder: H-PLOC (hierarchical parallel locally-ordered clustering; reference:
+// PlocBuilderKernels.h:120-307, host PlocBuilder.h:300-351). Lanes climb the same LBVH ranges
+// as the fast builder, but a range only COLLECTS cluster ids; once a range holds more than
+// PlocWindow/2 clusters (or is the whole array) the warp merges it: every cluster looks for its
+// nearest neighbour (union-box area) within PlocRadius positions, mutually nearest pairs merge
+// into a new binary node, survivors are compacted in order, until at most PlocWindow/2 (or 1 at
+// the root) remain. Output = the same ScratchNode/ReferenceNode records the collapse consumes.
+//
+// B200 version: the window lives in REGISTERS (one cluster per lane: id + box); neighbour boxes
+// come from shfl_down, the distance of the mirrored pair from shfl_up, compaction from a ballot
+// and __fns -- no shared memory, no shared-memory atomics. Distances are ordered by the 64-bit key
+// (area bits, lower position, higher position): a total order over pairs, so the globally
+// closest pair is always mutual and every round makes progress; the tree shape depends only on
+// the sorted keys and boxes (node ADDRESSES depend on atomic order, as in the reference).
+constexpr uint32_t PlocRadius = 8;
+constexpr uint32_t PlocWindow = 32; // clusters held by a warp: 16 from each side of the split
+constexpr uint32_t PlocBlock  = 256;
+
+__device__ __forceinline__ uint64_t shflU64( uint64_t v, uint32_t srcLane )
+{
+	const uint32_t lo = __shfl_sync( FullMask, uint32_t( v ), srcLane ), hi = __shfl_sync( FullMask, uint32_t( v >> 32 ), srcLane );
+	return ( uint64_t( hi ) << 32 ) | lo;
+}
+__device__ __forceinline__ uint64_t shflUpU64( uint64_t v, uint32_t d )
+{
+	const uint32_t lo = __shfl_up_sync( FullMask, uint32_t( v ), d ), hi = __shfl_up_sync( FullMask, uint32_t( v >> 32 ), d );
+	return ( uint64_t( hi ) << 32 ) | lo;
+}
+__device__ __forceinline__ DBox shflBox( const DBox& b, uint32_t srcLane )
+{
+	return DBox{
+		make_float3( __shfl_sync( FullMask, b.lo.x, srcLane ), __shfl_sync( FullMask, b.lo.y, srcLane ), __shfl_sync( FullMask, b.lo.z, srcLane ) ),
+		make_float3( __shfl_sync( FullMask, b.hi.x, srcLane ), __shfl_sync( FullMask, b.hi.y, srcLane ), __shfl_sync( FullMask, b.hi.z, srcLane ) ) };
+}
+__device__ __forceinline__ DBox shflDownBox( const DBox& b, uint32_t d )
+{
+	return DBox{
+		make_float3( __shfl_down_sync( FullMask, b.lo.x, d ), __shfl_down_sync( FullMask, b.lo.y, d ), __shfl_down_sync( FullMask, b.lo.z, d ) ),
+		make_float3( __shfl_down_sync( FullMask, b.hi.x, d ), __shfl_down_sync( FullMask, b.hi.y, d ), __shfl_down_sync( FullMask, b.hi.z, d ) ) };
+}
+
+template <uint32_t LeafType>
+__global__ void __launch_bounds__( PlocBlock ) hplocKernel(
+	BuildControl*	ctl,
+	const uint32_t* sortedKeys,
+	const uint32_t* sortedVals,
+	const void*		primRefs,
+	void*			sortedRefs,
+	void*			scratch,
+	uint32_t*		flags,		// per split gap: far end of the range of the first child to arrive (0xFF.. initially)
+	uint32_t*		clusterIds, // per sorted position: cluster occupying it (compacted to the front of each merged range)
+	uint32_t*		nodeCounter,
+	uint64_t*		taskQueue )
+{
+	const uint32_t n	= ctl->primCount;
+	const uint32_t k	= blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t lane = laneId();
+	bool		   active = k < n;
+	if ( active )
+	{
+		const uint32_t prim = sortedVals[k];
+		const DBox	   box	= loadRec( primRefs, prim ).box;
+		storeRec( sortedRefs, k, box, prim, 0u );
+		__stcg( &clusterIds[k], makeNodeIndex( k, LeafType ) );
+	}
+	uint32_t i = k, j = k + 1, s = k;
+	constexpr uint32_t Half = PlocWindow / 2;
+
+	while ( __any_sync( FullMask, active ) )
+	{
+		if ( active )
+		{
+			const bool	   left	  = ( i == 0 ) || ( j != n && gapDelta( sortedKeys, j - 1, n ) < gapDelta( sortedKeys, i - 1, n ) );
+			const uint32_t parent = left ? j - 1 : i - 1;
+			__threadfence();
+			const uint32_t other = atomicExch( &flags[parent], left ? i : j );
+			if ( left )
+				s = j, j = other;
+			else
+				s = i, i = other;
+			if ( other == InvalidValue ) active = false; // first to arrive: the sibling carries the range on
+			__threadfence();
+		}
+		const bool last	 = active && i == 0 && j == n;
+		uint32_t   merge = __ballot_sync( FullMask, active && ( j - i > Half || last ) );
+		while ( merge )
+		{
+			const uint32_t cur = __ffs( merge ) - 1;
+			merge &= merge - 1;
+			const uint32_t ci = __shfl_sync( FullMask, i, cur ), cj = __shfl_sync( FullMask, j, cur ), cs = __shfl_sync( FullMask, s, cur );
+			const bool	   clast = __shfl_sync( FullMask, uint32_t( last ), cur ) != 0;
+
+			// gather up to 16 clusters from the front of each side (valid ids are a prefix of each side)
+			const uint32_t numLeft = min( cs - ci, Half ), numRight = min( cj - cs, Half );
+			const uint32_t idL = lane < numLeft ? __ldcg( &clusterIds[ci + lane] ) : InvalidValue;
+			const uint32_t idR = lane < numRight ? __ldcg( &clusterIds[cs + lane] ) : InvalidValue;
+			const uint32_t vL = __popc( __ballot_sync( FullMask, idL != InvalidValue ) ), vR = __popc( __ballot_sync( FullMask, idR != InvalidValue ) );
+			const uint32_t fromR = __shfl_sync( FullMask, idR, ( lane - vL ) & 31u );
+			uint32_t	   count = vL + vR;
+			uint32_t	   id	 = lane < vL ? idL : ( lane < count ? fromR : InvalidValue );
+			const uint32_t threshold = clast ? 1u : Half;
+			DBox		   box		 = emptyBox();
+			if ( count > threshold && lane < count )
+				box = ( isBoxIndex( id ) ? loadRecCg( scratch, nodeAddr( id ) ) : loadRecCg( sortedRefs, nodeAddr( id ) ) ).box;
+
+			while ( count > threshold )
+			{
+				// nearest neighbour within PlocRadius positions, both directions
+				uint64_t best = ~0ull;
+#pragma unroll
+				for ( uint32_t d = 1; d <= PlocRadius; ++d )
+				{
+					const DBox	   nb	 = shflDownBox( box, d );
+					const bool	   valid = lane + d < count;
+					const uint64_t fwd	 = valid ? ( ( uint64_t( __float_as_uint( boxArea( uniteBox( box, nb ) ) ) ) << 32 ) | ( lane << 8 ) | ( lane + d ) ) : ~0ull;
+					const uint64_t bwd	 = shflUpU64( fwd, d ); // the pair (lane - d, lane), computed by lane - d
+					best				 = min( best, fwd );
+					if ( lane >= d ) best = min( best, bwd );
+				}
+				const bool	   has	  = lane < count; // count > 1 here, so every live lane has a neighbour
+				const uint32_t pa	  = ( uint32_t( best ) >> 8 ) & 0xFFu, pb = uint32_t( best ) & 0xFFu;
+				const uint32_t nbLane = has ? ( pa == lane ? pb : pa ) : lane;
+				const uint64_t nbBest = shflU64( best, nbLane );
+				const bool	   mutual = has && nbBest == best;
+				const bool	   merging = mutual && lane < nbLane; // the lower position keeps the merged cluster
+				const bool	   dropped = mutual && lane > nbLane;
+				const uint32_t nbId	   = __shfl_sync( FullMask, id, nbLane );
+				const DBox	   nbBox   = shflBox( box, nbLane );
+				const uint32_t mmask   = __ballot_sync( FullMask, merging );
+				uint32_t	   base	   = 0;
+				if ( lane == 0 ) base = atomicAdd( nodeCounter, __popc( mmask ) );
+				base = __shfl_sync( FullMask, base, 0 );
+				if ( merging )
+				{
+					const uint32_t addr = n - 2u - ( base + __popc( mmask & laneMaskLt() ) );
+					box					= uniteBox( box, nbBox );
+					storeRec( scratch, addr, box, id, nbId );
+					id = makeNodeIndex( addr, BoxType );
+				}
+				// compact the survivors in order
+				const uint32_t keep		= __ballot_sync( FullMask, has && !dropped );
+				const uint32_t newCount = __popc( keep );
+				const uint32_t src		= lane < newCount ? __fns( keep, 0, lane + 1 ) : lane;
+				id						= __shfl_sync( FullMask, id, src );
+				box						= shflBox( box, src );
+				if ( lane >= newCount ) id = InvalidValue;
+				count = newCount;
+			}
+
+			if ( lane < Half && ci + lane < n ) __stcg( &clusterIds[ci + lane], lane < count ? id : InvalidValue );
+			if ( clast && lane == 0 )
+			{
+				ctl->rootNode = nodeAddr( id );
+				taskQueue[0]  = ( uint64_t( InvalidValue ) << 32 ) | id; // root task of the collapse
+			}
+			__threadfence();
+			__syncwarp();
+		}
+		if ( last ) active = false;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // Collapse the binary tree into 4-wide nodes and pack the leaves (reference: Collapse + openNodes
 // BvhBuilderKernels.h:137-193,1088-1258; PackLeaves :1441-1479).
 // A task = (binary node, parent box address); the task's index in the queue IS the address of
@@ -378,7 +543,7 @@ __global__ void __launch_bounds__( CollapseBlock ) collapsePackKernel(
 				if ( __shfl_sync( FullMask, packed, 0 ) >= n ) return;
 				if ( ++idlePolls > ( 1u << 22 ) )
 				{
-					if ( lane == 0 ) ctl->pad[1] = 1; // build error flag
+					if ( lane == 0 ) ctl->pad[0] = 1; // build error flag
 					return;
 				}
 				continue;

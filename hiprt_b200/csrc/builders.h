@@ -83,6 +83,7 @@ struct TempLayout
 	size_t sortedRefs; // 32 B x N  {box, primIndex} in sorted order
 	size_t scratch;	   // 32 B x N  binary nodes
 	size_t flags;	   // u32 x N
+	size_t clusterIds; // u32 x N  (H-PLOC)
 	size_t taskQueue;  // u64 x maxBoxNodes (aliases keys/vals)
 	size_t total;
 };
@@ -95,7 +96,8 @@ struct BuildControl
 	uint32_t rootNode;		 // binary root id
 	uint32_t queueHead;		 // collapse: next task to claim
 	uint32_t pairTileCounter;
-	uint32_t pad[6];
+	uint32_t nodeCounter;	 // H-PLOC: binary nodes allocated so far
+	uint32_t pad[5];
 };
 static_assert( sizeof( BuildControl ) == 64, "BuildControl is one 64-byte line" );
 } // namespace hiprt

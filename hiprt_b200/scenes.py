@@ -233,3 +233,44 @@ def random_rays(n, box_lo, box_hi, seed=7):
     o = c + dirs * r
     tgt = lo + rng.random((n, 3)) * (hi - lo)
     return make_rays(o.astype(f32), normalize(tgt - o))
+
+
+# ---------------------------------------------------------------------------------------------
+# two-level scenes (config C4: geometries instanced with random rigid + uniform-scale transforms)
+def random_matrix_frames(n, seed=42, extent=50.0, scale_range=(0.5, 2.0)):
+    """hiprtFrameMatrix[n] as float32 [n,16]: rows of the 3x4 object-to-world matrix, time, padding.
+    Translation uniform in [-extent, extent]^3, rotation uniform (quaternion from 3 uniforms),
+    uniform scale in scale_range."""
+    rng = np.random.default_rng(seed)
+    u = rng.random((n, 3))
+    q = np.stack([np.sqrt(1 - u[:, 0]) * np.sin(2 * np.pi * u[:, 1]), np.sqrt(1 - u[:, 0]) * np.cos(2 * np.pi * u[:, 1]),
+                  np.sqrt(u[:, 0]) * np.sin(2 * np.pi * u[:, 2]), np.sqrt(u[:, 0]) * np.cos(2 * np.pi * u[:, 2])], -1)
+    x, y, z, w = q.T
+    R = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], -1),
+                  np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], -1),
+                  np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1)], 1)
+    s = rng.uniform(scale_range[0], scale_range[1], (n, 1, 1))
+    t = rng.uniform(-extent, extent, (n, 3))
+    out = np.zeros((n, 16), f32)
+    m = np.concatenate([R * s, t[:, :, None]], 2)  # [n,3,4]
+    out[:, :12] = m.reshape(n, 12).astype(f32)
+    return out
+
+
+def instanced_geometries(count=100, base_subdiv=None):
+    """The C4 geometry set: geometry g is an icosphere (even g) or a lat-long sphere (odd g) whose triangle
+    count grows with g mod 8 (about 128 * 2^(g mod 8) triangles)."""
+    out = []
+    for g in range(count):
+        k = g % 8
+        if g % 2 == 0:
+            n_lon = max(4, int(round((64 * 2 ** k) ** 0.5)))
+            out.append(sphere_mesh(2 * n_lon, n_lon // 2 + 1, radius=1.0 + 0.01 * g))
+        else:
+            n = max(3, int(round((64 * 2 ** k) ** 0.5)))
+            v, i = grid_mesh(n, n)
+            v = v.copy()
+            v[:, 2] = 0.3 * np.sin(3.0 * v[:, 0] + g) * np.cos(2.0 * v[:, 1])  # wavy patch in [0,1]^2
+            v[:, :2] = v[:, :2] * 2.0 - 1.0
+            out.append((np.ascontiguousarray(v.astype(f32)), i))
+    return out

@@ -87,6 +87,13 @@ def lib():
         L.orc_geometry_trace_all.restype = u64
         L.orc_canonicalize.argtypes = [vp, vp, u32, vp, vp, vp]
         L.orc_canonicalize.restype = u32
+        L.orc_scene_create.argtypes = [vp, u32, vp, vp, i32, vp, u32]
+        L.orc_scene_create.restype = vp
+        L.orc_scene_destroy.argtypes = [vp]
+        L.orc_scene_count.argtypes = [vp, i32]
+        L.orc_scene_count.restype = u32
+        L.orc_scene_read.argtypes = [vp, i32, vp]
+        L.orc_scene_trace.argtypes = [vp, vp, u32, vp, u32, i32]
         _lib = L
     return _lib
 
@@ -207,3 +214,48 @@ def canonicalize(box_nodes, leaves):
     nleaf = C.c_uint32(0)
     nb = lib().orc_canonicalize(_p(bn), _p(lv), lv.dtype.itemsize, _p(out_b), _p(out_l), C.byref(nleaf))
     return out_b[:nb], out_l[: nleaf.value]
+
+
+INSTANCE_NODE_DTYPE = np.dtype([("invMatrix", "<f4", (3, 4)), ("pointer", "<u8"), ("mask", "<u4"), ("bits", "<u4")])
+
+
+class Scene:
+    """Two-level scene of the oracle: instances of oracle Geometry objects, one frame per instance
+    (frame_type 0: hiprtFrameSRT rows of 12 floats, 1: hiprtFrameMatrix rows of 16 floats)."""
+
+    def __init__(self, geometries, geometry_of_instance, frames, frame_type=1, masks=None):
+        self.geometries = list(geometries)
+        self.geometry_of_instance = np.ascontiguousarray(geometry_of_instance, np.uint32)
+        n = len(self.geometry_of_instance)
+        self.frames = None if frames is None else np.ascontiguousarray(frames, np.float32).reshape(n, 16 if frame_type == 1 else 12)
+        self.masks = None if masks is None else np.ascontiguousarray(masks, np.uint32)
+        handles = (C.c_void_p * len(self.geometries))(*[g.h for g in self.geometries])
+        self.h = lib().orc_scene_create(handles, len(self.geometries), _p(self.geometry_of_instance), _p(self.frames), frame_type,
+                                        _p(self.masks), n)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_scene_destroy(self.h)
+            self.h = None
+
+    count = property(lambda s: int(lib().orc_scene_count(s.h, 0)))
+    box_count = property(lambda s: int(lib().orc_scene_count(s.h, 1)))
+    leaf_count = property(lambda s: int(lib().orc_scene_count(s.h, 2)))
+
+    def _read(self, what, dtype, n):
+        out = np.zeros(n, dtype)
+        lib().orc_scene_read(self.h, what, _p(out))
+        return out
+
+    prim_boxes = property(lambda s: s._read(0, np.float32, 6 * s.count).reshape(-1, 2, 3))
+    keys = property(lambda s: s._read(1, np.uint32, s.count))
+    box_nodes = property(lambda s: s._read(2, BOX4_DTYPE, s.box_count))
+    leaves = property(lambda s: s._read(3, INSTANCE_NODE_DTYPE, s.leaf_count))
+    sorted_keys = property(lambda s: s._read(4, np.uint32, s.count))
+    sorted_vals = property(lambda s: s._read(5, np.uint32, s.count))
+
+    def trace(self, rays, ray_mask=0xFFFFFFFF, tie_mode=1):
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        lib().orc_scene_trace(self.h, _p(rays), len(rays), _p(hits), ray_mask, tie_mode)
+        return hits

@@ -23,7 +23,7 @@ GEOM_HEADER_DTYPE = np.dtype(
 
 def available():
     return all(os.path.exists(os.path.join(REF_DIR, f)) for f in
-               ("libref_harness.so", "libhiprt_ref.so", "hiprt03001_0.0_nv.fatbin", "oro_compiled_kernels.fatbin", "ref_trace.fatbin"))
+               ("libref_harness.so", "libhiprt_ref.so", "hiprt03001_nv.fatbin", "oro_compiled_kernels.fatbin", "ref_trace.fatbin"))
 
 
 _lib = None

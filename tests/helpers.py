@@ -59,3 +59,44 @@ def tea16(v0, v1):
             v0 += ((v1 << np.uint32(4)) + np.uint32(0xA341316C)) ^ (v1 + s0) ^ ((v1 >> np.uint32(5)) + np.uint32(0xC8013EA4))
             v1 += ((v0 << np.uint32(4)) + np.uint32(0xAD90777D)) ^ (v0 + s0) ^ ((v0 >> np.uint32(5)) + np.uint32(0x7E95761E))
     return v0, v1
+
+
+def validate_wide_bvh(boxes, leaves, prim_count_expected=None):
+    """Structural check of a 4-wide BVH read back from the device (any builder): every leaf is referenced
+    exactly once, every child box equals the exact union of what is below it (boxes are fp32 min/max, so
+    equality is exact), parent links are consistent. Returns the SAH-style cost sum(child areas)/root area."""
+    INVALID = 0xFFFFFFFF
+    child = boxes["child"]
+    valid = child != INVALID
+    ctype = child & 7
+    is_box = valid & (ctype == 5)
+    is_leaf = valid & (ctype != 5)
+    assert np.array_equal(valid.sum(1), boxes["childCount"]), "childCount does not match the valid slots"
+    # leaves: referenced exactly once
+    leaf_addr = child[is_leaf] >> 3
+    assert len(leaf_addr) == len(leaves) and np.array_equal(np.sort(leaf_addr), np.arange(len(leaves))), "leaves not referenced exactly once"
+    # box children: referenced exactly once, never the root
+    box_addr = child[is_box] >> 4
+    assert np.array_equal(np.sort(box_addr), np.arange(1, len(boxes))), "box nodes not referenced exactly once"
+    # parent links
+    parent_of = np.full(len(boxes), INVALID, np.uint32)
+    rows = np.nonzero(is_box)[0]
+    parent_of[box_addr] = rows
+    assert np.array_equal(parent_of, boxes["parentAddr"]), "parent links are wrong"
+    # child boxes: exact unions
+    lo = np.where(valid[..., None], boxes["box"][:, :, 0, :], np.inf).min(1)
+    hi = np.where(valid[..., None], boxes["box"][:, :, 1, :], -np.inf).max(1)
+    cb = boxes["box"][is_box]
+    assert np.array_equal(cb[:, 0], lo[box_addr]) and np.array_equal(cb[:, 1], hi[box_addr]), "inner child box is not the union of its children"
+    if leaves.dtype.names and "v" in leaves.dtype.names:
+        v = leaves["v"]
+        lb = boxes["box"][is_leaf]
+        assert np.array_equal(lb[:, 0], v[leaf_addr].min(1)) and np.array_equal(lb[:, 1], v[leaf_addr].max(1)), "leaf box is not the box of its vertices"
+        prims = np.concatenate([leaves["primIndex0"], leaves["primIndex1"][leaves["primIndex1"] != leaves["primIndex0"]]])
+        if prim_count_expected is not None:
+            assert np.array_equal(np.sort(prims), np.arange(prim_count_expected)), "triangles are not covered exactly once"
+    ext = np.maximum(boxes["box"][:, :, 1, :] - boxes["box"][:, :, 0, :], 0)
+    area = 2 * (ext[..., 0] * ext[..., 1] + ext[..., 0] * ext[..., 2] + ext[..., 1] * ext[..., 2])
+    root_ext = hi[0] - lo[0]
+    root_area = 2 * (root_ext[0] * root_ext[1] + root_ext[0] * root_ext[2] + root_ext[1] * root_ext[2])
+    return float(np.where(valid, area, 0).sum() / max(root_area, 1e-30))

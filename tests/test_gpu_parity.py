@@ -201,3 +201,51 @@ def test_disable_pairing_flag(ctx):
     assert int(geom.header()["primNodeCount"]) == len(idx) == og.prim_count
     check_build_against_oracle(ctx, geom, og)
     geom.destroy()
+
+
+# ---- balanced builder (H-PLOC): topology is not pinned by the reference ("balanced-build topology is not
+# parity-checked, only hits are"), so: structural validity, hits equal to the oracle's, and better SAH than the fast build.
+BALANCED_CASES = {
+    "soup2": lambda: (scenes.random_soup(2, seed=1), None),
+    "soup17": lambda: (scenes.random_soup(17, seed=2), None),
+    "soup33": lambda: (scenes.random_soup(33, seed=3), None),
+    "soup5000": lambda: (scenes.random_soup(5000, seed=4), None),
+    "soup200k": lambda: (scenes.random_soup(200_000, seed=5), None),
+    "sphere": lambda: scenes.sphere_mesh(300, 300),
+    "grid": lambda: scenes.grid_mesh(64, 48),
+    "identical": lambda: (np.tile(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32), (3000, 1)), None),
+}
+
+
+@pytest.mark.parametrize("case", sorted(BALANCED_CASES))
+def test_balanced_build_is_valid_and_hits_match(ctx, case):
+    verts, idx = BALANCED_CASES[case]()
+    d_idx = None if idx is None else to_dev(ctx, idx)
+    n_tris = len(verts) // 3 if idx is None else len(idx)
+    geom = ctx.build(to_dev(ctx, verts), d_idx, flags=api.BALANCED_BUILD)
+    boxes, leaves = geom.nodes()
+    cost_balanced = H.validate_wide_bvh(boxes, leaves, n_tris)
+    fast = ctx.build(to_dev(ctx, verts), d_idx, flags=api.FAST_BUILD)
+    cost_fast = H.validate_wide_bvh(*fast.nodes(), n_tris)
+    if n_tris >= 5000 and case != "identical":
+        assert cost_balanced < cost_fast, f"H-PLOC SAH {cost_balanced:.1f} is not better than LBVH {cost_fast:.1f}"
+    og = orc.Geometry(verts, idx)
+    lo, hi = verts.min(0), verts.max(0)
+    rays = scenes.random_rays(20000, lo - 0.05, hi + 0.05, seed=9)
+    got = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays)))
+    compare_hits(got, og.trace(rays, tie_mode=1))
+    # building twice gives the same tree shape (node addresses may differ): same canonical structure
+    geom2 = ctx.build(to_dev(ctx, verts), d_idx, flags=api.BALANCED_BUILD)
+    b2, l2 = geom2.nodes()
+    c1 = orc.canonicalize(boxes.view(orc.BOX4_DTYPE), leaves.view(orc.TRIPAIR_DTYPE))
+    c2 = orc.canonicalize(b2.view(orc.BOX4_DTYPE), l2.view(orc.TRIPAIR_DTYPE))
+    assert c1[0].tobytes() == c2[0].tobytes() and c1[1].tobytes() == c2[1].tobytes(), "H-PLOC tree shape is not deterministic"
+    for g in (geom, fast, geom2):
+        g.destroy()
+
+
+def test_fast_build_structure_is_valid(ctx):
+    verts, idx = scenes.sphere_mesh(100, 50)
+    geom = ctx.build(to_dev(ctx, verts), to_dev(ctx, idx))
+    H.validate_wide_bvh(*geom.nodes(), len(idx))
+    geom.destroy()
