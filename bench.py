@@ -56,41 +56,56 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled through NVML (in-process, every ~5 ms) while the timed
+    regions run; falls back to one nvidia-smi query when NVML is not importable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, device_index):
-        self.samples, self.reasons, self.proc = [], set(), None
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = threading.Event()
+        self.thread = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={device_index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.proc.stdout:
-            p = [x.strip() for x in line.split(",")]
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[device_index]) if visible and visible.split(",")[device_index].isdigit() else device_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
             try:
-                self.samples.append((float(p[0]), float(p[1])))
-                for n, v in zip(names, p[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
-            except (ValueError, IndexError):
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, util))
+                for bit, name in self.REASONS.items():
+                    if bits & bit:
+                        self.reasons.add(name)
+            except Exception:
                 pass
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        self.proc.terminate()
+        if self.thread is None:
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0].split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1, "source": "nvidia-smi (single query)"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.stop_flag.set()
         self.thread.join(timeout=2)
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": sorted(self.reasons)}
         sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples), "reasons": sorted(self.reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "NVML, 5 ms period over the timed regions"}
 
 
 def embree_arm(verts, idx, primary, light, steps, warmup, threads):
@@ -309,7 +324,7 @@ def main():
         # build passes against the HBM roofline: algorithmic bytes per primitive pair
         n_prims = int(geom.header()["primNodeCount"])
         algo = {"pair": 32 * n_prims, "boxes": 96 * n_prims, "morton+histogram": 32 * n_prims, "sort": 64 * n_prims,
-                "emit+refit": 128 * n_prims, "collapse+pack": (123 + 152) * n_prims}
+                "emit+refit": 128 * n_prims, "hploc": 200 * n_prims, "collapse+pack": (123 + 152) * n_prims}
         build_roofline = {}
         for name, v in phases.items():
             ms = float(np.mean(v))

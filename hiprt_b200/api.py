@@ -326,6 +326,38 @@ class Context:
         self.build_geometry(inp, g, temp, flags)
         return Geometry(self, g, inp, temp, flags)
 
+    def build_geometries(self, inputs, flags=FAST_BUILD, batch_max=512, stream=None):
+        """hiprtCreateGeometries + hiprtBuildGeometries for a list of build inputs: inputs with at most `batch_max`
+        primitives go through the batch builder (one launch for all of them). Returns a list of Geometry wrappers
+        that share one device allocation and one temporary buffer."""
+        n = len(inputs)
+        arr = (GeometryBuildInput * n)(*inputs)
+        opts = BuildOptions(flags, batch_max)
+        sz = C.c_size_t()
+        self._check(lib().hiprtGetGeometriesBuildTemporaryBufferSize(self.h, n, arr, opts, C.byref(sz)), "hiprtGetGeometriesBuildTemporaryBufferSize")
+        temp = self.alloc_temp(sz.value)
+        handles = (C.c_void_p * n)()
+        base = C.addressof(handles)
+        slots = (C.c_void_p * n)(*[base + 8 * i for i in range(n)])
+        self._check(lib().hiprtCreateGeometries(self.h, n, arr, opts, C.cast(slots, _P(_P(_vp)))), "hiprtCreateGeometries")
+        self._check(lib().hiprtBuildGeometries(self.h, BUILD, n, arr, opts, _ptr(temp), _stream_handle(stream), handles), "hiprtBuildGeometries")
+        out = [Geometry(self, C.c_void_p(handles[i]), inputs[i], temp, flags) for i in range(n)]
+        for g in out:
+            g.batch = (arr, handles)
+        return out
+
+    def rebuild_geometries(self, geoms, batch_max=512, stream=None):
+        arr, handles = geoms[0].batch
+        self._check(lib().hiprtBuildGeometries(self.h, BUILD, len(geoms), arr, BuildOptions(geoms[0].flags, batch_max), _ptr(geoms[0].temp),
+                                               _stream_handle(stream), handles), "hiprtBuildGeometries")
+
+    def destroy_geometries(self, geoms):
+        n = len(geoms)
+        handles = (C.c_void_p * n)(*[g.h.value for g in geoms])
+        self._check(lib().hiprtDestroyGeometries(self.h, n, handles), "hiprtDestroyGeometries")
+        for g in geoms:
+            g.h = None
+
     # ---- scenes -------------------------------------------------------------------------------
     def build_scene(self, instance_handles, frames=None, frame_type=FRAME_MATRIX, masks=None, flags=FAST_BUILD,
                     instance_types=None, transform_headers=None, stream=None):
@@ -431,7 +463,10 @@ class Geometry:
         """(box nodes, triangle-pair leaves) copied to the host."""
         h = self.header()
         boxes = self.ctx.read_device(h["boxNodes"], int(h["boxNodeCount"]) * 128).view(BOX4_DTYPE)
-        leaves = self.ctx.read_device(h["primNodes"], int(h["primNodeCount"]) * 64).view(TRIPAIR_DTYPE)
+        if int(h["geomType"]) & 1:
+            leaves = self.ctx.read_device(h["primNodes"], int(h["primNodeCount"]) * 64).view(TRIPAIR_DTYPE)
+        else:
+            leaves = self.ctx.read_device(h["primNodes"], int(h["primNodeCount"]) * 4).view(np.uint32)
         return boxes, leaves
 
     def temp_array(self, name, dtype, count):

@@ -36,6 +36,98 @@ struct OutOfDeviceMemory : std::runtime_error
 	using std::runtime_error::runtime_error;
 };
 
+// End-to-end path with HOST buffers: rays are pushed, traced and the hits pulled back in chunks on
+// three streams so that the H2D copy of chunk c+1, the traversal of chunk c and the D2H copy of chunk
+// c-1 overlap (PCIe is full duplex; per ray 32 B go up and 48 B come down, so the call is bound by the
+// D2H direction). Device staging buffers and streams live in the context and are reused across calls.
+// Pageable host memory still works (the copies then serialise inside the driver).
+class HostTracePipeline
+{
+  public:
+	static constexpr uint32_t Chunk = 1u << 18; // rays per chunk: 8 MiB up, 12 MiB down
+	static constexpr int	  Slots = 3;
+
+	~HostTracePipeline()
+	{
+		if ( !m_ready ) return;
+		for ( int i = 0; i < Slots; ++i )
+		{
+			cudaFree( m_rays[i] );
+			cudaFree( m_hits[i] );
+			cudaEventDestroy( m_up[i] );
+			cudaEventDestroy( m_traced[i] );
+			cudaEventDestroy( m_down[i] );
+		}
+		cudaEventDestroy( m_begin );
+		cudaStreamDestroy( m_h2d );
+		cudaStreamDestroy( m_compute );
+		cudaStreamDestroy( m_d2h );
+	}
+
+	void run(
+		hiprtGeometry geometry, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t user )
+	{
+		std::lock_guard<std::mutex> lock( m_mutex );
+		init();
+		// order after whatever the caller has queued on its stream (e.g. the build)
+		checkCuda( cudaEventRecord( m_begin, user ), "cudaEventRecord" );
+		checkCuda( cudaStreamWaitEvent( m_h2d, m_begin, 0 ), "cudaStreamWaitEvent" );
+		checkCuda( cudaStreamWaitEvent( m_compute, m_begin, 0 ), "cudaStreamWaitEvent" );
+		const uint32_t chunks = ( numRays + Chunk - 1 ) / Chunk;
+		for ( uint32_t c = 0; c < chunks; ++c )
+		{
+			const int	   slot	 = int( c % Slots );
+			const uint32_t first = c * Chunk, count = std::min( Chunk, numRays - first );
+			if ( c >= uint32_t( Slots ) ) checkCuda( cudaStreamWaitEvent( m_h2d, m_traced[slot], 0 ), "cudaStreamWaitEvent" );
+			checkCuda( cudaMemcpyAsync( m_rays[slot], hostRays + first, size_t( count ) * sizeof( hiprtRay ), cudaMemcpyHostToDevice, m_h2d ), "H2D rays" );
+			checkCuda( cudaEventRecord( m_up[slot], m_h2d ), "cudaEventRecord" );
+
+			checkCuda( cudaStreamWaitEvent( m_compute, m_up[slot], 0 ), "cudaStreamWaitEvent" );
+			if ( c >= uint32_t( Slots ) ) checkCuda( cudaStreamWaitEvent( m_compute, m_down[slot], 0 ), "cudaStreamWaitEvent" );
+			if ( geometry )
+				traceGeometry( geometry, m_rays[slot], count, m_hits[slot], type, m_compute );
+			else
+				traceScene( scene, m_rays[slot], count, m_hits[slot], type, mask, m_compute );
+			checkCuda( cudaGetLastError(), "trace launch" );
+			checkCuda( cudaEventRecord( m_traced[slot], m_compute ), "cudaEventRecord" );
+
+			checkCuda( cudaStreamWaitEvent( m_d2h, m_traced[slot], 0 ), "cudaStreamWaitEvent" );
+			checkCuda( cudaMemcpyAsync( hostHits + first, m_hits[slot], size_t( count ) * sizeof( hiprtHit ), cudaMemcpyDeviceToHost, m_d2h ), "D2H hits" );
+			checkCuda( cudaEventRecord( m_down[slot], m_d2h ), "cudaEventRecord" );
+		}
+		checkCuda( cudaStreamSynchronize( m_d2h ), "cudaStreamSynchronize" );
+		launches += chunks;
+	}
+
+	uint64_t launches = 0;
+
+  private:
+	void init()
+	{
+		if ( m_ready ) return;
+		checkCuda( cudaStreamCreateWithFlags( &m_h2d, cudaStreamNonBlocking ), "cudaStreamCreate" );
+		checkCuda( cudaStreamCreateWithFlags( &m_compute, cudaStreamNonBlocking ), "cudaStreamCreate" );
+		checkCuda( cudaStreamCreateWithFlags( &m_d2h, cudaStreamNonBlocking ), "cudaStreamCreate" );
+		checkCuda( cudaEventCreateWithFlags( &m_begin, cudaEventDisableTiming ), "cudaEventCreate" );
+		for ( int i = 0; i < Slots; ++i )
+		{
+			checkCuda( cudaMalloc( reinterpret_cast<void**>( &m_rays[i] ), size_t( Chunk ) * sizeof( hiprtRay ) ), "cudaMalloc" );
+			checkCuda( cudaMalloc( reinterpret_cast<void**>( &m_hits[i] ), size_t( Chunk ) * sizeof( hiprtHit ) ), "cudaMalloc" );
+			checkCuda( cudaEventCreateWithFlags( &m_up[i], cudaEventDisableTiming ), "cudaEventCreate" );
+			checkCuda( cudaEventCreateWithFlags( &m_traced[i], cudaEventDisableTiming ), "cudaEventCreate" );
+			checkCuda( cudaEventCreateWithFlags( &m_down[i], cudaEventDisableTiming ), "cudaEventCreate" );
+		}
+		m_ready = true;
+	}
+
+	bool		 m_ready = false;
+	std::mutex	 m_mutex;
+	cudaStream_t m_h2d = nullptr, m_compute = nullptr, m_d2h = nullptr;
+	cudaEvent_t	 m_begin = nullptr, m_up[Slots]{}, m_traced[Slots]{}, m_down[Slots]{};
+	hiprtRay*	 m_rays[Slots]{};
+	hiprtHit*	 m_hits[Slots]{};
+};
+
 class Context
 {
   public:
@@ -148,7 +240,8 @@ class Context
 		}
 	}
 
-	std::string cacheDir;
+	std::string		  cacheDir;
+	HostTracePipeline hostPipeline;
 
   private:
 	struct Pool
@@ -795,30 +888,11 @@ hiprtError hiprtB200TraceScene(
 	} );
 }
 
-static void traceHost(
-	hiprtGeometry geometry, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t s )
-{
-	hiprtRay* dRays = nullptr;
-	hiprtHit* dHits = nullptr;
-	checkCuda( cudaMallocAsync( reinterpret_cast<void**>( &dRays ), size_t( numRays ) * sizeof( hiprtRay ), s ), "cudaMallocAsync" );
-	checkCuda( cudaMallocAsync( reinterpret_cast<void**>( &dHits ), size_t( numRays ) * sizeof( hiprtHit ), s ), "cudaMallocAsync" );
-	checkCuda( cudaMemcpyAsync( dRays, hostRays, size_t( numRays ) * sizeof( hiprtRay ), cudaMemcpyHostToDevice, s ), "H2D rays" );
-	if ( geometry )
-		traceGeometry( geometry, dRays, numRays, dHits, type, s );
-	else
-		traceScene( scene, dRays, numRays, dHits, type, mask, s );
-	checkCuda( cudaGetLastError(), "trace launch" );
-	checkCuda( cudaMemcpyAsync( hostHits, dHits, size_t( numRays ) * sizeof( hiprtHit ), cudaMemcpyDeviceToHost, s ), "D2H hits" );
-	checkCuda( cudaFreeAsync( dRays, s ), "cudaFreeAsync" );
-	checkCuda( cudaFreeAsync( dHits, s ), "cudaFreeAsync" );
-	checkCuda( cudaStreamSynchronize( s ), "cudaStreamSynchronize" );
-}
-
 hiprtError hiprtB200TraceGeometryHost(
 	hiprtContext context, hiprtGeometry geometry, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtApiStream stream )
 {
 	if ( !context || !geometry || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
-	return guarded( context, [&] { traceHost( geometry, nullptr, hostRays, numRays, hostHits, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ) ); } );
+	return guarded( context, [&] { ctx( context )->hostPipeline.run( geometry, nullptr, hostRays, numRays, hostHits, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ) ); } );
 }
 
 hiprtError hiprtB200TraceSceneHost(
@@ -832,7 +906,7 @@ hiprtError hiprtB200TraceSceneHost(
 	hiprtApiStream	   stream )
 {
 	if ( !context || !scene || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
-	return guarded( context, [&] { traceHost( nullptr, scene, hostRays, numRays, hostHits, type, mask, static_cast<cudaStream_t>( stream ) ); } );
+	return guarded( context, [&] { ctx( context )->hostPipeline.run( nullptr, scene, hostRays, numRays, hostHits, type, mask, static_cast<cudaStream_t>( stream ) ); } );
 }
 
 hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount, size_t* offsetsOut, uint32_t numOffsets )

@@ -1,7 +1,7 @@
 // Host orchestration of the builders: temporary-buffer layout, launch sequences.
 // (kernels: build_kernels.cuh; reference host side: hiprt/impl/LbvhBuilder.{h,cpp},
 // PlocBuilder.{h,cpp}, BatchBuilder.{h,cpp}, Context.cpp:144-290.)
-#include "build_kernels.cuh"
+#include "batch_kernels.cuh"
 
 namespace hiprt
 {
@@ -16,7 +16,7 @@ TempLayout tempLayout( size_t n, size_t pairTriangles )
 	};
 	L.control	  = take( sizeof( BuildControl ) );
 	L.pairs		  = take( pairTriangles * sizeof( uint2 ) );
-	L.pairScan	  = take( DivideRoundUp( pairTriangles, size_t( PairBlock ) ) * sizeof( uint32_t ) );
+	L.pairScan	  = take( DivideRoundUp( pairTriangles, size_t( PairTile ) ) * sizeof( uint32_t ) );
 	L.primRefs	  = take( n * 32 );
 	L.keys[0]	  = take( n * 4 );
 	L.vals[0]	  = take( n * 4 );
@@ -129,7 +129,7 @@ static void runLbvh(
 	}
 	else
 	{
-		emitTopologyKernel<Source::LeafType><<<DivideRoundUp( nMax, 256u ), 256, 0, stream>>>(
+		emitTopologyKernel<Source::LeafType><<<DivideRoundUp( nMax, EmitTile ), EmitTile, 0, stream>>>(
 			ctl, keys[0], vals[0], primRefs, sortedRefs, scratch, flags, taskQueue );
 		dev.mark( "emit+refit", stream );
 	}
@@ -183,7 +183,7 @@ void buildGeometry(
 		{
 			uint2*	  pairs = reinterpret_cast<uint2*>( temp + L.pairs );
 			uint32_t* scan	= reinterpret_cast<uint32_t*>( temp + L.pairScan );
-			const uint32_t tiles = DivideRoundUp( nMax, PairBlock );
+			const uint32_t tiles = DivideRoundUp( nMax, PairTile );
 			HIPRT_CUDA_CHECK( cudaMemsetAsync( scan, 0, size_t( tiles ) * 4, stream ) );
 			pairTrianglesKernel<<<tiles, PairBlock, 0, stream>>>( src, nMax, pairs, scan, ctl );
 			src.pairs = pairs;
@@ -280,10 +280,43 @@ void updateScene( const DeviceInfo&, const hiprtSceneBuildInput&, hiprtBuildOpti
 {
 	throw std::runtime_error( "scene update: not implemented yet" );
 }
-size_t batchTempSize( uint32_t ) { return 64; }
-void   buildGeometriesBatch(
-	  const DeviceInfo&, const hiprtGeometryBuildInput*, uint32_t, hiprtBuildOptions, void*, cudaStream_t, void* const* )
+// Batch of small geometries: the caller's host arrays (inputs, storage pointers) are copied into the
+// temporary buffer, then ONE launch builds everything (reference: BatchBuilder.h:58-132).
+size_t batchTempSize( uint32_t count )
 {
-	throw std::runtime_error( "batch build: not implemented yet" );
+	return alignUp( size_t( count ) * sizeof( hiprtGeometryBuildInput ) ) + alignUp( size_t( count ) * sizeof( void* ) );
+}
+
+void buildGeometriesBatch(
+	const DeviceInfo&			   dev,
+	const hiprtGeometryBuildInput* inputs,
+	uint32_t					   count,
+	hiprtBuildOptions			   options,
+	void*						   tempBuffer,
+	cudaStream_t				   stream,
+	void* const*				   storages )
+{
+	(void)options;
+	if ( count == 0 ) return;
+	for ( uint32_t i = 0; i < count; ++i )
+		if ( geometryPrimCount( inputs[i] ) > BatchMaxPrims ) throw std::runtime_error( "batch build: geometry exceeds hiprtMaxBatchBuildMaxPrimCount" );
+	uint8_t* temp	  = static_cast<uint8_t*>( tempBuffer );
+	auto*	 dInputs  = reinterpret_cast<hiprtGeometryBuildInput*>( temp );
+	auto*	 dStorage = reinterpret_cast<void**>( temp + alignUp( size_t( count ) * sizeof( hiprtGeometryBuildInput ) ) );
+	// pageable sources: the runtime stages them before returning, so the caller's arrays may go away
+	HIPRT_CUDA_CHECK( cudaMemcpyAsync( dInputs, inputs, size_t( count ) * sizeof( hiprtGeometryBuildInput ), cudaMemcpyHostToDevice, stream ) );
+	HIPRT_CUDA_CHECK( cudaMemcpyAsync( dStorage, storages, size_t( count ) * sizeof( void* ), cudaMemcpyHostToDevice, stream ) );
+	static bool configured = false; // same value every time: a benign race
+	if ( !configured )
+	{
+		HIPRT_CUDA_CHECK( cudaFuncSetAttribute( batchBuildKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int( sizeof( BatchSmem ) ) ) );
+		configured = true;
+	}
+	dev.beginProfile( stream );
+	const uint32_t gx = std::min( count, 65535u * 32u );
+	const dim3	   grid( gx, DivideRoundUp( count, gx ) );
+	batchBuildKernel<<<grid, BatchBlock, sizeof( BatchSmem ), stream>>>( dInputs, dStorage, count );
+	dev.mark( "batch", stream );
+	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
 } // namespace hiprt

@@ -37,6 +37,7 @@ namespace hiprt
 	} while ( 0 )
 
 static inline size_t alignUp( size_t v ) { return RoundUp( v, size_t( DefaultAlignment ) ); }
+__host__ __device__ inline size_t alignUpDev( size_t v ) { return ( v + DefaultAlignment - 1 ) / DefaultAlignment * DefaultAlignment; }
 
 constexpr uint32_t PairBlock = 256; // triangles per pairing tile
 
@@ -121,6 +122,8 @@ __global__ void __launch_bounds__( 256 ) initSceneKernel(
 // is atomic arrival order); made deterministic with a single-pass scan over 256-triangle tiles.
 constexpr uint32_t ScanAgg	= 1u << 30;
 constexpr uint32_t ScanIncl = 2u << 30;
+constexpr uint32_t PairItems = 8;					  // groups of 32 triangles per warp
+constexpr uint32_t PairTile	 = PairBlock * PairItems; // triangles per tile
 
 __global__ void __launch_bounds__( PairBlock )
 	pairTrianglesKernel( TriangleMeshSource mesh, uint32_t triCount, uint2* pairs, uint32_t* scanState, BuildControl* ctl )
@@ -131,33 +134,42 @@ __global__ void __launch_bounds__( PairBlock )
 	const uint32_t		lane = laneId(), warp = threadIdx.x >> 5;
 	if ( threadIdx.x == 0 ) sTile = atomicAdd( &ctl->pairTileCounter, 1u );
 	__syncthreads();
-	const uint32_t tile	 = sTile;
-	const uint32_t index = tile * PairBlock + threadIdx.x;
-	const bool	   valid = index < triCount;
-	uint3		   idx	 = make_uint3( 0, 0, 0 );
-	if ( valid ) idx = mesh.indices( index );
+	const uint32_t tile		= sTile;
+	const uint32_t warpBase = tile * PairTile + warp * ( 32 * PairItems );
 
-	uint32_t active	 = __ballot_sync( FullMask, valid );
-	uint32_t partner = InvalidValue; // set on the first triangle of each emitted pair
-	while ( active )
+	uint32_t partner[PairItems]; // set on the first triangle of each emitted pair
+	uint32_t emitMask[PairItems];
+	uint32_t warpTotal = 0;
+#pragma unroll
+	for ( uint32_t it = 0; it < PairItems; ++it )
 	{
-		const uint32_t a = __ffs( active ) - 1;
-		active &= active - 1;
-		const uint3 ia		 = make_uint3( __shfl_sync( FullMask, idx.x, a ), __shfl_sync( FullMask, idx.y, a ), __shfl_sync( FullMask, idx.z, a ) );
-		uint3		m;
-		const bool	pairable = ( ( active >> lane ) & 1u ) && TriangleMeshSource::mapIndices( ia, idx, m );
-		const uint32_t cand	 = __ballot_sync( FullMask, pairable );
-		uint32_t	   b	 = a;
-		if ( cand )
+		const uint32_t groupBase = warpBase + it * 32;
+		const uint32_t index	 = groupBase + lane;
+		const bool	   valid	 = index < triCount;
+		uint3		   idx		 = make_uint3( 0, 0, 0 );
+		if ( valid ) idx = mesh.indices( index );
+		uint32_t active = __ballot_sync( FullMask, valid );
+		partner[it]		= InvalidValue;
+		while ( active )
 		{
-			b = __ffs( cand ) - 1;
-			active &= ~( 1u << b );
+			const uint32_t a = __ffs( active ) - 1;
+			active &= active - 1;
+			const uint3 ia		 = make_uint3( __shfl_sync( FullMask, idx.x, a ), __shfl_sync( FullMask, idx.y, a ), __shfl_sync( FullMask, idx.z, a ) );
+			uint3		m;
+			const bool	pairable = ( ( active >> lane ) & 1u ) && TriangleMeshSource::mapIndices( ia, idx, m );
+			const uint32_t cand	 = __ballot_sync( FullMask, pairable );
+			uint32_t	   b	 = a;
+			if ( cand )
+			{
+				b = __ffs( cand ) - 1;
+				active &= ~( 1u << b );
+			}
+			if ( lane == a ) partner[it] = groupBase + b;
 		}
-		if ( lane == a ) partner = tile * PairBlock + ( warp << 5 ) + b;
+		emitMask[it] = __ballot_sync( FullMask, valid && partner[it] != InvalidValue );
+		warpTotal += __popc( emitMask[it] );
 	}
-	const bool	   emit		= valid && partner != InvalidValue;
-	const uint32_t emitMask = __ballot_sync( FullMask, emit );
-	if ( lane == 0 ) sWarpCount[warp] = __popc( emitMask );
+	if ( lane == 0 ) sWarpCount[warp] = warpTotal;
 	__syncthreads();
 	uint32_t warpOffset = 0, blockTotal = 0;
 #pragma unroll
@@ -166,32 +178,45 @@ __global__ void __launch_bounds__( PairBlock )
 		if ( w < warp ) warpOffset += sWarpCount[w];
 		blockTotal += sWarpCount[w];
 	}
-	if ( threadIdx.x == 0 )
+	if ( warp == 0 )
 	{
-		// decoupled look-back over preceding tiles
-		volatile uint32_t* st = scanState;
-		uint32_t		   prefix = 0;
-		if ( tile == 0 )
-			st[0] = ScanIncl | blockTotal;
-		else
+		// decoupled look-back over the preceding tiles, 32 tiles per step
+		if ( lane == 0 ) *reinterpret_cast<volatile uint32_t*>( scanState + tile ) = ( tile == 0 ? ScanIncl : ScanAgg ) | blockTotal;
+		uint32_t prefix = 0;
+		if ( tile > 0 )
 		{
-			st[tile] = ScanAgg | blockTotal;
-			int t	 = int( tile ) - 1;
+			int look = int( tile ) - 1;
 			while ( true )
 			{
-				const uint32_t v = st[t];
-				if ( ( v >> 30 ) == 0 ) continue;
-				prefix += v & ( ScanAgg - 1 );
-				if ( v & ScanIncl ) break;
-				--t;
+				const int	   t = look - int( lane );
+				const uint32_t v = t >= 0 ? ldVolatile( scanState + t ) : ScanIncl; // before the first tile: inclusive 0
+				if ( __any_sync( FullMask, ( v >> 30 ) == 0 ) ) continue;			// not all published yet
+				const uint32_t incl = __ballot_sync( FullMask, ( v & ScanIncl ) != 0 );
+				if ( incl )
+				{
+					const uint32_t first = __ffs( incl ) - 1;
+					prefix += __reduce_add_sync( FullMask, lane <= first ? ( v & ( ScanAgg - 1 ) ) : 0u );
+					break;
+				}
+				prefix += __reduce_add_sync( FullMask, v & ( ScanAgg - 1 ) );
+				look -= 32;
 			}
-			st[tile] = ScanIncl | ( prefix + blockTotal );
+			if ( lane == 0 ) *reinterpret_cast<volatile uint32_t*>( scanState + tile ) = ScanIncl | ( prefix + blockTotal );
 		}
-		sBase = prefix;
-		if ( tile == DivideRoundUp( triCount, PairBlock ) - 1 ) ctl->primCount = prefix + blockTotal;
+		if ( lane == 0 )
+		{
+			sBase = prefix;
+			if ( tile == DivideRoundUp( triCount, PairTile ) - 1 ) ctl->primCount = prefix + blockTotal;
+		}
 	}
 	__syncthreads();
-	if ( emit ) pairs[sBase + warpOffset + __popc( emitMask & laneMaskLt() )] = make_uint2( index, partner );
+	uint32_t out = sBase + warpOffset;
+#pragma unroll
+	for ( uint32_t it = 0; it < PairItems; ++it )
+	{
+		if ( ( emitMask[it] >> lane ) & 1u ) pairs[out + __popc( emitMask[it] & laneMaskLt() )] = make_uint2( warpBase + it * 32 + lane, partner[it] );
+		out += __popc( emitMask[it] );
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -272,8 +297,55 @@ __device__ __forceinline__ uint64_t gapDelta( const uint32_t* keys, uint32_t a, 
 	return ( uint64_t( k0 ^ k1 ) << 32 ) | uint64_t( a ^ ( a + 1 ) );
 }
 
+// Comparing two gap deltas is comparing the position of their highest set bit: for a sorted array two
+// gaps bounding a range can never share that position (the bit would have to go 0->1 twice without a
+// higher bit changing in between). A one-byte "level" per gap therefore replaces the 64-bit delta.
+__device__ __forceinline__ uint32_t gapLevel( const uint32_t* keys, uint32_t a, uint32_t n )
+{
+	if ( a >= n - 1 ) return 64u; // the ends of the array (also a == uint32(-1)): +infinity
+	const uint32_t x = keys[a] ^ keys[a + 1];
+	return x ? 63u - __clz( x ) : 31u - __clz( a ^ ( a + 1 ) );
+}
+
+// Tile-local version: a block owns EmitTile consecutive leaves. A node whose whole leaf range lies
+// inside the tile ("local": its gap level is below the maximum level on both sides within the tile,
+// found with two block-wide max scans) is resolved entirely in shared memory -- the first child to
+// arrive publishes {box, index} in its own thread slot and exchanges {range end, thread} through a
+// shared-memory flag; the second one unites and writes the finished 32-byte binary node with ONE
+// global store. Only the few nodes whose range crosses a tile boundary (~depth x N/EmitTile of them)
+// go through global flags and L2 as in the reference.
+constexpr uint32_t EmitTile = 512;
+
+__device__ __forceinline__ uint32_t blockExclusiveMaxScan( uint32_t v, bool reverse, uint32_t* warpTotals )
+{
+	const uint32_t lane = laneId(), warp = threadIdx.x >> 5;
+	uint32_t	   x	= v;
+#pragma unroll
+	for ( int o = 1; o < 32; o <<= 1 )
+	{
+		const uint32_t y = reverse ? __shfl_down_sync( FullMask, x, o ) : __shfl_up_sync( FullMask, x, o );
+		if ( reverse ? ( lane + o < 32 ) : ( lane >= uint32_t( o ) ) ) x = max( x, y );
+	}
+	if ( lane == ( reverse ? 0u : 31u ) ) warpTotals[warp] = x;
+	__syncthreads();
+	uint32_t excl = reverse ? __shfl_down_sync( FullMask, x, 1 ) : __shfl_up_sync( FullMask, x, 1 );
+	if ( lane == ( reverse ? 31u : 0u ) ) excl = 0;
+	constexpr uint32_t Warps = EmitTile / 32;
+	if ( reverse )
+	{
+		for ( uint32_t w = warp + 1; w < Warps; ++w )
+			excl = max( excl, warpTotals[w] );
+	}
+	else
+	{
+		for ( uint32_t w = 0; w < warp; ++w )
+			excl = max( excl, warpTotals[w] );
+	}
+	return excl;
+}
+
 template <uint32_t LeafType>
-__global__ void __launch_bounds__( 256 ) emitTopologyKernel(
+__global__ void __launch_bounds__( EmitTile ) emitTopologyKernel(
 	BuildControl*	ctl,
 	const uint32_t* sortedKeys,
 	const uint32_t* sortedVals,
@@ -283,38 +355,84 @@ __global__ void __launch_bounds__( 256 ) emitTopologyKernel(
 	uint32_t*		flags,
 	uint64_t*		taskQueue )
 {
-	const uint32_t n = ctl->primCount;
-	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	__shared__ float4	sOwn[EmitTile][2];		// {box, index} published by a thread that stops at a local node
+	__shared__ uint32_t sFlag[EmitTile];		// local gaps: {relative far range end << 16 | thread} of the first arriver
+	__shared__ uint8_t	sLevel[EmitTile + 1];	// gap base-1+g: level (bits 0-6), local (bit 7)
+	__shared__ uint32_t sWarpMax[2][EmitTile / 32];
+
+	const uint32_t n	= ctl->primCount;
+	const uint32_t t	= threadIdx.x;
+	const uint32_t base = blockIdx.x * EmitTile;
+	if ( base >= n ) return;
+	const uint32_t k = base + t;
+
+	// ---- gap levels of the tile and which gaps are local
+	const uint32_t lv	   = gapLevel( sortedKeys, k - 1u, n ); // my left gap
+	const uint32_t lvRight = gapLevel( sortedKeys, base + EmitTile - 1u, n );
+	sFlag[t]			   = InvalidValue;
+	const uint32_t maxLeft	= blockExclusiveMaxScan( lv, false, sWarpMax[0] );
+	const uint32_t maxRight = max( blockExclusiveMaxScan( lv, true, sWarpMax[1] ), lvRight );
+	const bool	   isLocal	= t >= 1 && lv < maxLeft && lv < maxRight;
+	sLevel[t]				= uint8_t( lv | ( isLocal ? 0x80u : 0u ) );
+	if ( t == 0 ) sLevel[EmitTile] = uint8_t( lvRight );
+	__syncthreads();
 	if ( k >= n ) return;
+
+	auto levelOf = [&]( uint32_t gap ) -> uint32_t {
+		const uint32_t g = gap + 1u - base; // position inside the tile's gap array (wraps for gaps left of the tile)
+		return g <= EmitTile ? ( sLevel[g] & 0x7Fu ) : gapLevel( sortedKeys, gap, n );
+	};
+
 	const uint32_t prim = sortedVals[k];
 	DBox		   box	= loadRec( primRefs, prim ).box;
 	storeRec( sortedRefs, k, box, prim, 0u );
 
-	uint32_t i = k, j = k + 1; // covered leaf range [i, j)
-	uint32_t self = makeNodeIndex( k, LeafType );
+	uint32_t  i = k, j = k + 1; // covered leaf range [i, j)
+	uint32_t  self		   = makeNodeIndex( k, LeafType );
 	uint32_t* scratchWords = reinterpret_cast<uint32_t*>( scratch );
 	while ( true )
 	{
-		const bool	   left	  = ( i == 0 ) || ( j != n && gapDelta( sortedKeys, j - 1, n ) < gapDelta( sortedKeys, i - 1, n ) );
+		const bool	   left	  = ( i == 0 ) || ( j != n && levelOf( j - 1 ) < levelOf( i - 1 ) );
 		const uint32_t parent = left ? j - 1 : i - 1;
-		scratchWords[size_t( parent ) * 8 + ( left ? 6 : 7 )] = self;
-		__threadfence();
-		const uint32_t other = atomicExch( &flags[parent], left ? i : j );
-		if ( other == InvalidValue ) return; // first to arrive: the sibling finishes the node
-		__threadfence();
-		if ( left )
-			j = other;
+		const uint32_t g	  = parent + 1u - base;
+		if ( g < EmitTile && ( sLevel[g] & 0x80u ) )
+		{
+			// ---- both children live in this tile: shared-memory handshake
+			sOwn[t][0] = make_float4( box.lo.x, box.lo.y, box.lo.z, box.hi.x );
+			sOwn[t][1] = make_float4( box.hi.y, box.hi.z, __uint_as_float( self ), 0.0f );
+			__threadfence_block();
+			const uint32_t other = atomicExch( &sFlag[g], ( ( ( left ? i : j ) - base ) << 16 ) | t );
+			if ( other == InvalidValue ) return; // first to arrive: the sibling finishes the node
+			__threadfence_block();
+			const float4   q0 = sOwn[other & 0xFFFFu][0], q1 = sOwn[other & 0xFFFFu][1];
+			const uint32_t sib = __float_as_uint( q1.z );
+			if ( left )
+				j = base + ( other >> 16 );
+			else
+				i = base + ( other >> 16 );
+			box = uniteBox( box, DBox{ make_float3( q0.x, q0.y, q0.z ), make_float3( q0.w, q1.x, q1.y ) } );
+			storeRec( scratch, parent, box, left ? self : sib, left ? sib : self );
+		}
 		else
-			i = other;
-		// sibling record: its index was stored in the parent's other child slot
-		const uint32_t sib	  = __ldcg( &scratchWords[size_t( parent ) * 8 + ( left ? 7 : 6 )] );
-		const Rec32	   sibRec = isBoxIndex( sib ) ? loadRecCg( scratch, nodeAddr( sib ) ) : loadRecCg( sortedRefs, nodeAddr( sib ) );
-		box					  = uniteBox( box, sibRec.box );
-		// write the node's box (children words are already in place)
-		float4* dst = reinterpret_cast<float4*>( scratch ) + 2 * size_t( parent );
-		dst[0]		= make_float4( box.lo.x, box.lo.y, box.lo.z, box.hi.x );
-		reinterpret_cast<float2*>( dst + 1 )[0] = make_float2( box.hi.y, box.hi.z );
-		self									= makeNodeIndex( parent, BoxType );
+		{
+			// ---- range crosses the tile boundary: global flags, sibling record through L2
+			scratchWords[size_t( parent ) * 8 + ( left ? 6 : 7 )] = self;
+			__threadfence();
+			const uint32_t other = atomicExch( &flags[parent], left ? i : j );
+			if ( other == InvalidValue ) return;
+			__threadfence();
+			if ( left )
+				j = other;
+			else
+				i = other;
+			const uint32_t sib	  = __ldcg( &scratchWords[size_t( parent ) * 8 + ( left ? 7 : 6 )] );
+			const Rec32	   sibRec = isBoxIndex( sib ) ? loadRecCg( scratch, nodeAddr( sib ) ) : loadRecCg( sortedRefs, nodeAddr( sib ) );
+			box					  = uniteBox( box, sibRec.box );
+			float4* dst = reinterpret_cast<float4*>( scratch ) + 2 * size_t( parent );
+			dst[0]		= make_float4( box.lo.x, box.lo.y, box.lo.z, box.hi.x );
+			reinterpret_cast<float2*>( dst + 1 )[0] = make_float2( box.hi.y, box.hi.z );
+		}
+		self = makeNodeIndex( parent, BoxType );
 		if ( i == 0 && j == n )
 		{
 			ctl->rootNode = parent;
@@ -336,9 +454,12 @@ __global__ void __launch_bounds__( 256 ) emitTopologyKernel(
 // B200 version: the window lives in REGISTERS (one cluster per lane: id + box); neighbour boxes
 // come from shfl_down, the distance of the mirrored pair from shfl_up, compaction from a ballot
 // and __fns -- no shared memory, no shared-memory atomics. Distances are ordered by the 64-bit key
-// (area bits, lower position, higher position): a total order over pairs, so the globally
-// closest pair is always mutual and every round makes progress; the tree shape depends only on
-// the sorted keys and boxes (node ADDRESSES depend on atomic order, as in the reference).
+// (area bits, distance in positions, parity of the lower position, lower position): a total order
+// over pairs, so the globally closest pair is always mutual and every round makes progress; on
+// exact area ties (identical primitives) neighbours pair up as (0,1),(2,3),... and the window halves
+// every round instead of degenerating into a chain (the reference gets the same effect from the
+// parity bit of its encodeOffset, PlocBuilderKernels.h:54-65). The tree shape depends only on the
+// sorted keys and boxes (node ADDRESSES depend on atomic order, as in the reference).
 constexpr uint32_t PlocRadius = 8;
 constexpr uint32_t PlocWindow = 32; // clusters held by a warp: 16 from each side of the split
 constexpr uint32_t PlocBlock  = 256;
@@ -439,13 +560,15 @@ __global__ void __launch_bounds__( PlocBlock ) hplocKernel(
 				{
 					const DBox	   nb	 = shflDownBox( box, d );
 					const bool	   valid = lane + d < count;
-					const uint64_t fwd	 = valid ? ( ( uint64_t( __float_as_uint( boxArea( uniteBox( box, nb ) ) ) ) << 32 ) | ( lane << 8 ) | ( lane + d ) ) : ~0ull;
+					const uint64_t fwd	 = valid ? ( ( uint64_t( __float_as_uint( boxArea( uniteBox( box, nb ) ) ) ) << 32 ) | ( ( d - 1u ) << 11 ) |
+												 ( ( lane & 1u ) << 10 ) | ( lane << 5 ) | ( lane + d ) )
+											   : ~0ull;
 					const uint64_t bwd	 = shflUpU64( fwd, d ); // the pair (lane - d, lane), computed by lane - d
 					best				 = min( best, fwd );
 					if ( lane >= d ) best = min( best, bwd );
 				}
 				const bool	   has	  = lane < count; // count > 1 here, so every live lane has a neighbour
-				const uint32_t pa	  = ( uint32_t( best ) >> 8 ) & 0xFFu, pb = uint32_t( best ) & 0xFFu;
+				const uint32_t pa	  = ( uint32_t( best ) >> 5 ) & 31u, pb = uint32_t( best ) & 31u;
 				const uint32_t nbLane = has ? ( pa == lane ? pb : pa ) : lane;
 				const uint64_t nbBest = shflU64( best, nbLane );
 				const bool	   mutual = has && nbBest == best;

@@ -1,0 +1,68 @@
+"""Multi-GPU plumbing: one process per GPU, the BVH is replicated (every rank builds it
+from the same input), work is sharded with NO data-path exchange:
+
+  * image tiles: tile i of a row-major tiling goes to rank i mod world (interleaving balances sky / geometry tiles);
+  * batch builds: the geometry list is split into contiguous slices;
+  * the only collectives are the framebuffer gather to rank 0 and the timing reductions.
+
+The reference is single-GPU (no collective call sites: SURVEY.md section 2); this module is the new part.
+Works on any torch.distributed backend (NCCL over NVLink on the GPU box, gloo in the CPU tests).
+"""
+import numpy as np
+
+
+def tile_grid(width, height, tile=64):
+    return (width + tile - 1) // tile, (height + tile - 1) // tile
+
+
+def tiles_of_rank(width, height, rank, world, tile=64):
+    """Indices (row-major over the tile grid) of the tiles rank `rank` renders."""
+    tx, ty = tile_grid(width, height, tile)
+    return np.arange(rank, tx * ty, world, dtype=np.int64)
+
+
+def tile_pixels(width, height, tile_index, tile=64):
+    """Pixel indices (row-major over the image) of one tile, clipped to the image; tile-local row-major order."""
+    tx, _ = tile_grid(width, height, tile)
+    x0, y0 = (tile_index % tx) * tile, (tile_index // tx) * tile
+    xs = np.arange(x0, min(x0 + tile, width), dtype=np.int64)
+    ys = np.arange(y0, min(y0 + tile, height), dtype=np.int64)
+    return (ys[:, None] * width + xs[None, :]).reshape(-1)
+
+
+def pixels_of_rank(width, height, rank, world, tile=64):
+    t = tiles_of_rank(width, height, rank, world, tile)
+    if len(t) == 0:
+        return np.zeros(0, np.int64)
+    return np.concatenate([tile_pixels(width, height, int(i), tile) for i in t])
+
+
+def split_batch(count, rank, world):
+    """Contiguous slice [begin, end) of a list of `count` independent geometries for this rank."""
+    base, extra = divmod(count, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def gather_framebuffer(local_values, width, height, rank, world, tile=64, dist=None, dst=0):
+    """Gather per-pixel values rendered by each rank (in pixels_of_rank order; any trailing shape/dtype torch supports)
+    into the full row-major image on rank `dst`. Returns the image there, None elsewhere."""
+    import torch
+
+    if world == 1:
+        out = torch.empty((width * height,) + tuple(local_values.shape[1:]), dtype=local_values.dtype, device=local_values.device)
+        out[torch.from_numpy(pixels_of_rank(width, height, 0, 1, tile)).to(local_values.device)] = local_values
+        return out
+    counts = [len(pixels_of_rank(width, height, r, world, tile)) for r in range(world)]
+    most = max(counts)
+    padded = torch.zeros((most,) + tuple(local_values.shape[1:]), dtype=local_values.dtype, device=local_values.device)
+    padded[: len(local_values)] = local_values
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bufs, dst=dst)
+    if rank != dst:
+        return None
+    out = torch.empty((width * height,) + tuple(local_values.shape[1:]), dtype=local_values.dtype, device=local_values.device)
+    for r in range(world):
+        idx = torch.from_numpy(pixels_of_rank(width, height, r, world, tile)).to(local_values.device)
+        out[idx] = bufs[r][: counts[r]]
+    return out

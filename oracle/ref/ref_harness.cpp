@@ -107,6 +107,9 @@ int ref_build_geometry(
 	mesh.vertices	  = g->dVerts;
 	mesh.vertexCount  = vertCount;
 	mesh.vertexStride = 12;
+	// non-indexed meshes: the reference sizes its buffers from triangleCount (BvhCommon.h:89-99) although its
+	// TriangleMesh falls back to vertexCount / 3 (TriangleMesh.h:66) -- so the count must always be given
+	mesh.triangleCount = vertCount / 3;
 	if ( indices )
 	{
 		CUDA_CHECK( cudaMalloc( &g->dIdx, size_t( triCount ) * 12 ) );

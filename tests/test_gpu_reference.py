@@ -41,7 +41,10 @@ def test_hits_match_reference(ctx, case, flags):
     if rays is None:
         lo, hi = verts.min(0), verts.max(0)
         rays = scenes.random_rays(30000, lo - 0.1, hi + 0.1, seed=5)
-    rg = ref.RefGeometry(verts, idx, build_flags=flags)
+    # The reference is always built with its LBVH: its H-PLOC kernel dies with an illegal memory access on sm_100
+    # (it shuffles under __activemask() inside divergent loops: PlocBuilderKernels.h:150-200), see DESIGN.md section 5.
+    # Hits do not depend on the builder, so OUR balanced build is checked against THEIR fast build.
+    rg = ref.RefGeometry(verts, idx, build_flags=api.FAST_BUILD)
     theirs, _ = rg.trace(rays, kind=2)
     geom = ctx.build(to_dev(ctx, verts), None if idx is None else to_dev(ctx, idx), flags=flags)
     ours = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays)))
@@ -98,13 +101,13 @@ def test_scene_hits_match_reference(ctx):
     geoms = [ctx.build(to_dev(ctx, v), to_dev(ctx, i)) for v, i in meshes]
     scene = ctx.build_scene([geoms[g] for g in geom_of], frames)
     ours = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays)))
-    ties = compare_hits(ours, theirs, rel=5e-5)
+    ties = compare_hits(ours, theirs, rel=5e-5, uv_tol=1e-3)  # see tests/test_gpu_scene.py SCENE_UV_TOL
     hit = (ours["primID"] == theirs["primID"]) & (theirs["primID"] != api.INVALID)
     assert hit.mean() > 0.05
     assert np.array_equal(ours["instanceIDs"][hit, 0], theirs["instanceIDs"][hit, 0])
     assert ties <= 0.002 * len(rays)
     # their traversal on our scene (instance nodes point at our geometries)
     cross, _ = ref.trace_scene(scene.h, rays, kind=2)
-    compare_hits(cross, theirs, rel=5e-5)
+    compare_hits(cross, theirs, rel=5e-5, uv_tol=1e-3)
     rs.destroy()
     scene.destroy()

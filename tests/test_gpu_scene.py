@@ -42,6 +42,14 @@ def check_scene_structure(scene, oscene):
     np.testing.assert_allclose(cl["invMatrix"], ol["invMatrix"], rtol=1e-5, atol=1e-6)
 
 
+# Barycentrics inside an instance are conditioned by (distance to the instance) / (triangle edge): the world ray is
+# moved into object space with a matrix that the GPU and the CPU oracle (and the reference, whose build kernels use
+# fast-math) compute with different rounding, so an object-space offset of a few 1e-6 turns into ~1e-4 in uv on the
+# small triangles of these meshes. t is unaffected (the direction is not re-normalised). Exact-arithmetic
+# transforms (test_integer_translations_are_exact) are held to the strict 1e-5.
+SCENE_UV_TOL = 1e-3
+
+
 def camera_rays(extent, n=192):
     return scenes.pinhole_rays(n, n, (0.0, 0.3 * extent, 2.6 * extent), (0, 0, 0))
 
@@ -74,8 +82,8 @@ def test_instanced_scene_hits_match_oracle(ctx, n_inst):
     got = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays)))
     ref = oscene.trace(rays)
     hit = ref["primID"] != orc.INVALID
-    assert hit.mean() > 0.05
-    ties = compare_hits(got, ref, rel=2e-5)
+    assert hit.mean() > (0.05 if n_inst >= 100 else 0.005)
+    ties = compare_hits(got, ref, rel=2e-5, uv_tol=SCENE_UV_TOL)
     same = got["primID"] == ref["primID"]
     assert np.array_equal(got["instanceIDs"][same & hit, 0], ref["instanceIDs"][same & hit, 0])
     assert ties <= 0.001 * len(rays)
@@ -96,7 +104,7 @@ def test_ray_mask_culls_instances(ctx):
     for ray_mask in (0x1, 0x2, 0x3):
         got = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays), mask=ray_mask))
         ref = oscene.trace(rays, ray_mask=ray_mask)
-        compare_hits(got, ref, rel=2e-5)
+        compare_hits(got, ref, rel=2e-5, uv_tol=SCENE_UV_TOL)
         hit = got["primID"] != api.INVALID
         if ray_mask != 0x3:
             assert np.all(masks[got["instanceIDs"][hit, 0]] == ray_mask)
@@ -118,5 +126,24 @@ def test_srt_frames(ctx):
     rays = camera_rays(4.0, 128)
     got = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays)))
     ref = oscene.trace(rays)
-    compare_hits(got, ref, rel=5e-5)
+    compare_hits(got, ref, rel=5e-5, uv_tol=SCENE_UV_TOL)
+    scene.destroy()
+
+
+def test_integer_translations_are_exact(ctx):
+    """Pure translations by small integers: the inverse matrix and the object-space ray are exact in fp32 when the
+    ray origin is representable, so hits must agree with the oracle to the strict tolerance."""
+    meshes = scenes.instanced_geometries(3)
+    n_inst = 27
+    frames = np.zeros((n_inst, 16), np.float32)
+    frames[:, [0, 5, 10]] = 1.0
+    g = np.stack(np.meshgrid(np.arange(3), np.arange(3), np.arange(3), indexing="ij"), -1).reshape(-1, 3)
+    frames[:, [3, 7, 11]] = (g * 4 - 4).astype(np.float32)
+    geoms, scene, oscene = build_pair(ctx, meshes, np.arange(n_inst) % 3, frames)
+    rays = scenes.pinhole_rays(160, 160, (0.0, 2.0, 16.0), (0, 0, 0))
+    got = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays)))
+    ref = oscene.trace(rays)
+    assert (ref["primID"] != orc.INVALID).mean() > 0.05
+    compare_hits(got, ref, rel=1e-5)
+    assert np.array_equal(got["instanceIDs"][:, 0], ref["instanceIDs"][:, 0])
     scene.destroy()
