@@ -177,7 +177,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        primary = scenes.pinhole_rays(WIDTH, HEIGHT, wl["eye"], wl["look"])
+        primary = scenes.pinhole_rays(WIDTH, HEIGHT, wl["eye"], wl["look"])[scenes.tile_order(WIDTH, HEIGHT)]
         r = embree_arm(verts, idx, primary, wl["light"], args.steps, args.warmup, host_threads)
         kind = "reference"
         if r is None:
@@ -226,7 +226,7 @@ def main():
 
     # every rank traces its own frame (weak scaling): the camera is nudged per rank
     eye = np.array(wl["eye"], np.float64) + np.array([0.01 * rank, 0.005 * rank, 0.0])
-    primary = scenes.pinhole_rays(WIDTH, HEIGHT, eye, wl["look"])
+    primary = scenes.pinhole_rays(WIDTH, HEIGHT, eye, wl["look"])[scenes.tile_order(WIDTH, HEIGHT)]
     d_primary = ctx.rays_to_device(primary)
     hits0 = ctx.hits_to_host(ctx.trace(geom, d_primary))
     shadow, _ = scenes.shadow_rays(primary, hits0, wl["light"])
@@ -336,7 +336,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "triangles": n_tris, "primitives_after_pairing": n_prims, "build": "PreferFastBuild (LBVH)",
                        "resolution": [WIDTH, HEIGHT], "rays_per_step_per_gpu": n_rays, "primary_rays": n_primary, "shadow_rays": n_shadow,
-                       "l2": "256 MiB flush write before every timed step", "bvh": "replicated per GPU", "sharding": "one frame-sized ray batch per GPU"},
+                       "l2": "256 MiB flush write before every timed step", "bvh": "replicated per GPU", "sharding": "one frame-sized ray batch per GPU",
+                       "ray_order": "8x4 pixel tiles (the reference's tests launch 8x8 / 2-D blocks); same order for every arm"},
             "build": {"mtris_per_s": round(n_tris * world * args.steps / build_total_ms / 1e3, 2), "ms_per_build": round(build_ms_avg, 4),
                       "bytes_per_triangle_model": round(sum(algo.values()) / n_tris, 1),
                       "achieved_gbs": round(sum(algo.values()) / (build_ms_avg * 1e-3) / 1e9, 1),

@@ -459,6 +459,11 @@ class Geometry:
         self.ctx.torch.cuda.synchronize()
         return self.ctx.read_device(self.h.value, 48).view(GEOM_HEADER_DTYPE)[0]
 
+    def build_error_flag(self):
+        """Non-zero when the last build that used this temporary buffer hit its watchdog (BuildControl.pad[0])."""
+        self.ctx.torch.cuda.synchronize()
+        return int(self.temp[44:48].cpu().numpy().view(np.uint32)[0])
+
     def nodes(self):
         """(box nodes, triangle-pair leaves) copied to the host."""
         h = self.header()

@@ -64,7 +64,8 @@ __device__ void batchBuildOne( BatchSmem& s, Source src, uint32_t n, uint32_t ge
 			if ( n == 1 )
 			{
 				const DBox b = src.box( 0 );
-				src.writeLeaf( leafNodes, 0, 0 );
+				const uint2 w = src.refWords( 0 );
+				src.writeLeaf( leafNodes, 0, w.x, w.y );
 				node.child[0] = makeNodeIndex( 0, Source::LeafType );
 				node.box[0]	  = Box{ { b.lo.x, b.lo.y, b.lo.z }, { b.hi.x, b.hi.y, b.hi.z } };
 			}
@@ -269,7 +270,8 @@ __device__ void batchBuildOne( BatchSmem& s, Source src, uint32_t n, uint32_t ge
 			if ( leaf )
 			{
 				const uint32_t addr = lbase + __popc( lmask & laneMaskLt() );
-				src.writeLeaf( leafNodes, addr, w0 );
+				const uint2 w = src.refWords( w0 );
+				src.writeLeaf( leafNodes, addr, w.x, w.y );
 				outChild = makeNodeIndex( addr, Source::LeafType );
 			}
 			if ( ready )

@@ -51,6 +51,7 @@ __global__ void initGeometryKernel(
 	ctl->queueHead		 = 0;
 	ctl->pairTileCounter = 0;
 	ctl->nodeCounter	 = 0;
+	ctl->pad[0]			 = 0; // build error flag
 	header->boxNodes	  = boxNodes;
 	header->primNodes	  = primNodes;
 	header->size		  = size;
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__( 256 ) initSceneKernel(
 		ctl->rootNode		 = InvalidValue;
 		ctl->queueHead		 = 0;
 		ctl->pairTileCounter = 0;
-	ctl->nodeCounter	 = 0;
+		ctl->nodeCounter	 = 0;
+		ctl->pad[0]			 = 0; // build error flag
 		header->boxNodes	   = boxNodes;
 		header->primNodes	   = instNodes;
 		header->instances	   = records;
@@ -150,13 +152,24 @@ __global__ void __launch_bounds__( PairBlock )
 		if ( valid ) idx = mesh.indices( index );
 		uint32_t active = __ballot_sync( FullMask, valid );
 		partner[it]		= InvalidValue;
+		// Fast path for the common layout (quad diagonals are consecutive triangles): if the lowest active
+		// triangle a can pair with a+1 and a+1 is still active, a+1 IS the lowest candidate, so the greedy
+		// rule picks it; such steps need no broadcast, only bit operations on warp-uniform masks.
+		const uint3	   in = make_uint3( __shfl_down_sync( FullMask, idx.x, 1 ), __shfl_down_sync( FullMask, idx.y, 1 ), __shfl_down_sync( FullMask, idx.z, 1 ) );
+		const uint32_t nextOk = __ballot_sync( FullMask, lane < 31 && TriangleMeshSource::sharesEdge( idx, in ) ) & ( active >> 1 );
+		uint32_t	   fastHeads = 0;
 		while ( active )
 		{
 			const uint32_t a = __ffs( active ) - 1;
+			if ( ( nextOk >> a ) & ( active >> ( a + 1 ) ) & 1u )
+			{
+				fastHeads |= 1u << a;
+				active &= ~( 3u << a );
+				continue;
+			}
 			active &= active - 1;
 			const uint3 ia		 = make_uint3( __shfl_sync( FullMask, idx.x, a ), __shfl_sync( FullMask, idx.y, a ), __shfl_sync( FullMask, idx.z, a ) );
-			uint3		m;
-			const bool	pairable = ( ( active >> lane ) & 1u ) && TriangleMeshSource::mapIndices( ia, idx, m );
+			const bool	pairable = ( ( active >> lane ) & 1u ) && TriangleMeshSource::sharesEdge( ia, idx );
 			const uint32_t cand	 = __ballot_sync( FullMask, pairable );
 			uint32_t	   b	 = a;
 			if ( cand )
@@ -166,6 +179,7 @@ __global__ void __launch_bounds__( PairBlock )
 			}
 			if ( lane == a ) partner[it] = groupBase + b;
 		}
+		if ( ( fastHeads >> lane ) & 1u ) partner[it] = groupBase + lane + 1;
 		emitMask[it] = __ballot_sync( FullMask, valid && partner[it] != InvalidValue );
 		warpTotal += __popc( emitMask[it] );
 	}
@@ -229,8 +243,9 @@ __global__ void __launch_bounds__( 256 ) primBoxesKernel( Source src, BuildContr
 	DBox		   mine = emptyBox();
 	for ( uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x )
 	{
-		const DBox b = src.box( p );
-		storeRec( primRefs, p, b, p, 0u );
+		const DBox	b = src.box( p );
+		const uint2 w = src.refWords( p );
+		storeRec( primRefs, p, b, w.x, w.y );
 		mine = uniteBox( mine, b );
 	}
 	mine = warpUniteBox( mine );
@@ -314,7 +329,7 @@ __device__ __forceinline__ uint32_t gapLevel( const uint32_t* keys, uint32_t a, 
 // shared-memory flag; the second one unites and writes the finished 32-byte binary node with ONE
 // global store. Only the few nodes whose range crosses a tile boundary (~depth x N/EmitTile of them)
 // go through global flags and L2 as in the reference.
-constexpr uint32_t EmitTile = 512;
+constexpr uint32_t EmitTile = 256;
 
 __device__ __forceinline__ uint32_t blockExclusiveMaxScan( uint32_t v, bool reverse, uint32_t* warpTotals )
 {
@@ -383,9 +398,9 @@ __global__ void __launch_bounds__( EmitTile ) emitTopologyKernel(
 		return g <= EmitTile ? ( sLevel[g] & 0x7Fu ) : gapLevel( sortedKeys, gap, n );
 	};
 
-	const uint32_t prim = sortedVals[k];
-	DBox		   box	= loadRec( primRefs, prim ).box;
-	storeRec( sortedRefs, k, box, prim, 0u );
+	const Rec32 mine = loadRec( primRefs, sortedVals[k] );
+	DBox		box	 = mine.box;
+	storeRec( sortedRefs, k, box, mine.a, mine.b );
 
 	uint32_t  i = k, j = k + 1; // covered leaf range [i, j)
 	uint32_t  self		   = makeNodeIndex( k, LeafType );
@@ -506,9 +521,8 @@ __global__ void __launch_bounds__( PlocBlock ) hplocKernel(
 	bool		   active = k < n;
 	if ( active )
 	{
-		const uint32_t prim = sortedVals[k];
-		const DBox	   box	= loadRec( primRefs, prim ).box;
-		storeRec( sortedRefs, k, box, prim, 0u );
+		const Rec32 mine = loadRec( primRefs, sortedVals[k] );
+		storeRec( sortedRefs, k, mine.box, mine.a, mine.b );
 		__stcg( &clusterIds[k], makeNodeIndex( k, LeafType ) );
 	}
 	uint32_t i = k, j = k + 1, s = k;
@@ -639,13 +653,47 @@ __global__ void __launch_bounds__( CollapseBlock ) collapsePackKernel(
 	const uint32_t group = lane >> 2, slot = lane & 3u;
 	const uint32_t groupMask = 0xFu << ( group * 4 );
 
-	uint32_t idlePolls = 0; // safety net: a corrupted tree must not hang the device
+	uint32_t idlePolls	 = 0; // safety net: a corrupted tree must not hang the device
+	uint32_t packedLocal = 0; // lane 0: leaves packed by this warp and not yet added to the global count
+	// "every leaf is packed" is the termination signal; the count is only flushed when a warp runs dry
+	auto finished = [&]() -> bool {
+		uint32_t packed = 0;
+		if ( lane == 0 )
+		{
+			if ( packedLocal ) atomicAdd( primNodeCounter, packedLocal ), packedLocal = 0;
+			packed = ldVolatile( primNodeCounter );
+		}
+		return __shfl_sync( FullMask, packed, 0 ) >= n;
+	};
 	while ( true )
 	{
-		uint32_t base = 0;
-		if ( lane == 0 ) base = atomicAdd( &ctl->queueHead, 8u );
-		base				   = __shfl_sync( FullMask, base, 0 );
-		if ( base >= maxBoxNodes ) return; // the queue is exhausted: every slot is owned by some warp
+		// claim 8 task slots, but only slots that have been allocated (their tasks are about to be published):
+		// warps do not run ahead of the producers and hammer L2 with polls
+		uint32_t base = InvalidValue;
+		while ( true )
+		{
+			uint32_t ok = 0;
+			if ( lane == 0 )
+			{
+				// (an add, not a compare-and-swap: every contender gets its own batch in one round; claims may run a
+				// little past the allocated slots when many warps pass the test at once, those warps simply wait)
+				if ( ldVolatile( &ctl->queueHead ) < ldVolatile( boxNodeCounter ) ) base = atomicAdd( &ctl->queueHead, 8u ), ok = 1;
+			}
+			if ( __shfl_sync( FullMask, ok, 0 ) ) break;
+			if ( finished() ) return;
+			if ( ++idlePolls > ( 1u << 20 ) )
+			{
+				if ( lane == 0 ) ctl->pad[0] = 1; // build error flag
+				return;
+			}
+			__nanosleep( 200 );
+		}
+		base = __shfl_sync( FullMask, base, 0 );
+		if ( base >= maxBoxNodes ) // ran past the end of the queue: nothing to do here (flush the leaf count first)
+		{
+			finished();
+			return;
+		}
 		const uint32_t taskIdx = base + group;
 		bool		   done	   = taskIdx >= maxBoxNodes; // such a slot can never be produced
 		uint64_t	   task	   = ~0ull;
@@ -661,14 +709,13 @@ __global__ void __launch_bounds__( CollapseBlock ) collapsePackKernel(
 			if ( !__any_sync( FullMask, ready ) )
 			{
 				// nothing arrived: stop once every leaf is packed (no task can appear any more)
-				uint32_t packed = 0;
-				if ( lane == 0 ) packed = ldVolatile( primNodeCounter );
-				if ( __shfl_sync( FullMask, packed, 0 ) >= n ) return;
-				if ( ++idlePolls > ( 1u << 22 ) )
+				if ( finished() ) return;
+				if ( ++idlePolls > ( 1u << 20 ) )
 				{
 					if ( lane == 0 ) ctl->pad[0] = 1; // build error flag
 					return;
 				}
+				__nanosleep( 100 );
 				continue;
 			}
 			idlePolls = 0;
@@ -721,14 +768,13 @@ __global__ void __launch_bounds__( CollapseBlock ) collapsePackKernel(
 			// warp-aggregated allocation of box nodes (= task slots) and leaf nodes
 			const uint32_t imask = __ballot_sync( FullMask, internal );
 			const uint32_t lmask = __ballot_sync( FullMask, leaf );
-			uint32_t	   ibase = 0, lbase = 0;
+			uint32_t	   ibase = 0;
 			if ( lane == 0 )
 			{
 				if ( imask ) ibase = atomicAdd( boxNodeCounter, __popc( imask ) );
-				if ( lmask ) lbase = atomicAdd( primNodeCounter, __popc( lmask ) );
+				packedLocal += __popc( lmask );
 			}
 			ibase			  = __shfl_sync( FullMask, ibase, 0 );
-			lbase			  = __shfl_sync( FullMask, lbase, 0 );
 			uint32_t outChild = InvalidValue;
 			if ( internal )
 			{
@@ -738,8 +784,9 @@ __global__ void __launch_bounds__( CollapseBlock ) collapsePackKernel(
 			}
 			if ( leaf )
 			{
-				const uint32_t addr = lbase + __popc( lmask & laneMaskLt() );
-				src.writeLeaf( leafNodes, addr, w0 );
+				// leaf address = sorted position: no allocation, Morton-ordered (cache friendly) leaf array
+				const uint32_t addr = nodeAddr( child );
+				src.writeLeaf( leafNodes, addr, w0, w1 );
 				outChild = makeNodeIndex( addr, Source::LeafType );
 			}
 
@@ -777,8 +824,9 @@ __global__ void __launch_bounds__( CollapseBlock ) collapsePackKernel(
 template <typename Source>
 __global__ void singletonKernel( Source src, uint32_t* primNodeCounter, Box4Node* boxNodes, void* leafNodes )
 {
-	const DBox b = src.box( 0 );
-	src.writeLeaf( leafNodes, 0, 0 );
+	const DBox	b = src.box( 0 );
+	const uint2 w = src.refWords( 0 );
+	src.writeLeaf( leafNodes, 0, w.x, w.y );
 	Box4Node node;
 	for ( int s = 0; s < 4; ++s )
 	{

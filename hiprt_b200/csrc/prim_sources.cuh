@@ -60,11 +60,23 @@ struct TriangleMeshSource
 		return ( m.x == 3u ) + ( m.y == 3u ) + ( m.z == 3u ) <= 1;
 	}
 
+	// pairable without the mapping: at least two of b's indices occur in a
+	static __device__ __forceinline__ bool sharesEdge( const uint3 a, const uint3 b )
+	{
+		const uint32_t hits = uint32_t( b.x == a.x || b.x == a.y || b.x == a.z ) + uint32_t( b.y == a.x || b.y == a.y || b.y == a.z ) +
+							  uint32_t( b.z == a.x || b.z == a.y || b.z == a.z );
+		return hits >= 2;
+	}
+
 	// 64-byte pair leaf: triangle 0 rotated so that its unshared vertex comes first, the shared
 	// edge is (v1,v2) and v3 is the unshared vertex of triangle 1 (TriangleMesh.h:89-157).
-	__device__ __forceinline__ void writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t p ) const
+	// the two words a primitive's 32-byte record carries through the build: its two triangle indices, so that
+	// the leaf can be written without going back to the pair list
+	__device__ __forceinline__ uint2 refWords( uint32_t p ) const { return pairOf( p ); }
+
+	__device__ __forceinline__ void writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t tri0, uint32_t tri1 ) const
 	{
-		const uint2 pr	  = pairOf( p );
+		const uint2 pr	  = make_uint2( tri0, tri1 );
 		uint3		i0	  = indices( pr.x );
 		uint32_t	flags = DefaultTriangleFlags;
 		uint32_t	i3	  = 0;
@@ -127,7 +139,8 @@ struct AabbListSource
 		const float* hi = reinterpret_cast<const float*>( aabbs + size_t( p ) * stride + ( stride >> 1 ) );
 		return DBox{ make_float3( __ldg( lo ), __ldg( lo + 1 ), __ldg( lo + 2 ) ), make_float3( __ldg( hi ), __ldg( hi + 1 ), __ldg( hi + 2 ) ) };
 	}
-	__device__ __forceinline__ void writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t p ) const
+	__device__ __forceinline__ uint2 refWords( uint32_t p ) const { return make_uint2( p, 0u ); }
+	__device__ __forceinline__ void	 writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t p, uint32_t ) const
 	{
 		static_cast<CustomNode*>( leafArray )[leafAddr].primIndex = p;
 	}
@@ -191,7 +204,8 @@ struct InstanceSource
 		return out;
 	}
 
-	__device__ __forceinline__ void writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t p ) const
+	__device__ __forceinline__ uint2 refWords( uint32_t p ) const { return make_uint2( p, 0u ); }
+	__device__ __forceinline__ void	 writeLeaf( void* leafArray, uint32_t leafAddr, uint32_t p, uint32_t ) const
 	{
 		const hiprtTransformHeader h	= header( p );
 		const hiprtInstance		   inst = instances[p];

@@ -54,7 +54,7 @@ struct __align__( 16 ) Smem
 		uint32_t stage[Tile];			 // scatter phase (keys, then values)
 	};
 	uint32_t digitStartLocal[Radix];  // first local rank of each digit inside the tile
-	uint32_t digitBaseGlobal[Radix];  // global position of the tile's first element of each digit
+	uint32_t digitBaseGlobal[Radix];  // global position of the tile's first element of each digit minus its local start
 	uint32_t tile;
 };
 
@@ -97,17 +97,21 @@ __global__ void __launch_bounds__( Block ) onesweepPass(
 		key[i]			   = idx < n ? keysIn[idx] : 0xFFFFFFFFu; // padding sorts last and is never written
 	}
 
-	// ---- rank inside the warp with match_any; the lowest lane of each digit group bumps the counter
+	// ---- rank inside the warp with match_any; the lowest lane of each digit group bumps the counter.
+	// The matches of all items are independent and issued first; only the counter updates are serial.
+	uint32_t peers[Items];
+#pragma unroll
+	for ( int i = 0; i < Items; ++i )
+		peers[i] = __match_any_sync( FullMask, ( key[i] >> shift ) & ( Radix - 1 ) );
 #pragma unroll
 	for ( int i = 0; i < Items; ++i )
 	{
-		const uint32_t d	 = ( key[i] >> shift ) & ( Radix - 1 );
-		const uint32_t peers = __match_any_sync( FullMask, d );
-		const uint32_t prev	 = s.warpHist[warp][d];
+		const uint32_t d	= ( key[i] >> shift ) & ( Radix - 1 );
+		const uint32_t prev = s.warpHist[warp][d];
 		__syncwarp();
-		if ( ( peers & laneMaskLt() ) == 0 ) s.warpHist[warp][d] = prev + __popc( peers );
+		if ( ( peers[i] & laneMaskLt() ) == 0 ) s.warpHist[warp][d] = prev + __popc( peers[i] );
 		__syncwarp();
-		rank[i] = prev + __popc( peers & laneMaskLt() );
+		rank[i] = prev + __popc( peers[i] & laneMaskLt() );
 	}
 	__syncthreads();
 
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__( Block ) onesweepPass(
 			volatile uint32_t* lb = lookback + size_t( tile ) * Radix + tid;
 			*lb					  = FlagIncl | ( prefix + tileTotal );
 		}
-		s.digitBaseGlobal[tid] = before + prefix;
+		s.digitBaseGlobal[tid] = before + prefix - s.digitStartLocal[tid]; // destination = this + local rank
 	}
 	__syncthreads();
 
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__( Block ) onesweepPass(
 		{
 			const uint32_t k = s.stage[r];
 			const uint32_t d = ( k >> shift ) & ( Radix - 1 );
-			keysOut[s.digitBaseGlobal[d] + r - s.digitStartLocal[d]] = k;
+			keysOut[s.digitBaseGlobal[d] + r] = k;
 		}
 	}
 	__syncthreads();
@@ -239,7 +243,7 @@ __global__ void __launch_bounds__( Block ) onesweepPass(
 		if ( r < valid )
 		{
 			const uint32_t d = destDigit[i];
-			valsOut[s.digitBaseGlobal[d] + r - s.digitStartLocal[d]] = s.stage[r];
+			valsOut[s.digitBaseGlobal[d] + r] = s.stage[r];
 		}
 	}
 }

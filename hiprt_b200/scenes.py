@@ -172,6 +172,15 @@ def pinhole_rays(width, height, eye, look_at, up=(0, 1, 0), fov_deg=45.0):
     return make_rays(o, d)
 
 
+def tile_order(width, height, tw=8, th=4):
+    """Permutation of the row-major pixel indices into tw x th tiles (tile after tile, row-major inside a tile):
+    32 consecutive rays cover an 8x4 pixel block, which is how the reference's tests launch their kernels
+    (2-D thread blocks, test/hiprtTest.cpp:1510-1514), instead of a 32x1 strip."""
+    ys, xs = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
+    key = ((ys // th) * ((width + tw - 1) // tw) + xs // tw) * (tw * th) + (ys % th) * tw + xs % tw
+    return np.argsort(key.reshape(-1), kind="stable")
+
+
 def cornell_rays(width=512, height=512):
     """CornellBoxKernel ray generator (reference test/kernels/HiprtTestKernel.h:118-134)."""
     x = np.arange(width, dtype=f32)[None, :].repeat(height, 0)

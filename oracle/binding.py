@@ -137,9 +137,12 @@ class Geometry:
             _p(self.pairs_in), 0 if self.pairs_in is None else len(self.pairs_in), int(allow_pairing))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_geometry_destroy(self.h)
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().orc_geometry_destroy(self.h)
+                self.h = None
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
     def _count(self, what):
         return int(lib().orc_geometry_count(self.h, what))
@@ -234,9 +237,12 @@ class Scene:
                                         _p(self.masks), n)
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().orc_scene_destroy(self.h)
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().orc_scene_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
     count = property(lambda s: int(lib().orc_scene_count(s.h, 0)))
     box_count = property(lambda s: int(lib().orc_scene_count(s.h, 1)))

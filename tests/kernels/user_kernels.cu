@@ -1,0 +1,98 @@
+// User trace kernels for tests/test_gpu_user_kernels.py, written against the public device API exactly as an
+// application of the reference would write them (cf. the reference's test/kernels/HiprtTestKernel.h:
+// CustomIntersectionKernel :177-214, CutoutKernel :216-260, TraceKernel :102-116). Compiled at test time
+// through hiprtBuildTraceKernels (NVRTC), which prepends <hiprt/hiprt_device.h> and the func-table dispatchers.
+
+// custom primitive: sphere (centre.xyz, radius) per AABB; data = float4 array
+__device__ bool intersectSphere( const hiprtRay& ray, const void* data, void* payload, hiprtHit& hit )
+{
+	const float4 s	= reinterpret_cast<const float4*>( data )[hit.primID];
+	const float3 oc = make_float3( ray.origin.x - s.x, ray.origin.y - s.y, ray.origin.z - s.z );
+	const float3 d	= ray.direction;
+	const float	 a	= d.x * d.x + d.y * d.y + d.z * d.z;
+	const float	 b	= 2.0f * ( oc.x * d.x + oc.y * d.y + oc.z * d.z );
+	const float	 c	= oc.x * oc.x + oc.y * oc.y + oc.z * oc.z - s.w * s.w;
+	const float	 disc = b * b - 4.0f * a * c;
+	if ( disc < 0.0f ) return false;
+	const float t = ( -b - sqrtf( disc ) ) / ( 2.0f * a );
+	if ( t < ray.minT || t > ray.maxT ) return false;
+	hit.t	   = t;
+	hit.normal = make_float3( oc.x + t * d.x, oc.y + t * d.y, oc.z + t * d.z );
+	hit.uv	   = make_float2( 0.0f, 0.0f );
+	if ( payload ) atomicAdd( reinterpret_cast<unsigned int*>( payload ), 1u );
+	return true;
+}
+
+// hit filter ("cutout"): returns true to REJECT the hit (reference convention); data = one float threshold
+__device__ bool cutoutFilter( const hiprtRay&, const void* data, void*, const hiprtHit& hit )
+{
+	const float threshold = *reinterpret_cast<const float*>( data );
+	return hit.uv.x + hit.uv.y > threshold;
+}
+
+extern "C" __global__ void customKernel(
+	hiprtGeometry geom, hiprtFuncTable table, const hiprtRay* rays, hiprtHit* hits, uint32_t numRays, unsigned int* counters )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= numRays ) return;
+	hiprtGeomCustomTraversalClosest tr( geom, rays[i], hiprtTraversalHintDefault, counters, table );
+	hits[i] = tr.getNextHit();
+}
+
+extern "C" __global__ void cutoutKernel( hiprtGeometry geom, hiprtFuncTable table, const hiprtRay* rays, hiprtHit* hits, uint32_t numRays )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= numRays ) return;
+	hiprtGeomTraversalClosest tr( geom, rays[i], hiprtTraversalHintDefault, nullptr, table );
+	hits[i] = tr.getNextHit();
+}
+
+// every hit along the ray, in traversal order, through the re-entrant any-hit iterator
+extern "C" __global__ void allHitsKernel(
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, uint32_t maxPerRay, uint32_t* counts, uint32_t* prims, float* ts )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= numRays ) return;
+	hiprtGeomTraversalAnyHit tr( geom, rays[i] );
+	uint32_t				 n = 0;
+	while ( true )
+	{
+		const hiprtHit h = tr.getNextHit();
+		if ( tr.getCurrentState() != hiprtTraversalStateHit ) break;
+		if ( n < maxPerRay ) prims[i * maxPerRay + n] = h.primID, ts[i * maxPerRay + n] = h.t;
+		++n;
+	}
+	counts[i] = n;
+}
+
+// the reference's TraceKernel layout: global stack with a shared-memory cache (test/hiprtTest.cpp:1510-1530)
+#define SHARED_STACK_SIZE 16
+#define BLOCK_SIZE 64
+extern "C" __global__ void __launch_bounds__( BLOCK_SIZE ) globalStackKernel(
+	hiprtGeometry geom, const hiprtRay* rays, hiprtHit* hits, uint32_t numRays, hiprtGlobalStackBuffer globalStackBuffer, int dynamic )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	__shared__ uint32_t	   cache[SHARED_STACK_SIZE * BLOCK_SIZE];
+	hiprtSharedStackBuffer sharedStackBuffer{ SHARED_STACK_SIZE, cache };
+	if ( i >= numRays ) return;
+	if ( dynamic )
+	{
+		hiprtDynamicStack									 stack( globalStackBuffer, sharedStackBuffer );
+		hiprtGeomTraversalClosestCustomStack<hiprtDynamicStack> tr( geom, rays[i], stack );
+		hits[i] = tr.getNextHit();
+	}
+	else
+	{
+		hiprtGlobalStack									stack( globalStackBuffer, sharedStackBuffer );
+		hiprtGeomTraversalClosestCustomStack<hiprtGlobalStack> tr( geom, rays[i], stack );
+		hits[i] = tr.getNextHit();
+	}
+}
+
+extern "C" __global__ void sceneKernel( hiprtScene scene, const hiprtRay* rays, hiprtHit* hits, uint32_t numRays, uint32_t mask )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= numRays ) return;
+	hiprtSceneTraversalClosest tr( scene, rays[i], mask );
+	hits[i] = tr.getNextHit();
+}

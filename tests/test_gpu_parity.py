@@ -52,6 +52,8 @@ def check_build_against_oracle(ctx, geom, og, expect_same_keys=False):
     n = og.prim_count
     hdr = geom.header()
     assert int(hdr["primNodeCount"]) == n
+    if n > 1:
+        assert geom.build_error_flag() == 0, "the collapse watchdog fired"
     if n == 1:  # singleton: no sort, no binary tree (reference: SingletonConstruction)
         boxes, leaves = geom.nodes()
         assert boxes.tobytes() == og.box_nodes.tobytes() and leaves.tobytes() == og.leaves.tobytes()
