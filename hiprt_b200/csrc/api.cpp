@@ -65,7 +65,8 @@ class HostTracePipeline
 	}
 
 	void run(
-		hiprtGeometry geometry, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t user )
+		hiprtGeometry geometry, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t user,
+		uint32_t smCount )
 	{
 		std::lock_guard<std::mutex> lock( m_mutex );
 		init();
@@ -85,7 +86,7 @@ class HostTracePipeline
 			checkCuda( cudaStreamWaitEvent( m_compute, m_up[slot], 0 ), "cudaStreamWaitEvent" );
 			if ( c >= uint32_t( Slots ) ) checkCuda( cudaStreamWaitEvent( m_compute, m_down[slot], 0 ), "cudaStreamWaitEvent" );
 			if ( geometry )
-				traceGeometry( geometry, m_rays[slot], count, m_hits[slot], type, m_compute );
+				traceGeometry( geometry, m_rays[slot], count, m_hits[slot], type, m_counters + slot * 16, smCount, m_compute );
 			else
 				traceScene( scene, m_rays[slot], count, m_hits[slot], type, mask, m_compute );
 			checkCuda( cudaGetLastError(), "trace launch" );
@@ -109,6 +110,7 @@ class HostTracePipeline
 		checkCuda( cudaStreamCreateWithFlags( &m_compute, cudaStreamNonBlocking ), "cudaStreamCreate" );
 		checkCuda( cudaStreamCreateWithFlags( &m_d2h, cudaStreamNonBlocking ), "cudaStreamCreate" );
 		checkCuda( cudaEventCreateWithFlags( &m_begin, cudaEventDisableTiming ), "cudaEventCreate" );
+		checkCuda( cudaMalloc( reinterpret_cast<void**>( &m_counters ), Slots * 64 ), "cudaMalloc" );
 		for ( int i = 0; i < Slots; ++i )
 		{
 			checkCuda( cudaMalloc( reinterpret_cast<void**>( &m_rays[i] ), size_t( Chunk ) * sizeof( hiprtRay ) ), "cudaMalloc" );
@@ -125,6 +127,7 @@ class HostTracePipeline
 	cudaStream_t m_h2d = nullptr, m_compute = nullptr, m_d2h = nullptr;
 	cudaEvent_t	 m_begin = nullptr, m_up[Slots]{}, m_traced[Slots]{}, m_down[Slots]{};
 	hiprtRay*	 m_rays[Slots]{};
+	uint32_t*	 m_counters = nullptr;
 	hiprtHit*	 m_hits[Slots]{};
 };
 
@@ -243,6 +246,16 @@ class Context
 	std::string		  cacheDir;
 	HostTracePipeline hostPipeline;
 
+	// ray-batch counters of the persistent trace kernels: a small ring so that launches in flight on different
+	// streams never share one
+	uint32_t* nextWorkCounter()
+	{
+		std::lock_guard<std::mutex> lock( m_mutex );
+		if ( !m_workCounters ) checkCuda( cudaMalloc( reinterpret_cast<void**>( &m_workCounters ), 64 * 64 ), "cudaMalloc" );
+		m_workCounterNext = ( m_workCounterNext + 1 ) % 64;
+		return m_workCounters + m_workCounterNext * 16;
+	}
+
   private:
 	struct Pool
 	{
@@ -259,6 +272,8 @@ class Context
 	std::string			  m_lastError;
 	std::map<void*, Pool> m_pools;
 	std::mutex			  m_mutex;
+	uint32_t*			  m_workCounters	= nullptr;
+	uint32_t			  m_workCounterNext = 0;
 };
 
 inline Context* ctx( hiprtContext c ) { return reinterpret_cast<Context*>( c ); }
@@ -866,7 +881,7 @@ hiprtError hiprtB200TraceGeometry(
 {
 	if ( !context || !geometry || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
-		traceGeometry( geometry, rays, numRays, hits, type, static_cast<cudaStream_t>( stream ) );
+		traceGeometry( geometry, rays, numRays, hits, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ) );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
 }
@@ -892,7 +907,7 @@ hiprtError hiprtB200TraceGeometryHost(
 	hiprtContext context, hiprtGeometry geometry, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtApiStream stream )
 {
 	if ( !context || !geometry || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
-	return guarded( context, [&] { ctx( context )->hostPipeline.run( geometry, nullptr, hostRays, numRays, hostHits, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ) ); } );
+	return guarded( context, [&] { ctx( context )->hostPipeline.run( geometry, nullptr, hostRays, numRays, hostHits, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount ); } );
 }
 
 hiprtError hiprtB200TraceSceneHost(
@@ -906,7 +921,7 @@ hiprtError hiprtB200TraceSceneHost(
 	hiprtApiStream	   stream )
 {
 	if ( !context || !scene || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
-	return guarded( context, [&] { ctx( context )->hostPipeline.run( nullptr, scene, hostRays, numRays, hostHits, type, mask, static_cast<cudaStream_t>( stream ) ); } );
+	return guarded( context, [&] { ctx( context )->hostPipeline.run( nullptr, scene, hostRays, numRays, hostHits, type, mask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount ); } );
 }
 
 hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount, size_t* offsetsOut, uint32_t numOffsets )

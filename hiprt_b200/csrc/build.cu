@@ -272,14 +272,64 @@ void buildScene(
 	primBoxesKernel<InstanceSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
 	runLbvh( dev, src, balanced, n, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
 }
-void updateGeometry( const DeviceInfo&, const hiprtGeometryBuildInput&, hiprtBuildOptions, void*, cudaStream_t, void* )
+// Refit in place (hiprtBuildOperationUpdate): same primitive count and order as the build, moved positions.
+void updateGeometry(
+	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions, void*, cudaStream_t stream, void* storage )
 {
-	throw std::runtime_error( "geometry update: not implemented yet" );
+	(void)dev;
+	const uint32_t nMax = uint32_t( geometryPrimCount( input ) );
+	if ( nMax == 0 ) throw std::runtime_error( "empty geometry" );
+	uint8_t*	out		  = static_cast<uint8_t*>( storage );
+	GeomHeader* header	  = reinterpret_cast<GeomHeader*>( out );
+	Box4Node*	boxNodes  = reinterpret_cast<Box4Node*>( out + alignUp( sizeof( GeomHeader ) ) );
+	void*		leafNodes = out + alignUp( sizeof( GeomHeader ) ) + alignUp( maxBoxNodeCount( nMax ) * sizeof( Box4Node ) );
+	const uint32_t grid	  = DivideRoundUp( uint32_t( maxBoxNodeCount( nMax ) ), 128u );
+	if ( input.type == hiprtPrimitiveTypeTriangleMesh )
+	{
+		const auto&		   m = input.primitive.triangleMesh;
+		TriangleMeshSource src{};
+		src.vertices	   = static_cast<const uint8_t*>( m.vertices );
+		src.vertexStride   = m.vertexStride;
+		src.triangles	   = ( m.triangleCount == 0 ) ? nullptr : static_cast<const uint8_t*>( m.triangleIndices );
+		src.triangleStride = m.triangleStride;
+		src.pairs		   = nullptr; // the pairing is read back from the leaves
+		refitKernel<TriangleMeshSource><<<grid, 128, 0, stream>>>( src, &header->boxNodeCount, boxNodes, leafNodes );
+	}
+	else
+	{
+		const auto&	   a = input.primitive.aabbList;
+		AabbListSource src{ static_cast<const uint8_t*>( a.aabbs ), a.aabbStride };
+		refitKernel<AabbListSource><<<grid, 128, 0, stream>>>( src, &header->boxNodeCount, boxNodes, leafNodes );
+	}
+	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
-void updateScene( const DeviceInfo&, const hiprtSceneBuildInput&, hiprtBuildOptions, void*, cudaStream_t, void* )
+
+void updateScene(
+	const DeviceInfo& dev, const hiprtSceneBuildInput& input, hiprtBuildOptions, void*, cudaStream_t stream, void* storage )
 {
-	throw std::runtime_error( "scene update: not implemented yet" );
+	(void)dev;
+	const uint32_t n = input.instanceCount;
+	if ( n == 0 ) throw std::runtime_error( "empty scene" );
+	const SceneLayout S			= sceneLayout( input );
+	uint8_t*		  out		= static_cast<uint8_t*>( storage );
+	SceneHeader*	  header	= reinterpret_cast<SceneHeader*>( out );
+	Box4Node*		  boxNodes	= reinterpret_cast<Box4Node*>( out + S.boxNodes );
+	InstanceNode*	  instNodes = reinterpret_cast<InstanceNode*>( out + S.primNodes );
+	InstanceRecord*	  records	= reinterpret_cast<InstanceRecord*>( out + S.instances );
+	SRTFrame*		  frames	= reinterpret_cast<SRTFrame*>( out + S.frames );
+	InstanceSource	  src{};
+	src.instances  = static_cast<const hiprtInstance*>( input.instances );
+	src.headers	   = static_cast<const hiprtTransformHeader*>( input.instanceTransformHeaders );
+	src.frames	   = ( input.frameCount > 0 && input.instanceFrames != nullptr ) ? frames : nullptr;
+	src.masks	   = static_cast<const uint32_t*>( input.instanceMasks );
+	src.frameCount = input.frameCount;
+	const uint32_t work = std::max( n, input.frameCount );
+	updateSceneInputsKernel<<<DivideRoundUp( work, 256u ), 256, 0, stream>>>(
+		records, frames, src, n, input.instanceFrames, input.frameType == hiprtFrameTypeMatrix );
+	refitKernel<InstanceSource><<<DivideRoundUp( uint32_t( maxBoxNodeCount( n ) ), 128u ), 128, 0, stream>>>( src, &header->boxNodeCount, boxNodes, instNodes );
+	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
+
 // Batch of small geometries: the caller's host arrays (inputs, storage pointers) are copied into the
 // temporary buffer, then ONE launch builds everything (reference: BatchBuilder.h:58-132).
 size_t batchTempSize( uint32_t count )

@@ -820,6 +820,126 @@ __global__ void __launch_bounds__( CollapseBlock ) collapsePackKernel(
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Update (refit) of a built structure: hiprtBuildOperationUpdate (reference: ResetCountersAndUpdateLeaves
+// + FitBounds, BvhBuilderKernels.h:550-814, host LbvhBuilder.h:432-484). Topology and node addresses are
+// kept; leaves are rewritten from the (moved) primitives and every child box is recomputed bottom-up.
+// One thread per box node, ONE launch: the thread refreshes its leaf children, then counts itself in on
+// its own node; each finished internal child counts in on its parent. The arrival that completes a node
+// (#internal children + 1) carries the node's union box one level up. Counters are left at zero again.
+template <typename Source>
+__device__ __forceinline__ DBox refreshLeaf( const Source& src, void* leafNodes, uint32_t leafAddr );
+
+template <>
+__device__ __forceinline__ DBox refreshLeaf<TriangleMeshSource>( const TriangleMeshSource& src, void* leafNodes, uint32_t leafAddr )
+{
+	float4*		   leaf	 = reinterpret_cast<float4*>( static_cast<TrianglePairNode*>( leafNodes ) + leafAddr );
+	const float4   meta	 = leaf[3]; // {pad, primIndex0, primIndex1, flags}: the pairing of the original build is kept
+	const uint32_t tri0 = __float_as_uint( meta.y ), tri1 = __float_as_uint( meta.z );
+	src.writeLeaf( leafNodes, leafAddr, tri0, tri1 );
+	const float4 q0 = leaf[0], q1 = leaf[1], q2 = leaf[2];
+	DBox		 b	= emptyBox();
+	growBox( b, make_float3( q0.x, q0.y, q0.z ) );
+	growBox( b, make_float3( q0.w, q1.x, q1.y ) );
+	growBox( b, make_float3( q1.z, q1.w, q2.x ) );
+	growBox( b, make_float3( q2.y, q2.z, q2.w ) );
+	return b;
+}
+template <>
+__device__ __forceinline__ DBox refreshLeaf<AabbListSource>( const AabbListSource& src, void* leafNodes, uint32_t leafAddr )
+{
+	return src.box( static_cast<const CustomNode*>( leafNodes )[leafAddr].primIndex );
+}
+template <>
+__device__ __forceinline__ DBox refreshLeaf<InstanceSource>( const InstanceSource& src, void* leafNodes, uint32_t leafAddr )
+{
+	const uint32_t p = reinterpret_cast<const uint32_t*>( static_cast<InstanceNode*>( leafNodes ) + leafAddr )[15] & 0xFFFFFFu;
+	src.writeLeaf( leafNodes, leafAddr, p, 0u );
+	return src.box( p );
+}
+
+template <typename Source>
+__global__ void __launch_bounds__( 128 ) refitKernel( Source src, const uint32_t* boxNodeCount, Box4Node* boxNodes, void* leafNodes )
+{
+	uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( node >= *boxNodeCount ) return;
+	uint32_t* words = reinterpret_cast<uint32_t*>( boxNodes + node );
+	const uint4 children = *reinterpret_cast<const uint4*>( words );
+	const uint32_t c[4]	 = { children.x, children.y, children.z, children.w };
+	uint32_t	   internal = 0;
+#pragma unroll
+	for ( uint32_t s = 0; s < 4; ++s )
+	{
+		if ( c[s] == InvalidValue ) continue;
+		if ( isBoxIndex( c[s] ) )
+		{
+			++internal;
+			continue;
+		}
+		const DBox b  = refreshLeaf<Source>( src, leafNodes, nodeAddr( c[s] ) );
+		float*	   bw = reinterpret_cast<float*>( words ) + 4 + 6 * s;
+		bw[0] = b.lo.x, bw[1] = b.lo.y, bw[2] = b.lo.z, bw[3] = b.hi.x, bw[4] = b.hi.y, bw[5] = b.hi.z;
+	}
+	// climb while this thread is the arrival that completes the node
+	while ( true )
+	{
+		__threadfence();
+		const uint32_t arrived = atomicAdd( &words[29], 1u ) + 1u; // updateCounter
+		if ( arrived < internal + 1u ) return;
+		words[29] = 0; // ready for the next update
+		__threadfence();
+		const uint32_t parent = __ldcg( &words[28] );
+		if ( parent == InvalidValue ) return; // the root is complete
+		// union of this node's child boxes (written by other threads of this launch: read through L2)
+		DBox		   u  = emptyBox();
+		const float4*  q  = reinterpret_cast<const float4*>( words );
+		const float4   q0 = __ldcg( q ), q1 = __ldcg( q + 1 ), q2 = __ldcg( q + 2 ), q3 = __ldcg( q + 3 ), q4 = __ldcg( q + 4 ), q5 = __ldcg( q + 5 ), q6 = __ldcg( q + 6 );
+		const float	   b[24] = { q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w,
+								 q4.x, q4.y, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, q6.x, q6.y, q6.z, q6.w };
+		const uint32_t cc[4] = { __float_as_uint( q0.x ), __float_as_uint( q0.y ), __float_as_uint( q0.z ), __float_as_uint( q0.w ) };
+#pragma unroll
+		for ( uint32_t s = 0; s < 4; ++s )
+			if ( cc[s] != InvalidValue )
+				u = uniteBox( u, DBox{ make_float3( b[6 * s], b[6 * s + 1], b[6 * s + 2] ), make_float3( b[6 * s + 3], b[6 * s + 4], b[6 * s + 5] ) } );
+		// my slot in the parent, and how many internal children the parent waits for
+		uint32_t*	   pw	= reinterpret_cast<uint32_t*>( boxNodes + parent );
+		const uint4	   pc	= *reinterpret_cast<const uint4*>( pw );
+		const uint32_t me	= makeNodeIndex( node, BoxType );
+		const uint32_t slot = pc.x == me ? 0u : ( pc.y == me ? 1u : ( pc.z == me ? 2u : 3u ) );
+		float*		   bw	= reinterpret_cast<float*>( pw ) + 4 + 6 * slot;
+		bw[0] = u.lo.x, bw[1] = u.lo.y, bw[2] = u.lo.z, bw[3] = u.hi.x, bw[4] = u.hi.y, bw[5] = u.hi.z;
+		internal = uint32_t( pc.x != InvalidValue && isBoxIndex( pc.x ) ) + uint32_t( pc.y != InvalidValue && isBoxIndex( pc.y ) ) +
+				   uint32_t( pc.z != InvalidValue && isBoxIndex( pc.z ) ) + uint32_t( pc.w != InvalidValue && isBoxIndex( pc.w ) );
+		node  = parent;
+		words = pw;
+	}
+}
+
+// Scene update: refresh the per-instance records and the converted frames (the part of initSceneKernel that
+// depends on the inputs), leaving header counters and topology alone.
+__global__ void __launch_bounds__( 256 ) updateSceneInputsKernel(
+	InstanceRecord* records, SRTFrame* frames, InstanceSource src, uint32_t instanceCount, const void* apiFrames, bool matrixFrames )
+{
+	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( index < instanceCount )
+	{
+		const hiprtInstance		   inst = src.instances[index];
+		const hiprtTransformHeader h	= src.header( index );
+		uint4					   rec;
+		rec.x			   = h.frameIndex;
+		rec.y			   = ( h.frameCount & 0x7FFFFFFFu ) | ( uint32_t( inst.type == hiprtInstanceTypeScene ) << 31 );
+		const uint64_t ptr = reinterpret_cast<uint64_t>( inst.geometry );
+		rec.z = uint32_t( ptr ), rec.w = uint32_t( ptr >> 32 );
+		reinterpret_cast<uint4*>( records )[index] = rec;
+	}
+	if ( index < src.frameCount && apiFrames != nullptr )
+	{
+		const DFrame f = matrixFrames ? frameFromMatrix( static_cast<const hiprtFrameMatrix*>( apiFrames )[index] )
+									  : frameFromSRT( static_cast<const hiprtFrameSRT*>( apiFrames )[index] );
+		storeFrame( frames, index, f );
+	}
+}
+
 // A single primitive: root with one child (reference: SingletonConstruction BvhBuilderKernels.h:296-331).
 template <typename Source>
 __global__ void singletonKernel( Source src, uint32_t* primNodeCounter, Box4Node* boxNodes, void* leafNodes )

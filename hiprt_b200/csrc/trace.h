@@ -5,7 +5,9 @@
 
 namespace hiprt
 {
-void traceGeometry( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, cudaStream_t stream );
+// workCounter: one device uint32 the persistent variant uses as its ray-batch counter (reset on `stream` before the launch)
+void traceGeometry(
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream );
 void traceScene(
 	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t stream );
 } // namespace hiprt

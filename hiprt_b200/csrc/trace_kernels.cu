@@ -11,90 +11,122 @@
 #include "builders.h"
 #include "trace.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace hiprt
 {
-constexpr uint32_t TraceBlock		= 128;
+constexpr uint32_t TraceBlock		= 128; // scene kernels
 constexpr uint32_t SharedStackDepth = 12;
-constexpr uint32_t FastStackDepth	= 32; // shared-memory stack entries per ray on the fast path (16 KiB per block)
 
-class HybridStack
+// Top `SharedDepth` entries in shared memory (entry e of a thread at base[e * 32], one bank per lane), the rest of the
+// 64 entries the reference's private stack offers in a per-thread local array.
+template <uint32_t SharedDepth>
+class HybridStackT
 {
   public:
-	__device__ HybridStack( uint32_t* sharedBase ) : m_shared( sharedBase + ( threadIdx.x & 31u ) + ( threadIdx.x >> 5 ) * 32u * SharedStackDepth ) { reset(); }
+	__device__ HybridStackT( uint32_t* sharedBase ) : m_shared( sharedBase + ( threadIdx.x & 31u ) + ( threadIdx.x >> 5 ) * 32u * SharedDepth ) { reset(); }
 	__device__ void push( uint32_t v )
 	{
-		if ( m_top < SharedStackDepth )
+		if ( m_top < SharedDepth )
 			m_shared[m_top * 32u] = v;
 		else
-			m_local[m_top - SharedStackDepth] = v;
+			m_local[m_top - SharedDepth] = v;
 		++m_top;
 	}
 	__device__ uint32_t pop()
 	{
 		--m_top;
-		return m_top < SharedStackDepth ? m_shared[m_top * 32u] : m_local[m_top - SharedStackDepth];
+		return m_top < SharedDepth ? m_shared[m_top * 32u] : m_local[m_top - SharedDepth];
 	}
 	__device__ bool		empty() const { return m_top == 0; }
-	__device__ uint32_t vacancy() const { return SharedStackDepth + LocalDepth - m_top; }
+	__device__ uint32_t vacancy() const { return SharedDepth + LocalDepth - m_top; }
 	__device__ void		reset() { m_top = 0; }
 
   private:
-	static constexpr uint32_t LocalDepth = 52;
+	static constexpr uint32_t LocalDepth = 64 - SharedDepth;
 	uint32_t*				  m_shared;
 	uint32_t				  m_local[LocalDepth];
 	uint32_t				  m_top;
 };
+using HybridStack = HybridStackT<SharedStackDepth>;
 
-// General path (custom primitives, or a ray whose stack outgrew the fast path's shared memory): the public
-// traversal object with a per-thread local stack.
-template <hiprtTraversalType Type>
-__device__ __noinline__ hiprtHit traceGeometryGeneral( hiprtGeometry geom, const hiprtRay& ray, bool triangles )
+__device__ __forceinline__ hiprtRay loadRay( const hiprtRay* rays, uint32_t index )
 {
-	hiprtPrivateStack stack;
-	if ( triangles )
-	{
-		hiprtGeomTraversalT<hiprtPrivateStack, hiprtTriangleNode, Type> tr( geom, ray, stack );
-		return tr.getNextHit();
-	}
-	hiprtGeomTraversalT<hiprtPrivateStack, hiprtCustomNode, Type> tr( geom, ray, stack );
-	return tr.getNextHit();
-}
-
-// Variant: 0 = general traversal object with the hybrid (shared + local) stack, 1 = fast path, 2 = fast path without
-// leaf postponement, 3 / 4 = 1 / 2 compiled for 10 resident blocks per SM (<= 51 registers). Selected at run time by HIPRT_B200_TRACE_VARIANT (tuning knob; default 1).
-template <hiprtTraversalType Type, int Variant>
-__global__ void __launch_bounds__( TraceBlock, Variant >= 3 ? 10 : 1 )
-	traceGeometryKernel( hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits )
-{
-	__shared__ uint32_t sStack[TraceBlock * ( Variant == 0 ? SharedStackDepth : FastStackDepth )];
-	const uint32_t		index = blockIdx.x * TraceBlock + threadIdx.x;
-	if ( index >= numRays ) return;
 	const float4* rp = reinterpret_cast<const float4*>( rays + index );
 	const float4  r0 = __ldg( rp ), r1 = __ldg( rp + 1 );
 	hiprtRay	  ray;
 	ray.origin = make_float3( r0.x, r0.y, r0.z ), ray.minT = r0.w;
 	ray.direction = make_float3( r1.x, r1.y, r1.z ), ray.maxT = r1.w;
-	hiprtHit hit;
-	if constexpr ( Variant == 0 )
-	{
-		HybridStack												  stack( sStack );
-		hiprtGeomTraversalT<HybridStack, hiprtTriangleNode, Type> tr( geom, ray, stack );
-		hit = tr.getNextHit();
-	}
-	else
-	{
-		const GeomHeader* header	= reinterpret_cast<const GeomHeader*>( geom );
-		const bool		  triangles = header->geomType & 1u;
-		if ( !triangles || !traceTrianglesFast<Type == hiprtTraversalTerminateAtAnyHit, TraceBlock, FastStackDepth, Variant == 1 || Variant == 3>(
-							   header, ray, sStack + threadIdx.x, hit ) )
-			hit = traceGeometryGeneral<Type>( geom, ray, triangles );
-	}
+	return ray;
+}
+__device__ __forceinline__ void storeHit( hiprtHit* hits, uint32_t index, const hiprtHit& hit )
+{
 	float4* hp = reinterpret_cast<float4*>( hits + index );
 	hp[0] = make_float4( __uint_as_float( hit.instanceIDs[0] ), __uint_as_float( hit.instanceIDs[1] ), __uint_as_float( hit.instanceIDs[2] ), __uint_as_float( hit.instanceIDs[3] ) );
 	hp[1] = make_float4( __uint_as_float( hit.primID ), 0.0f, hit.uv.x, hit.uv.y );
 	hp[2] = make_float4( hit.normal.x, hit.normal.y, hit.normal.z, hit.t );
+}
+
+// One thread per ray. Persistent = the grid only fills the machine and every warp keeps fetching batches of 32
+// consecutive rays from a global counter until the buffer is exhausted (no block-granular tail: a block slot is
+// never held by one long ray while its other warps sit idle).
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, bool Persistent>
+__global__ void __launch_bounds__( Block ) traceGeometryKernel(
+	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, uint32_t* workCounter )
+{
+	__shared__ uint32_t sStack[Block * SharedDepth];
+	using Stack		= HybridStackT<SharedDepth>;
+	const bool mesh = reinterpret_cast<const GeomHeader*>( geom )->geomType & 1u;
+	if constexpr ( Persistent )
+	{
+		const uint32_t lane = threadIdx.x & 31u;
+		while ( true )
+		{
+			uint32_t base = 0;
+			if ( lane == 0 ) base = atomicAdd( workCounter, 32u );
+			base = __shfl_sync( 0xFFFFFFFFu, base, 0 );
+			if ( base >= numRays ) return;
+			const uint32_t index = base + lane;
+			if ( index < numRays )
+			{
+				Stack		   stack( sStack );
+				const hiprtRay ray = loadRay( rays, index );
+				hiprtHit	   hit;
+				if ( mesh )
+				{
+					hiprtGeomTraversalT<Stack, hiprtTriangleNode, Type> tr( geom, ray, stack );
+					hit = tr.getNextHit();
+				}
+				else
+				{
+					hiprtGeomTraversalT<Stack, hiprtCustomNode, Type> tr( geom, ray, stack );
+					hit = tr.getNextHit();
+				}
+				storeHit( hits, index, hit );
+			}
+			__syncwarp();
+		}
+	}
+	else
+	{
+		const uint32_t index = blockIdx.x * Block + threadIdx.x;
+		if ( index >= numRays ) return;
+		Stack		   stack( sStack );
+		const hiprtRay ray = loadRay( rays, index );
+		hiprtHit	   hit;
+		if ( mesh )
+		{
+			hiprtGeomTraversalT<Stack, hiprtTriangleNode, Type> tr( geom, ray, stack );
+			hit = tr.getNextHit();
+		}
+		else
+		{
+			hiprtGeomTraversalT<Stack, hiprtCustomNode, Type> tr( geom, ray, stack );
+			hit = tr.getNextHit();
+		}
+		storeHit( hits, index, hit );
+	}
 }
 
 template <hiprtTraversalType Type>
@@ -128,23 +160,42 @@ static int traceVariant()
 	return v;
 }
 
-void traceGeometry( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, cudaStream_t stream )
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, bool Persistent>
+static void launchGeometry( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
+{
+	auto kernel = traceGeometryKernel<Type, Block, SharedDepth, Persistent>;
+	if constexpr ( Persistent )
+	{
+		static int blocksPerSm = 0; // same value for every caller: a benign race
+		if ( blocksPerSm == 0 ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSm, kernel, int( Block ), 0 );
+		cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), stream );
+		const uint32_t blocks = std::min( DivideRoundUp( numRays, Block ), smCount * uint32_t( std::max( blocksPerSm, 1 ) ) );
+		kernel<<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits, workCounter );
+	}
+	else
+		kernel<<<DivideRoundUp( numRays, Block ), Block, 0, stream>>>( geom, rays, numRays, hits, workCounter );
+}
+
+// Tuning variants (HIPRT_B200_TRACE_VARIANT): block size / shared stack depth / persistent warps.
+void traceGeometry(
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
 {
 	if ( numRays == 0 ) return;
-	const uint32_t blocks = DivideRoundUp( numRays, TraceBlock );
-	const bool	   any	  = type == hiprtTraversalTerminateAtAnyHit;
-#define HIPRT_B200_LAUNCH( V )                                                                                                          \
-	if ( any )                                                                                                                          \
-		traceGeometryKernel<hiprtTraversalTerminateAtAnyHit, V><<<blocks, TraceBlock, 0, stream>>>( geom, rays, numRays, hits );        \
-	else                                                                                                                                \
-		traceGeometryKernel<hiprtTraversalTerminateAtClosestHit, V><<<blocks, TraceBlock, 0, stream>>>( geom, rays, numRays, hits );
+	const bool any = type == hiprtTraversalTerminateAtAnyHit;
+#define HIPRT_B200_LAUNCH( B, D, P )                                                                                                       \
+	if ( any )                                                                                                                             \
+		launchGeometry<hiprtTraversalTerminateAtAnyHit, B, D, P>( geom, rays, numRays, hits, workCounter, smCount, stream );               \
+	else                                                                                                                                   \
+		launchGeometry<hiprtTraversalTerminateAtClosestHit, B, D, P>( geom, rays, numRays, hits, workCounter, smCount, stream );
 	switch ( traceVariant() )
 	{
-	case 0: HIPRT_B200_LAUNCH( 0 ) break;
-	case 2: HIPRT_B200_LAUNCH( 2 ) break;
-	case 3: HIPRT_B200_LAUNCH( 3 ) break;
-	case 4: HIPRT_B200_LAUNCH( 4 ) break;
-	default: HIPRT_B200_LAUNCH( 1 ) break;
+	case 0: HIPRT_B200_LAUNCH( 128, 12, false ) break;
+	case 2: HIPRT_B200_LAUNCH( 64, 12, false ) break;
+	case 3: HIPRT_B200_LAUNCH( 64, 32, false ) break;
+	case 4: HIPRT_B200_LAUNCH( 128, 32, true ) break;
+	case 5: HIPRT_B200_LAUNCH( 64, 32, true ) break;
+	case 6: HIPRT_B200_LAUNCH( 128, 24, false ) break;
+	default: HIPRT_B200_LAUNCH( 128, 32, false ) break;
 	}
 #undef HIPRT_B200_LAUNCH
 }

@@ -204,128 +204,6 @@ HIPRT_DEVICE HIPRT_INLINE hiprtRay transformRayToObject( const InstanceNode* nod
 	return out;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Fast rays-in/hits-out traversal of a triangle geometry (no custom primitives, no filter), used by
-// the library trace kernels. Same node tests, same arithmetic and the same order-independent
-// closest-hit rule as hiprtGeomTraversalT, organised for the SM's issue rate (the kernel is bound by
-// ALU issue slots, not by memory: see profiles/):
-//   * the traversal stack lives entirely in shared memory, lane-interleaved (entry e of thread t at
-//     stack[e * BlockThreads + t]: 32 lanes hit 32 banks), so the hit children of a node are written
-//     straight to their final stack slots from their RANK by entry distance -- 6 compares instead of a
-//     5-comparator sorting network with 20 selects followed by three pushes;
-//   * "while-while" control flow with one postponed leaf per lane: a lane that reaches a leaf keeps
-//     descending box nodes until the whole warp is out of box nodes, so the box loop and the triangle
-//     loop each run with more lanes active.
-// Returns false when the shared stack would overflow; the caller then re-traces the ray with the
-// general traversal object.
-template <bool AnyHit, uint32_t BlockThreads, uint32_t Depth, bool PostponeLeaf = true>
-HIPRT_DEVICE HIPRT_INLINE bool traceTrianglesFast( const GeomHeader* header, hiprtRay ray, uint32_t* stack, hiprtHit& result )
-{
-	const Box4Node*			boxNodes = header->boxNodes;
-	const TrianglePairNode* leaves	 = reinterpret_cast<const TrianglePairNode*>( header->primNodes );
-	const float3			o = ray.origin, invD = rcp3( ray.direction );
-	uint32_t				top = 0, node = RootIndex, stash = InvalidValue;
-	hiprtHit				best;
-
-	auto pop = [&]() -> uint32_t { return top ? stack[( --top ) * BlockThreads] : InvalidValue; };
-	auto leaf = [&]( uint32_t index ) -> bool {
-		const uint32_t addr = nodeAddr( index );
-#pragma unroll
-		for ( uint32_t which = 0; which < 2; ++which )
-		{
-			hiprtHit hit;
-			if ( intersectPairTriangle( leaves, addr, which, ray, hit ) )
-			{
-				if constexpr ( AnyHit )
-				{
-					best = hit;
-					return true;
-				}
-				else if ( acceptCloser( hit, best ) )
-				{
-					best	 = hit;
-					ray.maxT = hit.t;
-				}
-			}
-		}
-		return false;
-	};
-
-	while ( true )
-	{
-		while ( isBoxIndex( node ) )
-		{
-			const void*	 p	= boxNodes + nodeAddr( node );
-			const float4 q0 = ldg4( p, 0 ), q1 = ldg4( p, 1 ), q2 = ldg4( p, 2 ), q3 = ldg4( p, 3 );
-			const float4 q4 = ldg4( p, 4 ), q5 = ldg4( p, 5 ), q6 = ldg4( p, 6 );
-			const float	 b[24] = { q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w,
-								   q4.x, q4.y, q4.z, q4.w, q5.x, q5.y, q5.z, q5.w, q6.x, q6.y, q6.z, q6.w };
-			const uint32_t c[4] = { __float_as_uint( q0.x ), __float_as_uint( q0.y ), __float_as_uint( q0.z ), __float_as_uint( q0.w ) };
-			float		   d[4];
-			uint32_t	   nhit = 0;
-#pragma unroll
-			for ( int s = 0; s < 4; ++s )
-			{
-				const float fx = __fmul_rn( __fsub_rn( b[6 * s + 3], o.x ), invD.x ), nx = __fmul_rn( __fsub_rn( b[6 * s + 0], o.x ), invD.x );
-				const float fy = __fmul_rn( __fsub_rn( b[6 * s + 4], o.y ), invD.y ), ny = __fmul_rn( __fsub_rn( b[6 * s + 1], o.y ), invD.y );
-				const float fz = __fmul_rn( __fsub_rn( b[6 * s + 5], o.z ), invD.z ), nz = __fmul_rn( __fsub_rn( b[6 * s + 2], o.z ), invD.z );
-				const float t1 = fminf( fminf( fminf( fmaxf( fx, nx ), fmaxf( fy, ny ) ), fmaxf( fz, nz ) ), ray.maxT );
-				const float t0 = fmaxf( fmaxf( fmaxf( fminf( fx, nx ), fminf( fy, ny ) ), fminf( fz, nz ) ), 0.0f );
-				const bool	hit = t0 <= t1 && c[s] != InvalidValue;
-				d[s]			= hit ? t0 : __int_as_float( 0x7f800000 ); // misses sort last
-				nhit += hit;
-			}
-			if ( nhit == 0 )
-			{
-				node = pop();
-				continue;
-			}
-			if ( top + 3 > Depth ) return false;
-			// rank of every child by entry distance (ties: lower slot first)
-			const bool c01 = d[1] < d[0], c02 = d[2] < d[0], c03 = d[3] < d[0], c12 = d[2] < d[1], c13 = d[3] < d[1], c23 = d[3] < d[2];
-			const uint32_t r0 = uint32_t( c01 ) + uint32_t( c02 ) + uint32_t( c03 );
-			const uint32_t r1 = uint32_t( !c01 ) + uint32_t( c12 ) + uint32_t( c13 );
-			const uint32_t r2 = uint32_t( !c02 ) + uint32_t( !c12 ) + uint32_t( c23 );
-			const uint32_t r3 = uint32_t( !c03 ) + uint32_t( !c13 ) + uint32_t( !c23 );
-			// rank 0 is visited next; rank k (0 < k < nhit) goes to stack slot top + nhit - 1 - k (nearest on top)
-			uint32_t* slot = stack + ( top + nhit - 1 ) * BlockThreads;
-			if ( r0 && r0 < nhit ) slot[-int( r0 * BlockThreads )] = c[0];
-			if ( r1 && r1 < nhit ) slot[-int( r1 * BlockThreads )] = c[1];
-			if ( r2 && r2 < nhit ) slot[-int( r2 * BlockThreads )] = c[2];
-			if ( r3 && r3 < nhit ) slot[-int( r3 * BlockThreads )] = c[3];
-			top += nhit - 1;
-			node = r0 == 0 ? c[0] : ( r1 == 0 ? c[1] : ( r2 == 0 ? c[2] : c[3] ) );
-			if constexpr ( PostponeLeaf )
-			{
-				if ( !isBoxIndex( node ) && stash == InvalidValue )
-				{
-					stash = node; // postpone one leaf and keep descending
-					node  = pop();
-				}
-			}
-		}
-		// leaf phase: the postponed leaf, then leaves coming off the stack (ONE code site, so lanes stay converged)
-		bool done = false;
-		while ( true )
-		{
-			uint32_t cur;
-			if ( stash != InvalidValue )
-				cur = stash, stash = InvalidValue;
-			else if ( node != InvalidValue && !isBoxIndex( node ) )
-				cur = node, node = pop();
-			else
-				break;
-			if ( leaf( cur ) )
-			{
-				done = true;
-				break;
-			}
-		}
-		if ( done || node == InvalidValue ) break;
-	}
-	result = best;
-	return true;
-}
 } // namespace hiprt
 
 // ================================================================================================
