@@ -82,7 +82,12 @@ def test_reference_structure_matches_oracle_for_unpaired_input(ctx):
     key = lambda a: np.sort(a["primIndex0"])
     assert np.array_equal(key(cl), key(og.leaves))
     if cb.tobytes() == og.box_nodes.tobytes():
-        assert cl.tobytes() == og.leaves.tobytes()
+        # the reference never writes the 4 padding bytes of a triangle-pair node (offset 48): whatever the
+        # allocation held shows through, so they are excluded from the byte comparison
+        cl, ol = cl.copy(), og.leaves.copy()
+        cl["_pad"] = 0
+        ol["_pad"] = 0
+        assert cl.tobytes() == ol.tobytes()
     else:
         same = (cb["child"] == og.box_nodes["child"]).all(1).mean() if len(cb) == len(og.box_nodes) else 0.0
         print(f"reference structure differs from the IEEE oracle in Morton boundary cases: {same:.4f} of nodes identical")
