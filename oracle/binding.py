@@ -94,6 +94,7 @@ def lib():
         L.orc_scene_count.restype = u32
         L.orc_scene_read.argtypes = [vp, i32, vp]
         L.orc_scene_trace.argtypes = [vp, vp, u32, vp, u32, i32]
+        L.orc_scene_set_inv_matrices.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -259,6 +260,13 @@ class Scene:
     leaves = property(lambda s: s._read(3, INSTANCE_NODE_DTYPE, s.leaf_count))
     sorted_keys = property(lambda s: s._read(4, np.uint32, s.count))
     sorted_vals = property(lambda s: s._read(5, np.uint32, s.count))
+
+    def adopt_transforms(self, instance_leaves):
+        """Use the world->object matrices of externally built instance leaves (INSTANCE_NODE_DTYPE, any order)."""
+        leaves = np.asarray(instance_leaves).view(INSTANCE_NODE_DTYPE)
+        inv = np.zeros((self.count, 3, 4), np.float32)
+        inv[leaves["bits"] & 0xFFFFFF] = leaves["invMatrix"]
+        lib().orc_scene_set_inv_matrices(self.h, _p(inv))
 
     def trace(self, rays, ray_mask=0xFFFFFFFF, tie_mode=1):
         rays = np.ascontiguousarray(rays, RAY_DTYPE)

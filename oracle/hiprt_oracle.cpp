@@ -1382,6 +1382,16 @@ void orc_scene_read( void* h, int what, void* out )
 	}
 }
 
+// Replace the world->object matrices of the instance leaves by externally built ones (12 floats per instance,
+// indexed by instance id). Lets a test separate "the transform was built the same way up to rounding"
+// (checked on the matrices themselves) from "given identical instance nodes, traversal agrees to the strict bar".
+void orc_scene_set_inv_matrices( void* h, const float* invMatrices )
+{
+	SceneObj& s = *static_cast<SceneObj*>( h );
+	for ( InstanceNode& n : s.leaves )
+		if ( !n.identity ) memcpy( n.invMatrix, invMatrices + 12 * size_t( n.primIndex ), 12 * sizeof( float ) );
+}
+
 void orc_scene_trace( void* h, const hiprtRay* rays, uint32_t n, hiprtHit* hits, uint32_t rayMask, int tieMode )
 {
 	SceneObj& s = *static_cast<SceneObj*>( h );

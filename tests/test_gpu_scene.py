@@ -44,10 +44,26 @@ def check_scene_structure(scene, oscene):
 
 # Barycentrics inside an instance are conditioned by (distance to the instance) / (triangle edge): the world ray is
 # moved into object space with a matrix that the GPU and the CPU oracle (and the reference, whose build kernels use
-# fast-math) compute with different rounding, so an object-space offset of a few 1e-6 turns into ~1e-4 in uv on the
-# small triangles of these meshes. t is unaffected (the direction is not re-normalised). Exact-arithmetic
-# transforms (test_integer_translations_are_exact) are held to the strict 1e-5.
+# fast-math) compute with different rounding (fma contraction), so an object-space offset of a few 1e-6 turns into
+# ~1e-4 in uv on the small triangles of these meshes, and into a few 1e-5 in t at grazing incidence. The tests
+# therefore split the claim in two: (1) the world->object matrices agree to 1e-5 (check_scene_structure), and
+# (2) with the SAME matrices (the oracle adopts the ones the GPU build wrote: pin_transforms) hits agree to the
+# strict bar: primID / instanceID exact, t and uv within 1e-5. SCENE_UV_TOL is the loose bound used where the
+# matrices are NOT shared (comparison with the compiled reference).
 SCENE_UV_TOL = 1e-3
+
+
+def matrices_by_instance(leaves):
+    leaves = np.asarray(leaves).view(orc.INSTANCE_NODE_DTYPE)
+    return leaves["invMatrix"][np.argsort(leaves["bits"] & 0xFFFFFF)]
+
+
+def pin_transforms(scene, oscene):
+    """Checks that both sides built the same world->object matrices up to rounding, then makes the oracle use the
+    GPU's so that the traversal comparison is held to the strict bar."""
+    _, leaves = scene.nodes()
+    np.testing.assert_allclose(matrices_by_instance(leaves), matrices_by_instance(oscene.leaves), rtol=1e-5, atol=2e-6)
+    oscene.adopt_transforms(leaves)
 
 
 def camera_rays(extent, n=192):
@@ -80,10 +96,12 @@ def test_instanced_scene_hits_match_oracle(ctx, n_inst):
     check_scene_structure(scene, oscene)
     rays = camera_rays(6.0)
     got = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays)))
+    compare_hits(got, oscene.trace(rays), rel=1e-4, uv_tol=SCENE_UV_TOL)  # independently built matrices
+    pin_transforms(scene, oscene)
     ref = oscene.trace(rays)
     hit = ref["primID"] != orc.INVALID
     assert hit.mean() > (0.05 if n_inst >= 100 else 0.005)
-    ties = compare_hits(got, ref, rel=2e-5, uv_tol=SCENE_UV_TOL)
+    ties = compare_hits(got, ref, rel=1e-5)
     same = got["primID"] == ref["primID"]
     assert np.array_equal(got["instanceIDs"][same & hit, 0], ref["instanceIDs"][same & hit, 0])
     assert ties <= 0.001 * len(rays)
@@ -100,11 +118,12 @@ def test_ray_mask_culls_instances(ctx):
     frames = scenes.random_matrix_frames(n_inst, seed=5, extent=5.0)
     masks = np.where(np.arange(n_inst) % 2 == 0, 0x1, 0x2).astype(np.uint32)
     geoms, scene, oscene = build_pair(ctx, meshes, geom_of, frames, masks)
+    pin_transforms(scene, oscene)
     rays = camera_rays(5.0, 128)
     for ray_mask in (0x1, 0x2, 0x3):
         got = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays), mask=ray_mask))
         ref = oscene.trace(rays, ray_mask=ray_mask)
-        compare_hits(got, ref, rel=2e-5, uv_tol=SCENE_UV_TOL)
+        compare_hits(got, ref, rel=1e-5)
         hit = got["primID"] != api.INVALID
         if ray_mask != 0x3:
             assert np.all(masks[got["instanceIDs"][hit, 0]] == ray_mask)
@@ -125,8 +144,9 @@ def test_srt_frames(ctx):
     geoms, scene, oscene = build_pair(ctx, meshes, np.arange(n_inst) % 3, frames, frame_type=api.FRAME_SRT)
     rays = camera_rays(4.0, 128)
     got = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays)))
+    pin_transforms(scene, oscene)
     ref = oscene.trace(rays)
-    compare_hits(got, ref, rel=5e-5, uv_tol=SCENE_UV_TOL)
+    compare_hits(got, ref, rel=1e-5)
     scene.destroy()
 
 

@@ -9,7 +9,7 @@ from hiprt_b200 import api, scenes
 from oracle import binding as orc
 from tests import helpers as H
 from tests.test_gpu_parity import compare_hits, to_dev
-from tests.test_gpu_scene import SCENE_UV_TOL
+from tests.test_gpu_scene import pin_transforms
 
 pytestmark = pytest.mark.gpu
 
@@ -90,9 +90,10 @@ def test_scene_update_with_new_frames(ctx):
     oscene = orc.Scene(ogeoms, geom_of, new_frames, 1)
     rays = scenes.pinhole_rays(160, 160, (0.0, 2.0, 17.0), (0, 0, 0))
     got = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays)))
+    pin_transforms(scene, oscene)  # same world->object matrices on both sides: strict bar (tests/test_gpu_scene.py)
     ref = oscene.trace(rays)
     assert (ref["primID"] != orc.INVALID).mean() > 0.03
-    compare_hits(got, ref, rel=2e-5, uv_tol=SCENE_UV_TOL)
+    compare_hits(got, ref, rel=1e-5)
     same = got["primID"] == ref["primID"]
     assert np.array_equal(got["instanceIDs"][same, 0], ref["instanceIDs"][same, 0])
     scene.destroy()
