@@ -17,6 +17,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <unordered_map>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -65,7 +66,7 @@ class HostTracePipeline
 	}
 
 	void run(
-		hiprtGeometry geometry, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t user,
+		hiprtGeometry geometry, bool triangles, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t user,
 		uint32_t smCount )
 	{
 		std::lock_guard<std::mutex> lock( m_mutex );
@@ -86,7 +87,7 @@ class HostTracePipeline
 			checkCuda( cudaStreamWaitEvent( m_compute, m_up[slot], 0 ), "cudaStreamWaitEvent" );
 			if ( c >= uint32_t( Slots ) ) checkCuda( cudaStreamWaitEvent( m_compute, m_down[slot], 0 ), "cudaStreamWaitEvent" );
 			if ( geometry )
-				traceGeometry( geometry, m_rays[slot], count, m_hits[slot], type, m_counters + slot * 16, smCount, m_compute );
+				traceGeometry( geometry, triangles, m_rays[slot], count, m_hits[slot], type, m_counters + slot * 16, smCount, m_compute );
 			else
 				traceScene( scene, m_rays[slot], count, m_hits[slot], type, mask, m_compute );
 			checkCuda( cudaGetLastError(), "trace launch" );
@@ -246,6 +247,34 @@ class Context
 	std::string		  cacheDir;
 	HostTracePipeline hostPipeline;
 
+	// ---- primitive kind of built geometries (chooses the library trace kernel without a device read) ----
+	void noteGeometryKind( void* geometry, bool triangles )
+	{
+		std::lock_guard<std::mutex> lock( m_mutex );
+		m_geomKind[geometry] = triangles;
+	}
+	void forgetGeometry( void* geometry )
+	{
+		std::lock_guard<std::mutex> lock( m_mutex );
+		m_geomKind.erase( geometry );
+	}
+	// Geometries this context did not build (e.g. written by another library with the same format): the header
+	// word is read back once per call, after the work queued on `stream`.
+	bool geometryHasTriangles( void* geometry, cudaStream_t stream )
+	{
+		{
+			std::lock_guard<std::mutex> lock( m_mutex );
+			auto						it = m_geomKind.find( geometry );
+			if ( it != m_geomKind.end() ) return it->second;
+		}
+		uint32_t geomType = 0;
+		checkCuda(
+			cudaMemcpyAsync( &geomType, static_cast<uint8_t*>( geometry ) + offsetof( GeomHeader, geomType ), sizeof( uint32_t ), cudaMemcpyDeviceToHost, stream ),
+			"cudaMemcpyAsync" );
+		checkCuda( cudaStreamSynchronize( stream ), "cudaStreamSynchronize" );
+		return geomType & 1u;
+	}
+
 	// ray-batch counters of the persistent trace kernels: a small ring so that launches in flight on different
 	// streams never share one
 	uint32_t* nextWorkCounter()
@@ -271,6 +300,7 @@ class Context
 	hiprtLogLevel		  m_logMask = hiprtLogLevelNone;
 	std::string			  m_lastError;
 	std::map<void*, Pool> m_pools;
+	std::unordered_map<void*, bool> m_geomKind;
 	std::mutex			  m_mutex;
 	uint32_t*			  m_workCounters	= nullptr;
 	uint32_t			  m_workCounterNext = 0;
@@ -387,7 +417,10 @@ hiprtError hiprtDestroyGeometries( hiprtContext context, uint32_t numGeometries,
 		if ( !geometries[i] ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
 		for ( uint32_t i = 0; i < numGeometries; ++i )
+		{
+			ctx( context )->forgetGeometry( geometries[i] );
 			ctx( context )->releaseFromPool( geometries[i] );
+		}
 	} );
 }
 
@@ -421,6 +454,8 @@ hiprtError hiprtBuildGeometries(
 		Context* c = ctx( context );
 		checkBuildFlags( c, buildOptions );
 		cudaStream_t s = static_cast<cudaStream_t>( stream );
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+			c->noteGeometryKind( geometriesOut[i], buildInputs[i].type == hiprtPrimitiveTypeTriangleMesh );
 		if ( buildOperation == hiprtBuildOperationUpdate )
 		{
 			for ( uint32_t i = 0; i < numGeometries; ++i )
@@ -515,10 +550,14 @@ hiprtError hiprtCompactGeometries(
 			h.size		= sizes[i];
 			checkCuda( cudaMemcpyAsync( dst, &h, sizeof( GeomHeader ), cudaMemcpyHostToDevice, s ), "write header" );
 			*geometriesOut[i] = reinterpret_cast<hiprtGeometry>( dst );
+			c->noteGeometryKind( dst, headers[i].geomType & 1u );
 		}
 		checkCuda( cudaStreamSynchronize( s ), "cudaStreamSynchronize" );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
+		{
+			c->forgetGeometry( geometriesIn[i] );
 			c->releaseFromPool( geometriesIn[i] );
+		}
 	} );
 }
 
@@ -783,6 +822,7 @@ hiprtError hiprtLoadGeometry( hiprtContext context, hiprtGeometry& geometryOut, 
 		memcpy( buf.data(), &h, sizeof( h ) );
 		checkCuda( cudaMemcpy( out[0], buf.data(), buf.size(), cudaMemcpyHostToDevice ), "cudaMemcpy" );
 		geometryOut = reinterpret_cast<hiprtGeometry>( out[0] );
+		ctx( context )->noteGeometryKind( out[0], h.geomType & 1u );
 	} );
 }
 
@@ -881,7 +921,8 @@ hiprtError hiprtB200TraceGeometry(
 {
 	if ( !context || !geometry || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
-		traceGeometry( geometry, rays, numRays, hits, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ) );
+		const bool triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) );
+		traceGeometry( geometry, triangles, rays, numRays, hits, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ) );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
 }
@@ -907,7 +948,10 @@ hiprtError hiprtB200TraceGeometryHost(
 	hiprtContext context, hiprtGeometry geometry, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtApiStream stream )
 {
 	if ( !context || !geometry || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
-	return guarded( context, [&] { ctx( context )->hostPipeline.run( geometry, nullptr, hostRays, numRays, hostHits, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount ); } );
+	return guarded( context, [&] {
+		const bool triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) );
+		ctx( context )->hostPipeline.run( geometry, triangles, nullptr, hostRays, numRays, hostHits, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount );
+	} );
 }
 
 hiprtError hiprtB200TraceSceneHost(
@@ -921,7 +965,7 @@ hiprtError hiprtB200TraceSceneHost(
 	hiprtApiStream	   stream )
 {
 	if ( !context || !scene || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
-	return guarded( context, [&] { ctx( context )->hostPipeline.run( nullptr, scene, hostRays, numRays, hostHits, type, mask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount ); } );
+	return guarded( context, [&] { ctx( context )->hostPipeline.run( nullptr, false, scene, hostRays, numRays, hostHits, type, mask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount ); } );
 }
 
 hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount, size_t* offsetsOut, uint32_t numOffsets )

@@ -6,8 +6,9 @@
 namespace hiprt
 {
 // workCounter: one device uint32 the persistent variant uses as its ray-batch counter (reset on `stream` before the launch)
+// triangles: the geometry holds triangle pairs (fast kernel) rather than custom primitives (generic kernel)
 void traceGeometry(
-	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream );
+	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream );
 void traceScene(
 	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t stream );
 } // namespace hiprt

@@ -18,6 +18,7 @@ namespace hiprt
 {
 constexpr uint32_t TraceBlock		= 128; // scene kernels
 constexpr uint32_t SharedStackDepth = 12;
+constexpr uint32_t FullMask			= 0xFFFFFFFFu;
 
 // Top `SharedDepth` entries in shared memory (entry e of a thread at base[e * 32], one bank per lane), the rest of the
 // 64 entries the reference's private stack offers in a per-thread local array.
@@ -129,6 +130,255 @@ __global__ void __launch_bounds__( Block ) traceGeometryKernel(
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path for triangle geometries without custom functions (the library's own default table rejects
+// nothing): same slab and Moller-Trumbore arithmetic as the generic traversal objects (the helpers
+// of hiprt_device.h), restructured around what ncu shows to be the limiter of one-thread-per-ray
+// traversal on sm_100a: the half-rate ALU pipe (min/max, select, compare), not the FMA pipe and not memory
+// (profiles/r01_ncu_trace_fast_*.csv).
+//  * while-while loop with warp votes (box phase / leaf phase), so lanes of a warp execute the same phase;
+//    the box phase ends when no lane has a box node, or fewer than `BoxQuorum` have one while some lane waits
+//    with a leaf;
+//  * when every ray of a warp has the same direction octant and finite non-zero 1/d, the near and far plane of
+//    each slab are known at compile time of the octant's code copy: (near - o) * invD and (far - o) * invD are
+//    the very products the reference takes min/max of (Aabb.h:92-101; rounding is monotonic, lo <= hi), so the
+//    six per-child min/max disappear with bit-identical results. Mixed warps and rays with a zero direction
+//    component (where the reference's min/max see NaN/inf) run the general code;
+//  * stack top in a register, entries in lane-interleaved shared memory (local array only beyond SharedDepth);
+//  * children ordered by a 5-exchange network on (entry distance, index) with misses at -inf, so the hit
+//    children are the LAST n of the four: all four are stored unconditionally far-to-near above the stack top,
+//    the top moves by n and the nearest child is simply popped -- no per-child predicates;
+//  * closest hit keeps only (t, leaf, triangle) in the loop; uv mapping and the normal are produced once
+//    per ray at the end by re-running the reference-order test on the winning triangle.
+// The winner is the minimum of (t, primID), as in hiprt::acceptCloser.
+constexpr uint32_t GeneralOctant = 8;
+
+// 32-byte read-only load (LDG.E.256, sm_100+): a 128-byte box node is 4 of these instead of 7 16-byte loads, a
+// 64-byte triangle pair 2 instead of 4 -- the traversal is bound by L1TEX wavefronts (one per distinct line and
+// instruction when the lanes of a warp are in different nodes), so fewer, wider loads are the lever.
+struct F8
+{
+	float v[8];
+};
+__device__ __forceinline__ F8 ldg8( const void* p, uint32_t i )
+{
+	F8 r;
+	asm( "ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		 : "=f"( r.v[0] ), "=f"( r.v[1] ), "=f"( r.v[2] ), "=f"( r.v[3] ), "=f"( r.v[4] ), "=f"( r.v[5] ), "=f"( r.v[6] ), "=f"( r.v[7] )
+		 : "l"( reinterpret_cast<const char*>( p ) + 32u * i ) );
+	return r;
+}
+
+// Slab test of child `s` of a box node. Octant bit k set = direction component k negative (near plane is hi).
+template <uint32_t Octant>
+__device__ __forceinline__ bool slabTest( const float* b, const float3 o, const float3 invD, float maxT, float& t0Out )
+{
+	if constexpr ( Octant == GeneralOctant )
+	{
+		const float fx = __fmul_rn( __fsub_rn( b[3], o.x ), invD.x ), nx = __fmul_rn( __fsub_rn( b[0], o.x ), invD.x );
+		const float fy = __fmul_rn( __fsub_rn( b[4], o.y ), invD.y ), ny = __fmul_rn( __fsub_rn( b[1], o.y ), invD.y );
+		const float fz = __fmul_rn( __fsub_rn( b[5], o.z ), invD.z ), nz = __fmul_rn( __fsub_rn( b[2], o.z ), invD.z );
+		const float t1 = fminf( fminf( fminf( fmaxf( fx, nx ), fmaxf( fy, ny ) ), fmaxf( fz, nz ) ), maxT );
+		const float t0 = fmaxf( fmaxf( fmaxf( fminf( fx, nx ), fminf( fy, ny ) ), fminf( fz, nz ) ), 0.0f );
+		t0Out		   = t0;
+		return t0 <= t1;
+	}
+	else
+	{
+		constexpr int nxI = ( Octant & 1u ) ? 3 : 0, nyI = ( Octant & 2u ) ? 4 : 1, nzI = ( Octant & 4u ) ? 5 : 2;
+		constexpr int fxI = 3 - nxI, fyI = 5 - nyI, fzI = 7 - nzI;
+		const float	  nx = __fmul_rn( __fsub_rn( b[nxI], o.x ), invD.x ), fx = __fmul_rn( __fsub_rn( b[fxI], o.x ), invD.x );
+		const float	  ny = __fmul_rn( __fsub_rn( b[nyI], o.y ), invD.y ), fy = __fmul_rn( __fsub_rn( b[fyI], o.y ), invD.y );
+		const float	  nz = __fmul_rn( __fsub_rn( b[nzI], o.z ), invD.z ), fz = __fmul_rn( __fsub_rn( b[fzI], o.z ), invD.z );
+		const float	  t1 = fminf( fminf( fminf( fx, fy ), fz ), maxT );
+		const float	  t0 = fmaxf( fmaxf( fmaxf( nx, ny ), nz ), 0.0f );
+		t0Out			 = t0;
+		return t0 <= t1;
+	}
+}
+
+// One box-node visit: tests the four children, leaves the hit ones sorted (nearest last) in c[4-n..3].
+template <uint32_t Octant>
+__device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxNodes, uint32_t node, const float3 o, const float3 invD, float maxT, uint32_t c[4] )
+{
+	const void* p  = boxNodes + ( node >> 4 );
+	const F8	w0 = ldg8( p, 0 ), w1 = ldg8( p, 1 ), w2 = ldg8( p, 2 ), w3 = ldg8( p, 3 );
+	const float b[24] = { w0.v[4], w0.v[5], w0.v[6], w0.v[7], w1.v[0], w1.v[1], w1.v[2], w1.v[3], w1.v[4], w1.v[5], w1.v[6], w1.v[7],
+						  w2.v[0], w2.v[1], w2.v[2], w2.v[3], w2.v[4], w2.v[5], w2.v[6], w2.v[7], w3.v[0], w3.v[1], w3.v[2], w3.v[3] };
+	c[0] = __float_as_uint( w0.v[0] ), c[1] = __float_as_uint( w0.v[1] ), c[2] = __float_as_uint( w0.v[2] ), c[3] = __float_as_uint( w0.v[3] );
+	float	 d[4];
+	uint32_t n = 0;
+#pragma unroll
+	for ( int s = 0; s < 4; ++s )
+	{
+		float	   t0;
+		const bool hit = slabTest<Octant>( b + 6 * s, o, invD, maxT, t0 ) && c[s] != InvalidValue; // (unused slots need not hold the empty box)
+		d[s]		   = hit ? t0 : __int_as_float( 0xff800000 );
+		c[s]		   = hit ? c[s] : InvalidValue;
+		n += hit ? 1u : 0u;
+	}
+#define HIPRT_B200_CSWAP( A, B )                                     \
+	{                                                                \
+		const bool	   sw = d[B] < d[A];                             \
+		const float	   lo = sw ? d[B] : d[A], hi = sw ? d[A] : d[B]; \
+		const uint32_t cl = sw ? c[B] : c[A], ch = sw ? c[A] : c[B]; \
+		d[A] = lo, d[B] = hi, c[A] = cl, c[B] = ch;                  \
+	}
+	HIPRT_B200_CSWAP( 0, 2 )
+	HIPRT_B200_CSWAP( 1, 3 )
+	HIPRT_B200_CSWAP( 0, 1 )
+	HIPRT_B200_CSWAP( 2, 3 )
+	HIPRT_B200_CSWAP( 1, 2 )
+#undef HIPRT_B200_CSWAP
+	return n;
+}
+
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum>
+__global__ void __launch_bounds__( Block ) traceTrianglesKernel(
+	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits )
+{
+	__shared__ uint32_t sStack[Block * SharedDepth];
+	constexpr uint32_t	TotalDepth = 64; // the reference's private stack size
+	const uint32_t		index	   = blockIdx.x * Block + threadIdx.x;
+	const bool			live	   = index < numRays;
+	const GeomHeader*	header	   = reinterpret_cast<const GeomHeader*>( geom );
+	const Box4Node* __restrict__ boxNodes		 = header->boxNodes;
+	const TrianglePairNode* __restrict__ leaves = reinterpret_cast<const TrianglePairNode*>( header->primNodes );
+
+	uint32_t* const stackBase = sStack + ( threadIdx.x & 31u ) + ( threadIdx.x >> 5 ) * 32u * SharedDepth;
+	uint32_t		localStack[TotalDepth - SharedDepth];
+	uint32_t		top = 0;
+
+	hiprtRay	 ray	  = loadRay( rays, live ? index : 0u );
+	const float3 invD	  = rcp3( ray.direction );
+	const float	 maxT0	  = ray.maxT;
+	uint32_t	 bestRef  = InvalidValue; // (leaf address << 1) | triangle of the pair
+	uint32_t	 bestPrim = InvalidValue;
+	bool		 overflow = false;
+	uint32_t	 node	  = live ? RootIndex : InvalidValue;
+
+	// direction octant of the warp, or GeneralOctant when its rays disagree / have a zero, denormal-reciprocal or
+	// non-finite direction component
+	uint32_t octant = ( ray.direction.x < 0.0f ? 1u : 0u ) | ( ray.direction.y < 0.0f ? 2u : 0u ) | ( ray.direction.z < 0.0f ? 4u : 0u );
+	{
+		const bool regular = isfinite( invD.x ) && isfinite( invD.y ) && isfinite( invD.z ) && invD.x != 0.0f && invD.y != 0.0f && invD.z != 0.0f &&
+							 isfinite( ray.origin.x ) && isfinite( ray.origin.y ) && isfinite( ray.origin.z );
+		const uint32_t first = __shfl_sync( FullMask, octant, 0 );
+		if ( !__all_sync( FullMask, !live || ( regular && octant == first ) ) ) octant = GeneralOctant;
+		else octant = first;
+	}
+
+	auto pop = [&]() -> uint32_t {
+		if ( top == 0 ) return InvalidValue;
+		--top;
+		return top < SharedDepth ? stackBase[top * 32u] : localStack[top - SharedDepth];
+	};
+
+	while ( __any_sync( FullMask, node != InvalidValue ) )
+	{
+		// ---- box phase
+		while ( true )
+		{
+			const bool	   isBox	= isBoxIndex( node );
+			const uint32_t boxLanes = __ballot_sync( FullMask, isBox );
+			if ( boxLanes == 0 ) break;
+			if ( BoxQuorum > 1 && __popc( boxLanes ) < BoxQuorum && __any_sync( FullMask, !isBox && node != InvalidValue ) ) break;
+			if ( isBox )
+			{
+				uint32_t c[4];
+				uint32_t n;
+				switch ( octant ) // warp-uniform
+				{
+				case 0: n = visitBox4<0>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 1: n = visitBox4<1>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 2: n = visitBox4<2>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 3: n = visitBox4<3>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 4: n = visitBox4<4>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 5: n = visitBox4<5>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 6: n = visitBox4<6>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 7: n = visitBox4<7>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				default: n = visitBox4<GeneralOctant>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				}
+				// hit children: c[4-n..3], nearest first. Far-to-near onto the stack, then the nearest is popped.
+				if ( top + 4 <= SharedDepth )
+				{
+					uint32_t* slot = stackBase + top * 32u;
+					slot[0] = c[3], slot[32] = c[2], slot[64] = c[1], slot[96] = c[0];
+					top += n;
+					node = InvalidValue;
+					if ( top != 0 )
+					{
+						--top;
+						node = stackBase[top * 32u];
+					}
+				}
+				else if ( top + 3 > TotalDepth )
+				{
+					overflow = true;
+					node	 = InvalidValue;
+					top		 = 0;
+				}
+				else
+				{
+#pragma unroll
+					for ( int k = 3; k >= 0; --k )
+						if ( c[k] != InvalidValue )
+						{
+							if ( top < SharedDepth )
+								stackBase[top * 32u] = c[k];
+							else
+								localStack[top - SharedDepth] = c[k];
+							++top;
+						}
+					node = pop();
+				}
+			}
+		}
+
+		// ---- leaf phase
+		if ( node != InvalidValue && !isBoxIndex( node ) )
+		{
+			const uint32_t addr = node >> 3;
+			const void*	   p	= leaves + addr;
+			const F8	   l0 = ldg8( p, 0 ), l1 = ldg8( p, 1 );
+			const uint32_t prim0 = __float_as_uint( l1.v[5] ), prim1 = __float_as_uint( l1.v[6] );
+			const float3   pv0 = make_float3( l0.v[0], l0.v[1], l0.v[2] ), pv1 = make_float3( l0.v[3], l0.v[4], l0.v[5] );
+			const float3   pv2 = make_float3( l0.v[6], l0.v[7], l1.v[0] ), pv3 = make_float3( l1.v[1], l1.v[2], l1.v[3] );
+			bool		   found = false;
+			HitTriangle	   h;
+			if ( intersectTriangle( pv0, pv1, pv2, ray, h ) && ( h.t < ray.maxT || prim0 < bestPrim ) )
+			{
+				ray.maxT = h.t, bestRef = addr << 1, bestPrim = prim0;
+				found = true;
+			}
+			if ( prim0 != prim1 && !( Type == hiprtTraversalTerminateAtAnyHit && found ) )
+			{
+				if ( intersectTriangle( pv1, pv3, pv2, ray, h ) && ( h.t < ray.maxT || prim1 < bestPrim ) )
+				{
+					ray.maxT = h.t, bestRef = ( addr << 1 ) | 1u, bestPrim = prim1;
+					found = true;
+				}
+			}
+			if ( Type == hiprtTraversalTerminateAtAnyHit && found )
+			{
+				node = InvalidValue;
+				top	 = 0;
+			}
+			else
+				node = pop();
+		}
+	}
+
+	if ( !live ) return;
+	hiprtHit hit;
+	if ( bestRef != InvalidValue && !overflow )
+	{
+		ray.maxT = maxT0;
+		intersectPairTriangle( leaves, bestRef >> 1, bestRef & 1u, ray, hit );
+	}
+	storeHit( hits, index, hit );
+}
+
 template <hiprtTraversalType Type>
 __global__ void __launch_bounds__( TraceBlock ) traceSceneKernel(
 	hiprtScene scene, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, hiprtRayMask mask )
@@ -155,7 +405,7 @@ static int traceVariant()
 {
 	static const int v = [] {
 		const char* e = getenv( "HIPRT_B200_TRACE_VARIANT" );
-		return e ? atoi( e ) : 1;
+		return e ? atoi( e ) : -1;
 	}();
 	return v;
 }
@@ -177,11 +427,37 @@ static void launchGeometry( hiprtGeometry geom, const hiprtRay* rays, uint32_t n
 }
 
 // Tuning variants (HIPRT_B200_TRACE_VARIANT): block size / shared stack depth / persistent warps.
+template <uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum>
+static void launchTriangles( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, bool any, cudaStream_t stream )
+{
+	const uint32_t blocks = DivideRoundUp( numRays, Block );
+	if ( any )
+		traceTrianglesKernel<hiprtTraversalTerminateAtAnyHit, Block, SharedDepth, BoxQuorum><<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits );
+	else
+		traceTrianglesKernel<hiprtTraversalTerminateAtClosestHit, Block, SharedDepth, BoxQuorum><<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits );
+}
+
 void traceGeometry(
-	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
+	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount,
+	cudaStream_t stream )
 {
 	if ( numRays == 0 ) return;
 	const bool any = type == hiprtTraversalTerminateAtAnyHit;
+	if ( triangles )
+	{
+		switch ( traceVariant() )
+		{
+		case 10: launchTriangles<128, 32, 1>( geom, rays, numRays, hits, any, stream ); return;
+		case 11: launchTriangles<128, 32, 8>( geom, rays, numRays, hits, any, stream ); return;
+		case 12: launchTriangles<128, 32, 16>( geom, rays, numRays, hits, any, stream ); return;
+		case 13: launchTriangles<64, 32, 8>( geom, rays, numRays, hits, any, stream ); return;
+		case 14: launchTriangles<128, 24, 8>( geom, rays, numRays, hits, any, stream ); return;
+		case 15: launchTriangles<128, 16, 8>( geom, rays, numRays, hits, any, stream ); return;
+		case 16: launchTriangles<128, 32, 24>( geom, rays, numRays, hits, any, stream ); return;
+		case 1: break; // generic traversal objects (as a user kernel would use them)
+		default: launchTriangles<128, 32, 16>( geom, rays, numRays, hits, any, stream ); return;
+		}
+	}
 #define HIPRT_B200_LAUNCH( B, D, P )                                                                                                       \
 	if ( any )                                                                                                                             \
 		launchGeometry<hiprtTraversalTerminateAtAnyHit, B, D, P>( geom, rays, numRays, hits, workCounter, smCount, stream );               \

@@ -82,6 +82,7 @@ def lib():
         L.orc_lbvh_topology.argtypes = [vp, vp, u32, u32, vp]
         L.orc_lbvh_topology.restype = u32
         L.orc_geometry_trace.argtypes = [vp, vp, u32, vp, i32, vp]
+        L.orc_geometry_trace_visits.argtypes = [vp, vp, u32, vp, vp]
         L.orc_trace_nodes.argtypes = [vp, vp, vp, u32, vp, i32]
         L.orc_geometry_trace_all.argtypes = [vp, vp, u32, vp, vp, vp, u32]
         L.orc_geometry_trace_all.restype = u64
@@ -181,6 +182,14 @@ class Geometry:
         visits = np.zeros(2, np.uint32)
         lib().orc_geometry_trace(self.h, _p(rays), len(rays), _p(hits), tie_mode, _p(visits))
         return (hits, visits) if want_visits else hits
+
+    def trace_visits(self, rays):
+        """Per-ray (box visits, leaf visits) of the closest-hit traversal."""
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        bv = np.zeros(len(rays), np.uint32)
+        lv = np.zeros(len(rays), np.uint32)
+        lib().orc_geometry_trace_visits(self.h, _p(rays), len(rays), _p(bv), _p(lv))
+        return bv, lv
 
     def trace_all(self, rays, max_per_ray=16):
         rays = np.ascontiguousarray(rays, RAY_DTYPE)

@@ -1192,6 +1192,20 @@ void orc_geometry_trace( void* h, const hiprtRay* rays, uint32_t n, hiprtHit* hi
 	if ( visits ) visits[0] = bv, visits[1] = lv;
 }
 
+// Per-ray visit counts (box nodes, leaves) of the closest-hit traversal: input of the SIMT-efficiency model
+// in tools/simt_model.py.
+void orc_geometry_trace_visits( void* h, const hiprtRay* rays, uint32_t n, uint32_t* boxVisits, uint32_t* leafVisits )
+{
+	Geometry& g = *static_cast<Geometry*>( h );
+	BvhView	  v{ g.wide.boxes.data(), g.leaves.data() };
+	for ( uint32_t i = 0; i < n; ++i )
+	{
+		uint32_t bv = 0, lv = 0;
+		traceClosest( v, rays[i], 1, &bv, &lv );
+		boxVisits[i] = bv, leafVisits[i] = lv;
+	}
+}
+
 // Trace through arbitrary node arrays in the library's HBM format (e.g. a GPU-built structure
 // copied to the host): checks traversal independently of the builder.
 void orc_trace_nodes( const void* boxNodes, const void* triNodes, const hiprtRay* rays, uint32_t n, hiprtHit* hits, int tieMode )

@@ -255,3 +255,57 @@ def test_fast_build_structure_is_valid(ctx):
     geom = ctx.build(to_dev(ctx, verts), to_dev(ctx, idx))
     H.validate_wide_bvh(*geom.nodes(), len(idx))
     geom.destroy()
+
+
+def _octant_rays(lo, hi, n, seed):
+    """Warps of 32 rays sharing a direction octant (the fast kernel's specialised slab code), then warps whose rays
+    have exactly-zero / negative-zero direction components or mixed octants (its general code)."""
+    rng = np.random.default_rng(seed)
+    centre, ext = (lo + hi) / 2, (hi - lo)
+    origins, dirs = [], []
+    for octant in range(8):
+        sign = np.array([-1.0 if octant & (1 << k) else 1.0 for k in range(3)])
+        o = centre - sign * ext * rng.uniform(0.6, 1.4, (n, 3))
+        target = centre + ext * rng.uniform(-0.5, 0.5, (n, 3))
+        d = np.abs(target - o) * sign + sign * 1e-3
+        origins.append(o), dirs.append(d)
+    # axis-aligned and planar rays: zero components (both signs of zero)
+    for axis in range(3):
+        for s in (1.0, -1.0):
+            o = centre + ext * rng.uniform(-0.5, 0.5, (n, 3))
+            o[:, axis] = centre[axis] - s * ext[axis] * 1.2
+            d = np.zeros((n, 3))
+            d[:, axis] = s
+            d[::2, (axis + 1) % 3] = -0.0
+            d[::3, (axis + 2) % 3] = 0.25 * s
+            origins.append(o), dirs.append(d)
+    o = centre + ext * rng.uniform(-1.3, 1.3, (n, 3))
+    d = rng.normal(size=(n, 3))
+    origins.append(o), dirs.append(d)
+    return orc.make_rays(np.concatenate(origins).astype(np.float32), np.concatenate(dirs).astype(np.float32))
+
+
+@pytest.mark.parametrize("mesh", ["cornell", "sphere", "soup"])
+def test_fast_kernel_octants_and_degenerate_directions(ctx, mesh):
+    """The library's triangle kernel takes the near/far planes from the warp's direction octant when it can; hits must be
+    bit-identical to the oracle (which restates the reference's min/max slab test) in every octant, for rays with
+    zero / negative-zero direction components and for mixed warps."""
+    if mesh == "cornell":
+        verts, _, _ = H.cornell_box()
+        idx = np.arange(96, dtype=np.uint32).reshape(-1, 3)
+    elif mesh == "sphere":
+        verts, idx = scenes.sphere_mesh(96, 48)
+    else:
+        verts, idx = scenes.random_soup(3000, seed=11, extent=1.0, size=0.08), None
+    geom = ctx.build(to_dev(ctx, verts), None if idx is None else to_dev(ctx, idx))
+    og = orc.Geometry(verts, idx)
+    rays = _octant_rays(verts.min(0), verts.max(0), 1024, seed=5)
+    got = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays)))
+    ref = og.trace(rays, tie_mode=1)
+    assert (ref["primID"] != orc.INVALID).mean() > 0.2
+    assert np.array_equal(got["primID"], ref["primID"])
+    hit = ref["primID"] != orc.INVALID
+    assert np.array_equal(got["t"][hit], ref["t"][hit]) and np.array_equal(got["uv"][hit], ref["uv"][hit])
+    occluded = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays), kind=api.ANY_HIT))
+    assert np.array_equal(occluded["primID"] != api.INVALID, ref["primID"] != orc.INVALID)
+    geom.destroy()
