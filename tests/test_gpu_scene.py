@@ -62,7 +62,9 @@ def pin_transforms(scene, oscene):
     """Checks that both sides built the same world->object matrices up to rounding, then makes the oracle use the
     GPU's so that the traversal comparison is held to the strict bar."""
     _, leaves = scene.nodes()
-    np.testing.assert_allclose(matrices_by_instance(leaves), matrices_by_instance(oscene.leaves), rtol=1e-5, atol=2e-6)
+    mine, theirs = matrices_by_instance(leaves), matrices_by_instance(oscene.leaves)
+    # the translation column is -dot(row, t): its absolute rounding error scales with |t|
+    np.testing.assert_allclose(mine, theirs, rtol=1e-5, atol=5e-7 * max(1.0, float(np.abs(theirs).max())))
     oscene.adopt_transforms(leaves)
 
 
