@@ -89,7 +89,7 @@ class HostTracePipeline
 			if ( geometry )
 				traceGeometry( geometry, triangles, m_rays[slot], count, m_hits[slot], type, m_counters + slot * 16, smCount, m_compute );
 			else
-				traceScene( scene, m_rays[slot], count, m_hits[slot], type, mask, m_compute );
+				traceScene( scene, m_rays[slot], count, m_hits[slot], type, mask, m_counters + slot * 16, smCount, m_compute );
 			checkCuda( cudaGetLastError(), "trace launch" );
 			checkCuda( cudaEventRecord( m_traced[slot], m_compute ), "cudaEventRecord" );
 
@@ -939,7 +939,7 @@ hiprtError hiprtB200TraceScene(
 {
 	if ( !context || !scene || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
-		traceScene( scene, rays, numRays, hits, type, mask, static_cast<cudaStream_t>( stream ) );
+		traceScene( scene, rays, numRays, hits, type, mask, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ) );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
 }

@@ -10,5 +10,6 @@ namespace hiprt
 void traceGeometry(
 	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream );
 void traceScene(
-	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t stream );
+	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, uint32_t* workCounter, uint32_t smCount,
+	cudaStream_t stream );
 } // namespace hiprt

@@ -476,10 +476,241 @@ void traceGeometry(
 #undef HIPRT_B200_LAUNCH
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fast path for single-level scenes (what the library's own scene kernel covers: instances of geometries, static
+// transforms, no custom intersection functions -- the library's default table rejects every custom primitive, so
+// instances of custom-primitive geometries are skipped). Same structure as traceTrianglesWarp: while-while with warp votes,
+// stack top in a register, four children stored unconditionally, closest hit kept as (t, instance leaf, pair leaf,
+// triangle) and completed once at the end. An instance is entered by pushing a marker; popping it restores the world ray.
+// Arithmetic (transform, slab, triangle) is that of the generic hiprtSceneTraversalT, winner = min (t, instanceID, primID).
+constexpr uint32_t InstanceExitMarker = 0xFFFFFFFEu; // instance-typed index no scene can hold (2^24 instance limit)
+
+template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum>
+__device__ __forceinline__ void traceSceneWarp(
+	const SceneHeader* __restrict__ scene,
+	const hiprtRay* __restrict__ rays,
+	hiprtHit* __restrict__ hits,
+	uint32_t		index,
+	bool			live,
+	hiprtRayMask	rayMask,
+	uint32_t* const stackBase )
+{
+	constexpr uint32_t TotalDepth = 64;
+	uint32_t		   localStack[TotalDepth - SharedDepth];
+	uint32_t		   top = 0;
+
+	const Box4Node* __restrict__ sceneBoxes	   = scene->boxNodes;
+	const InstanceNode* __restrict__ instNodes = scene->primNodes;
+	const Box4Node*			boxNodes		   = sceneBoxes;
+	const TrianglePairNode* leaves			   = nullptr;
+
+	hiprtRay	ray		 = loadRay( rays, live ? index : 0u );
+	float3		invD	 = rcp3( ray.direction );
+	const float maxT0	 = ray.maxT;
+	uint32_t	bestRef	 = InvalidValue; // (pair leaf address << 1) | triangle
+	uint32_t	bestPrim = InvalidValue, bestId = InvalidValue, bestInst = InvalidValue;
+	uint32_t	curInst	 = InvalidValue; // instance leaf (node index) the ray is inside of
+	uint32_t	curId	 = InvalidValue;
+	bool		overflow = false;
+	uint32_t	node	 = live ? RootIndex : InvalidValue;
+
+	auto push = [&]( uint32_t v ) {
+		if ( top < SharedDepth )
+			stackBase[top * 32u] = v;
+		else
+			localStack[top - SharedDepth] = v;
+		++top;
+	};
+	auto pop = [&]() -> uint32_t {
+		if ( top == 0 ) return InvalidValue;
+		--top;
+		return top < SharedDepth ? stackBase[top * 32u] : localStack[top - SharedDepth];
+	};
+
+	while ( __any_sync( FullMask, node != InvalidValue ) )
+	{
+		// ---- box phase (scene level and geometry level alike)
+		while ( true )
+		{
+			const bool	   isBox	= isBoxIndex( node );
+			const uint32_t boxLanes = __ballot_sync( FullMask, isBox );
+			if ( boxLanes == 0 ) break;
+			if ( BoxQuorum > 1 && __popc( boxLanes ) < BoxQuorum && __any_sync( FullMask, !isBox && node != InvalidValue ) ) break;
+			if ( isBox )
+			{
+				uint32_t	   c[4];
+				const uint32_t n = visitBox4<GeneralOctant>( boxNodes, node, ray.origin, invD, ray.maxT, c );
+				if ( top + 4 <= SharedDepth )
+				{
+					uint32_t* slot = stackBase + top * 32u;
+					slot[0] = c[3], slot[32] = c[2], slot[64] = c[1], slot[96] = c[0];
+					top += n;
+					node = InvalidValue;
+					if ( top != 0 )
+					{
+						--top;
+						node = stackBase[top * 32u];
+					}
+				}
+				else if ( top + 4 > TotalDepth )
+				{
+					overflow = true;
+					node	 = InvalidValue;
+					top		 = 0;
+				}
+				else
+				{
+#pragma unroll
+					for ( int k = 3; k >= 0; --k )
+						if ( c[k] != InvalidValue ) push( c[k] );
+					node = pop();
+				}
+			}
+		}
+
+		// ---- leaf phase: leave an instance / enter an instance / test a triangle pair
+		if ( node != InvalidValue && !isBoxIndex( node ) )
+		{
+			if ( node == InstanceExitMarker )
+			{
+				const float	   maxT	 = ray.maxT;
+				ray					 = loadRay( rays, index );
+				ray.maxT			 = maxT;
+				invD				 = rcp3( ray.direction );
+				boxNodes			 = sceneBoxes;
+				curInst				 = InvalidValue;
+				node				 = pop();
+			}
+			else if ( curInst == InvalidValue )
+			{
+				const InstanceNode* in	 = instNodes + ( node >> 4 );
+				const uint4			meta = __ldg( reinterpret_cast<const uint4*>( in ) + 3 ); // {geometry.lo, geometry.hi, mask, bits}
+				bool				enter = ( meta.z & rayMask ) != 0u;
+				if ( enter )
+				{
+					const GeomHeader* g = reinterpret_cast<const GeomHeader*>( ( uint64_t( meta.y ) << 32 ) | meta.x );
+					const uint4 ptrs	= __ldg( reinterpret_cast<const uint4*>( g ) ); // {boxNodes, primNodes}
+					const uint32_t geomType = __ldg( &g->geomType );
+					enter					= geomType & 1u; // custom primitives cannot hit through the default function table
+					if ( enter && top + 1 >= TotalDepth )
+					{
+						overflow = true;
+						enter	 = false;
+						top		 = 0;
+					}
+					if ( enter )
+					{
+						push( InstanceExitMarker );
+						if ( !( ( meta.w >> 26 ) & 1u ) )
+						{
+							const float maxT = ray.maxT;
+							ray				 = transformRayToObject( in, ray );
+							ray.maxT		 = maxT;
+							invD			 = rcp3( ray.direction );
+						}
+						boxNodes = reinterpret_cast<const Box4Node*>( ( uint64_t( ptrs.y ) << 32 ) | ptrs.x );
+						leaves	 = reinterpret_cast<const TrianglePairNode*>( ( uint64_t( ptrs.w ) << 32 ) | ptrs.z );
+						curInst	 = node;
+						curId	 = meta.w & 0xFFFFFFu;
+						node	 = RootIndex;
+					}
+				}
+				if ( !enter ) node = pop();
+			}
+			else
+			{
+				const uint32_t addr = node >> 3;
+				const void*	   p	= leaves + addr;
+				const F8	   l0 = ldg8( p, 0 ), l1 = ldg8( p, 1 );
+				const uint32_t prim0 = __float_as_uint( l1.v[5] ), prim1 = __float_as_uint( l1.v[6] );
+				const float3   pv0 = make_float3( l0.v[0], l0.v[1], l0.v[2] ), pv1 = make_float3( l0.v[3], l0.v[4], l0.v[5] );
+				const float3   pv2 = make_float3( l0.v[6], l0.v[7], l1.v[0] ), pv3 = make_float3( l1.v[1], l1.v[2], l1.v[3] );
+				bool		   found = false;
+				HitTriangle	   h;
+				if ( intersectTriangle( pv0, pv1, pv2, ray, h ) && ( h.t < ray.maxT || curId < bestId || ( curId == bestId && prim0 < bestPrim ) ) )
+				{
+					ray.maxT = h.t, bestRef = addr << 1, bestPrim = prim0, bestId = curId, bestInst = curInst;
+					found = true;
+				}
+				if ( prim0 != prim1 && !( Type == hiprtTraversalTerminateAtAnyHit && found ) )
+				{
+					if ( intersectTriangle( pv1, pv3, pv2, ray, h ) && ( h.t < ray.maxT || curId < bestId || ( curId == bestId && prim1 < bestPrim ) ) )
+					{
+						ray.maxT = h.t, bestRef = ( addr << 1 ) | 1u, bestPrim = prim1, bestId = curId, bestInst = curInst;
+						found = true;
+					}
+				}
+				if ( Type == hiprtTraversalTerminateAtAnyHit && found )
+				{
+					node = InvalidValue;
+					top	 = 0;
+				}
+				else
+					node = pop();
+			}
+		}
+	}
+
+	if ( !live ) return;
+	hiprtHit hit;
+	if ( bestRef != InvalidValue && !overflow )
+	{
+		const InstanceNode* in	 = instNodes + ( bestInst >> 4 );
+		const uint4			meta = __ldg( reinterpret_cast<const uint4*>( in ) + 3 );
+		const GeomHeader*	g	 = reinterpret_cast<const GeomHeader*>( ( uint64_t( meta.y ) << 32 ) | meta.x );
+		hiprtRay			objectRay = loadRay( rays, index );
+		if ( !( ( meta.w >> 26 ) & 1u ) ) objectRay = transformRayToObject( in, objectRay );
+		objectRay.maxT	= maxT0;
+		hit.instanceID	= meta.w & 0xFFFFFFu;
+		intersectPairTriangle( reinterpret_cast<const TrianglePairNode*>( g->primNodes ), bestRef >> 1, bestRef & 1u, objectRay, hit );
+	}
+	storeHit( hits, index, hit );
+}
+
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum>
+__global__ void __launch_bounds__( Block ) traceSceneFastKernel(
+	hiprtScene scene, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, hiprtRayMask mask, uint32_t* workCounter )
+{
+	__shared__ uint32_t sStack[Block * SharedDepth];
+	uint32_t* const		stackBase = sStack + ( threadIdx.x & 31u ) + ( threadIdx.x >> 5 ) * 32u * SharedDepth;
+	const uint32_t		lane	  = threadIdx.x & 31u;
+	while ( true )
+	{
+		uint32_t base = 0;
+		if ( lane == 0 ) base = atomicAdd( workCounter, 32u );
+		base = __shfl_sync( FullMask, base, 0 );
+		if ( base >= numRays ) return;
+		traceSceneWarp<Type, SharedDepth, BoxQuorum>(
+			reinterpret_cast<const SceneHeader*>( scene ), rays, hits, base + lane, base + lane < numRays, mask, stackBase );
+	}
+}
+
+template <hiprtTraversalType Type>
+static void launchSceneFast( hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtRayMask mask, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
+{
+	constexpr uint32_t Block = 128;
+	auto			   kernel = traceSceneFastKernel<Type, Block, 32, 16>;
+	static int		   blocksPerSm = 0; // same value for every caller: a benign race
+	if ( blocksPerSm == 0 ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSm, kernel, int( Block ), 0 );
+	cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), stream );
+	const uint32_t blocks = std::min( DivideRoundUp( numRays, Block ), smCount * uint32_t( std::max( blocksPerSm, 1 ) ) );
+	kernel<<<blocks, Block, 0, stream>>>( scene, rays, numRays, hits, mask, workCounter );
+}
+
 void traceScene(
-	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t stream )
+	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, uint32_t* workCounter, uint32_t smCount,
+	cudaStream_t stream )
 {
 	if ( numRays == 0 ) return;
+	if ( traceVariant() != 1 )
+	{
+		if ( type == hiprtTraversalTerminateAtAnyHit )
+			launchSceneFast<hiprtTraversalTerminateAtAnyHit>( scene, rays, numRays, hits, mask, workCounter, smCount, stream );
+		else
+			launchSceneFast<hiprtTraversalTerminateAtClosestHit>( scene, rays, numRays, hits, mask, workCounter, smCount, stream );
+		return;
+	}
+
 	const uint32_t blocks = DivideRoundUp( numRays, TraceBlock );
 	if ( type == hiprtTraversalTerminateAtAnyHit )
 		traceSceneKernel<hiprtTraversalTerminateAtAnyHit><<<blocks, TraceBlock, 0, stream>>>( scene, rays, numRays, hits, mask );
