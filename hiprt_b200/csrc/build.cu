@@ -136,8 +136,12 @@ static void runLbvh(
 
 	const uint32_t warpsNeeded = DivideRoundUp( maxBox, 8u );
 	const uint32_t blocks	   = std::max( 1u, std::min( DivideRoundUp( warpsNeeded, CollapseBlock / 32 ), dev.smCount * 16 ) );
+	// slots per claim: large trees amortise the claim atomic over 32 tasks, small ones keep 8 so that the tasks of a level
+	// spread over many warps instead of queueing inside one
+	const uint32_t residentWarps = dev.smCount * 40;
+	const uint32_t claimSize	 = std::max( 8u, std::min( 32u, ( maxBox / ( residentWarps * 16 ) ) & ~7u ) );
 	collapsePackKernel<Source><<<blocks, CollapseBlock, 0, stream>>>(
-		src, ctl, boxNodeCounter, primNodeCounter, scratch, sortedRefs, taskQueue, maxBox, boxNodes, leafNodes );
+		src, ctl, boxNodeCounter, primNodeCounter, scratch, sortedRefs, taskQueue, maxBox, claimSize, boxNodes, leafNodes );
 	dev.mark( "collapse+pack", stream );
 	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
