@@ -48,6 +48,15 @@ def make_mesh(spec):
     raise ValueError(spec)
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one primary-ray launch, from the committed ncu capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p)).get(workload, {}).get("trace_closest_dram_bytes")
+    except Exception:
+        return None
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -342,11 +351,16 @@ def main():
                       "bytes_per_triangle_model": round(sum(algo.values()) / n_tris, 1),
                       "achieved_gbs": round(sum(algo.values()) / (build_ms_avg * 1e-3) / 1e9, 1),
                       "frac_of_hbm_peak": round(sum(algo.values()) / (build_ms_avg * 1e-3) / 1e9 / peak, 4), "phases": build_roofline},
-            "roofline": {"kernel": "traceGeometryKernel<closest> (primary rays)", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
-                         "note": "80 B/ray compulsory I/O; traversal is L2/latency bound, see DESIGN.md and profiles/"},
+            "roofline": {"kernel": "traceTrianglesKernel<closest> (primary rays)", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "launch_ms": round(prim_ms_avg, 4),
+                         "note": "80 B/ray compulsory I/O (32 B hiprtRay in + 48 B hiprtHit out) x rays / launch time; traversal is bound by "
+                                 "L1TEX wavefronts and dependent-load latency, not HBM: see DESIGN.md section 3 and profiles/ "
+                                 "(traffic = dram bytes read+written by one launch, from the ncu --set full capture named there)"},
             "e2e": {"value": round(rays_all * args.steps / e2e_total_ms / 1e3, 2), "unit": "Mrays/s", "h2d_bytes_per_step": 32 * n_rays,
                     "d2h_bytes_per_step": 48 * n_rays, "api": "hiprtB200TraceGeometryHost (pinned host buffers)"},
+            # timed trace region: 2 trace kernels per step; timed build region: init, pair (indexed meshes), boxes, morton,
+            # 4 sort passes, emit, collapse per build (memsets not counted)
             "gpu_launches": args.steps * 2 + args.steps * (10 if n_prims != n_tris else 9),
             "clocks": clocks,
             "wall_s_timed_region": round(wall_s, 3),

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <map>
@@ -45,7 +46,13 @@ struct OutOfDeviceMemory : std::runtime_error
 class HostTracePipeline
 {
   public:
-	static constexpr uint32_t Chunk = 1u << 18; // rays per chunk: 8 MiB up, 12 MiB down
+	static constexpr uint32_t MaxChunk = 1u << 20;
+	// rays per chunk (default 256 Ki: 8 MiB up, 12 MiB down); HIPRT_B200_HOST_CHUNK overrides it for tuning
+	const uint32_t Chunk = [] {
+		const char* e = getenv( "HIPRT_B200_HOST_CHUNK" );
+		const long	v = e ? atol( e ) : 0;
+		return v >= 1024 && v <= long( MaxChunk ) ? uint32_t( v ) : 1u << 18;
+	}();
 	static constexpr int	  Slots = 3;
 
 	~HostTracePipeline()

@@ -233,21 +233,20 @@ __device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxN
 	return n;
 }
 
-template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum>
-__global__ void __launch_bounds__( Block ) traceTrianglesKernel(
-	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits )
+// Traversal of one ray per lane; every lane of the warp must call it (warp votes inside), `live` = has a ray.
+template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum>
+__device__ __forceinline__ void traceTrianglesWarp(
+	const Box4Node* __restrict__ boxNodes,
+	const TrianglePairNode* __restrict__ leaves,
+	const hiprtRay* __restrict__ rays,
+	hiprtHit* __restrict__ hits,
+	uint32_t		index,
+	bool			live,
+	uint32_t* const stackBase )
 {
-	__shared__ uint32_t sStack[Block * SharedDepth];
-	constexpr uint32_t	TotalDepth = 64; // the reference's private stack size
-	const uint32_t		index	   = blockIdx.x * Block + threadIdx.x;
-	const bool			live	   = index < numRays;
-	const GeomHeader*	header	   = reinterpret_cast<const GeomHeader*>( geom );
-	const Box4Node* __restrict__ boxNodes		 = header->boxNodes;
-	const TrianglePairNode* __restrict__ leaves = reinterpret_cast<const TrianglePairNode*>( header->primNodes );
-
-	uint32_t* const stackBase = sStack + ( threadIdx.x & 31u ) + ( threadIdx.x >> 5 ) * 32u * SharedDepth;
-	uint32_t		localStack[TotalDepth - SharedDepth];
-	uint32_t		top = 0;
+	constexpr uint32_t TotalDepth = 64; // the reference's private stack size
+	uint32_t		   localStack[TotalDepth - SharedDepth];
+	uint32_t		   top = 0;
 
 	hiprtRay	 ray	  = loadRay( rays, live ? index : 0u );
 	const float3 invD	  = rcp3( ray.direction );
@@ -379,6 +378,37 @@ __global__ void __launch_bounds__( Block ) traceTrianglesKernel(
 	storeHit( hits, index, hit );
 }
 
+// Persistent = the grid only fills the machine and every warp keeps fetching batches of 32 consecutive rays from a
+// global counter: ray costs are heavy-tailed (silhouette rays visit 10x the mean number of nodes), and a block-per-128-rays
+// grid holds a block slot until its slowest warp is done while the other three warp slots sit empty.
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent>
+__global__ void __launch_bounds__( Block ) traceTrianglesKernel(
+	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, uint32_t* workCounter )
+{
+	__shared__ uint32_t sStack[Block * SharedDepth];
+	const GeomHeader*	header					 = reinterpret_cast<const GeomHeader*>( geom );
+	const Box4Node* __restrict__ boxNodes		 = header->boxNodes;
+	const TrianglePairNode* __restrict__ leaves = reinterpret_cast<const TrianglePairNode*>( header->primNodes );
+	uint32_t* const stackBase = sStack + ( threadIdx.x & 31u ) + ( threadIdx.x >> 5 ) * 32u * SharedDepth;
+	if constexpr ( Persistent )
+	{
+		const uint32_t lane = threadIdx.x & 31u;
+		while ( true )
+		{
+			uint32_t base = 0;
+			if ( lane == 0 ) base = atomicAdd( workCounter, 32u );
+			base = __shfl_sync( FullMask, base, 0 );
+			if ( base >= numRays ) return;
+			traceTrianglesWarp<Type, SharedDepth, BoxQuorum>( boxNodes, leaves, rays, hits, base + lane, base + lane < numRays, stackBase );
+		}
+	}
+	else
+	{
+		const uint32_t index = blockIdx.x * Block + threadIdx.x;
+		traceTrianglesWarp<Type, SharedDepth, BoxQuorum>( boxNodes, leaves, rays, hits, index, index < numRays, stackBase );
+	}
+}
+
 template <hiprtTraversalType Type>
 __global__ void __launch_bounds__( TraceBlock ) traceSceneKernel(
 	hiprtScene scene, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, hiprtRayMask mask )
@@ -426,15 +456,31 @@ static void launchGeometry( hiprtGeometry geom, const hiprtRay* rays, uint32_t n
 		kernel<<<DivideRoundUp( numRays, Block ), Block, 0, stream>>>( geom, rays, numRays, hits, workCounter );
 }
 
-// Tuning variants (HIPRT_B200_TRACE_VARIANT): block size / shared stack depth / persistent warps.
-template <uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum>
-static void launchTriangles( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, bool any, cudaStream_t stream )
+// Tuning variants (HIPRT_B200_TRACE_VARIANT): block size / shared stack depth / box-phase quorum / persistent warps.
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent>
+static void launchTrianglesT( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
 {
-	const uint32_t blocks = DivideRoundUp( numRays, Block );
-	if ( any )
-		traceTrianglesKernel<hiprtTraversalTerminateAtAnyHit, Block, SharedDepth, BoxQuorum><<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits );
+	auto kernel = traceTrianglesKernel<Type, Block, SharedDepth, BoxQuorum, Persistent>;
+	if constexpr ( Persistent )
+	{
+		static int blocksPerSm = 0; // same value for every caller: a benign race
+		if ( blocksPerSm == 0 ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSm, kernel, int( Block ), 0 );
+		cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), stream );
+		const uint32_t blocks = std::min( DivideRoundUp( numRays, Block ), smCount * uint32_t( std::max( blocksPerSm, 1 ) ) );
+		kernel<<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits, workCounter );
+	}
 	else
-		traceTrianglesKernel<hiprtTraversalTerminateAtClosestHit, Block, SharedDepth, BoxQuorum><<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits );
+		kernel<<<DivideRoundUp( numRays, Block ), Block, 0, stream>>>( geom, rays, numRays, hits, workCounter );
+}
+
+template <uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent>
+static void launchTriangles(
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, bool any, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
+{
+	if ( any )
+		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, Block, SharedDepth, BoxQuorum, Persistent>( geom, rays, numRays, hits, workCounter, smCount, stream );
+	else
+		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, Block, SharedDepth, BoxQuorum, Persistent>( geom, rays, numRays, hits, workCounter, smCount, stream );
 }
 
 void traceGeometry(
@@ -445,18 +491,19 @@ void traceGeometry(
 	const bool any = type == hiprtTraversalTerminateAtAnyHit;
 	if ( triangles )
 	{
+#define HIPRT_B200_TRI( B, D, Q, P ) launchTriangles<B, D, Q, P>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
 		switch ( traceVariant() )
 		{
-		case 10: launchTriangles<128, 32, 1>( geom, rays, numRays, hits, any, stream ); return;
-		case 11: launchTriangles<128, 32, 8>( geom, rays, numRays, hits, any, stream ); return;
-		case 12: launchTriangles<128, 32, 16>( geom, rays, numRays, hits, any, stream ); return;
-		case 13: launchTriangles<64, 32, 8>( geom, rays, numRays, hits, any, stream ); return;
-		case 14: launchTriangles<128, 24, 8>( geom, rays, numRays, hits, any, stream ); return;
-		case 15: launchTriangles<128, 16, 8>( geom, rays, numRays, hits, any, stream ); return;
-		case 16: launchTriangles<128, 32, 24>( geom, rays, numRays, hits, any, stream ); return;
 		case 1: break; // generic traversal objects (as a user kernel would use them)
-		default: launchTriangles<128, 32, 16>( geom, rays, numRays, hits, any, stream ); return;
+		case 10: HIPRT_B200_TRI( 128, 32, 1, false )
+		case 11: HIPRT_B200_TRI( 128, 32, 8, false )
+		case 12: HIPRT_B200_TRI( 128, 32, 16, false )
+		case 13: HIPRT_B200_TRI( 64, 32, 16, false )
+		case 21: HIPRT_B200_TRI( 64, 32, 16, true )
+		case 25: HIPRT_B200_TRI( 128, 16, 16, true )
+		default: HIPRT_B200_TRI( 128, 32, 16, true )
 		}
+#undef HIPRT_B200_TRI
 	}
 #define HIPRT_B200_LAUNCH( B, D, P )                                                                                                       \
 	if ( any )                                                                                                                             \
