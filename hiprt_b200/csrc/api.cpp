@@ -354,7 +354,6 @@ bool usesBatch( size_t primCount, hiprtBuildOptions o )
 
 void checkBuildFlags( Context* c, hiprtBuildOptions o )
 {
-	if ( ( o.buildFlags & 3 ) == hiprtBuildFlagBitCustomBvhImport ) throw compiler::NotAvailable( "custom BVH import is not implemented in this build" );
 	if ( ( o.buildFlags & 3 ) == hiprtBuildFlagBitPreferHighQualityBuild )
 		c->log( hiprtLogLevelInfo, "PreferHighQualityBuild is served by the balanced (H-PLOC) builder" );
 }

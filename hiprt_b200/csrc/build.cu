@@ -33,6 +33,14 @@ TempLayout tempLayout( size_t n, size_t pairTriangles )
 }
 
 // ------------------------------------------------------------------------------------------------
+// Custom BVH import (hiprtBuildFlagBitCustomBvhImport): the caller's binary tree decides the leaf count, which exceeds the
+// primitive count when several leaves reference one primitive (spatial splits). Storage is sized for whichever is larger.
+static bool isImport( hiprtBuildOptions options ) { return ( options.buildFlags & 3u ) == hiprtBuildFlagBitCustomBvhImport; }
+static size_t importLeafCount( const hiprtGeometryBuildInput& input )
+{
+	return ( input.nodeList.internalNodes != nullptr || input.nodeList.leafNodes != nullptr ) ? input.nodeList.nodeCount : 0;
+}
+
 size_t geometryPrimCount( const hiprtGeometryBuildInput& input )
 {
 	if ( input.type == hiprtPrimitiveTypeTriangleMesh )
@@ -60,18 +68,19 @@ static bool wantsPairing( const hiprtGeometryBuildInput& input, hiprtBuildOption
 	const auto& m = input.primitive.triangleMesh;
 	// reference: TriangleMesh::pairable() (TriangleMesh.h:246) and LbvhBuilder.h:186-189
 	return m.triangleIndices != nullptr && m.triangleCount > 2 && m.trianglePairCount == 0 &&
-		   !( options.buildFlags & hiprtBuildFlagBitDisableTrianglePairing );
+		   !( options.buildFlags & hiprtBuildFlagBitDisableTrianglePairing ) && !isImport( options );
 }
 
 size_t geometryStorageSize( const hiprtGeometryBuildInput& input )
 {
-	const size_t n		  = geometryPrimCount( input );
+	const size_t n		  = std::max( geometryPrimCount( input ), importLeafCount( input ) );
 	const size_t leafSize = input.type == hiprtPrimitiveTypeTriangleMesh ? sizeof( TrianglePairNode ) : sizeof( CustomNode );
 	return alignUp( sizeof( GeomHeader ) ) + alignUp( maxBoxNodeCount( n ) * sizeof( Box4Node ) ) + alignUp( n * leafSize );
 }
 
 size_t geometryTempSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
 {
+	if ( isImport( options ) ) return tempLayout( std::max<size_t>( importLeafCount( input ), 1 ), 0 ).total;
 	const size_t n = geometryPrimCount( input );
 	return tempLayout( n, wantsPairing( input, options ) ? n : 0 ).total;
 }
@@ -146,10 +155,74 @@ static void runLbvh(
 	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
 
+// Custom BVH import (reference: BvhImporter.h:150-330): the caller's binary nodes already ARE what the collapse consumes --
+// an internal node carries its own box and two typed child indices, a leaf its box and a primitive id -- so the import is
+// one conversion launch into the scratch / reference records followed by the same collapse + pack kernel as every other build
+// (the reference patches the child types in place, then runs its Collapse / CompactTasks / PackLeaves with two host syncs).
+template <typename Source>
+__global__ void __launch_bounds__( 256 ) importNodesKernel(
+	Source src, const hiprtInternalNode* internals, const hiprtLeafNode* leafs, uint32_t leafCount, BuildControl* ctl, void* scratch, void* sortedRefs,
+	uint64_t* taskQueue )
+{
+	const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( k < leafCount )
+	{
+		const hiprtLeafNode l = leafs[k];
+		const uint2			w = src.refWords( l.primID );
+		storeRec( sortedRefs, k, DBox{ make_float3( l.aabbMin.x, l.aabbMin.y, l.aabbMin.z ), make_float3( l.aabbMax.x, l.aabbMax.y, l.aabbMax.z ) }, w.x, w.y );
+	}
+	if ( k + 1 < leafCount )
+	{
+		const hiprtInternalNode n = internals[k];
+		const uint32_t c0 = makeNodeIndex( n.childIndices[0], n.childNodeTypes[0] == hiprtBvhNodeTypeLeaf ? uint32_t( Source::LeafType ) : uint32_t( BoxType ) );
+		const uint32_t c1 = makeNodeIndex( n.childIndices[1], n.childNodeTypes[1] == hiprtBvhNodeTypeLeaf ? uint32_t( Source::LeafType ) : uint32_t( BoxType ) );
+		storeRec( scratch, k, DBox{ make_float3( n.aabbMin.x, n.aabbMin.y, n.aabbMin.z ), make_float3( n.aabbMax.x, n.aabbMax.y, n.aabbMax.z ) }, c0, c1 );
+	}
+	if ( k == 0 )
+	{
+		ctl->primCount = leafCount;
+		ctl->rootNode  = 0; // "the root node is assumed to be at the first position" (hiprt_types.h:421-424)
+		taskQueue[0]   = ( uint64_t( InvalidValue ) << 32 ) | makeNodeIndex( 0u, BoxType );
+	}
+}
+
+template <typename Source>
+static void runImport(
+	const DeviceInfo& dev, Source src, const hiprtBvhNodeList& nodes, uint8_t* temp, const TempLayout& L, cudaStream_t stream, GeomHeader* header, Box4Node* boxNodes,
+	void* leafNodes )
+{
+	const uint32_t n = nodes.nodeCount;
+	if ( n == 1 )
+	{
+		singletonKernel<Source><<<1, 1, 0, stream>>>( src, &header->primNodeCount, boxNodes, leafNodes );
+		HIPRT_CUDA_CHECK( cudaGetLastError() );
+		return;
+	}
+	BuildControl*  ctl		 = reinterpret_cast<BuildControl*>( temp + L.control );
+	uint64_t*	   taskQueue = reinterpret_cast<uint64_t*>( temp + L.taskQueue );
+	const uint32_t maxBox	 = uint32_t( maxBoxNodeCount( n ) );
+	HIPRT_CUDA_CHECK( cudaMemsetAsync( taskQueue, 0xFF, size_t( maxBox ) * 8, stream ) );
+	importNodesKernel<Source><<<DivideRoundUp( n, 256u ), 256, 0, stream>>>(
+		src, static_cast<const hiprtInternalNode*>( nodes.internalNodes ), static_cast<const hiprtLeafNode*>( nodes.leafNodes ), n, ctl, temp + L.scratch,
+		temp + L.sortedRefs, taskQueue );
+	dev.mark( "import", stream );
+	const uint32_t warpsNeeded	 = DivideRoundUp( maxBox, 8u );
+	const uint32_t blocks		 = std::max( 1u, std::min( DivideRoundUp( warpsNeeded, CollapseBlock / 32 ), dev.smCount * 16 ) );
+	const uint32_t residentWarps = dev.smCount * 40;
+	const uint32_t claimSize	 = std::max( 8u, std::min( 32u, ( maxBox / ( residentWarps * 16 ) ) & ~7u ) );
+	collapsePackKernel<Source><<<blocks, CollapseBlock, 0, stream>>>(
+		src, ctl, &header->boxNodeCount, &header->primNodeCount, temp + L.scratch, temp + L.sortedRefs, taskQueue, maxBox, claimSize, boxNodes, leafNodes );
+	dev.mark( "collapse+pack", stream );
+	HIPRT_CUDA_CHECK( cudaGetLastError() );
+}
+
 void buildGeometry(
 	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* tempBuffer, cudaStream_t stream, void* storage )
 {
-	const uint32_t nMax = uint32_t( geometryPrimCount( input ) );
+	const bool import = isImport( options );
+	if ( import && ( input.nodeList.nodeCount == 0 || input.nodeList.leafNodes == nullptr || ( input.nodeList.nodeCount > 1 && input.nodeList.internalNodes == nullptr ) ) )
+		throw std::runtime_error( "custom BVH import needs a node list" );
+	const uint32_t nMax = import ? input.nodeList.nodeCount : uint32_t( geometryPrimCount( input ) );
 	if ( nMax == 0 ) throw std::runtime_error( "empty geometry" );
 	const bool		 pairing  = wantsPairing( input, options );
 	const bool		 balanced = usesBalancedBuilder( options );
@@ -177,6 +250,11 @@ void buildGeometry(
 		src.triangles	   = ( m.triangleCount == 0 ) ? nullptr : static_cast<const uint8_t*>( m.triangleIndices );
 		src.triangleStride = m.triangleStride;
 		src.pairs		   = m.trianglePairCount > 0 ? static_cast<const uint2*>( m.trianglePairIndices ) : nullptr;
+		if ( import )
+		{
+			runImport( dev, src, input.nodeList, temp, L, stream, header, boxNodes, leafNodes );
+			return;
+		}
 		if ( nMax == 1 )
 		{
 			singletonKernel<TriangleMeshSource><<<1, 1, 0, stream>>>( src, &header->primNodeCount, boxNodes, leafNodes );
@@ -201,6 +279,11 @@ void buildGeometry(
 	{
 		const auto&	   a = input.primitive.aabbList;
 		AabbListSource src{ static_cast<const uint8_t*>( a.aabbs ), a.aabbStride };
+		if ( import )
+		{
+			runImport( dev, src, input.nodeList, temp, L, stream, header, boxNodes, leafNodes );
+			return;
+		}
 		if ( nMax == 1 )
 		{
 			singletonKernel<AabbListSource><<<1, 1, 0, stream>>>( src, &header->primNodeCount, boxNodes, leafNodes );
