@@ -188,13 +188,13 @@ __global__ void __launch_bounds__( 256 ) importNodesKernel(
 
 template <typename Source>
 static void runImport(
-	const DeviceInfo& dev, Source src, const hiprtBvhNodeList& nodes, uint8_t* temp, const TempLayout& L, cudaStream_t stream, GeomHeader* header, Box4Node* boxNodes,
-	void* leafNodes )
+	const DeviceInfo& dev, Source src, const hiprtBvhNodeList& nodes, uint8_t* temp, const TempLayout& L, cudaStream_t stream, uint32_t* boxNodeCounter,
+	uint32_t* primNodeCounter, Box4Node* boxNodes, void* leafNodes )
 {
 	const uint32_t n = nodes.nodeCount;
 	if ( n == 1 )
 	{
-		singletonKernel<Source><<<1, 1, 0, stream>>>( src, &header->primNodeCount, boxNodes, leafNodes );
+		singletonKernel<Source><<<1, 1, 0, stream>>>( src, primNodeCounter, boxNodes, leafNodes );
 		HIPRT_CUDA_CHECK( cudaGetLastError() );
 		return;
 	}
@@ -211,7 +211,7 @@ static void runImport(
 	const uint32_t residentWarps = dev.smCount * 40;
 	const uint32_t claimSize	 = std::max( 8u, std::min( 32u, ( maxBox / ( residentWarps * 16 ) ) & ~7u ) );
 	collapsePackKernel<Source><<<blocks, CollapseBlock, 0, stream>>>(
-		src, ctl, &header->boxNodeCount, &header->primNodeCount, temp + L.scratch, temp + L.sortedRefs, taskQueue, maxBox, claimSize, boxNodes, leafNodes );
+		src, ctl, boxNodeCounter, primNodeCounter, temp + L.scratch, temp + L.sortedRefs, taskQueue, maxBox, claimSize, boxNodes, leafNodes );
 	dev.mark( "collapse+pack", stream );
 	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
@@ -252,7 +252,7 @@ void buildGeometry(
 		src.pairs		   = m.trianglePairCount > 0 ? static_cast<const uint2*>( m.trianglePairIndices ) : nullptr;
 		if ( import )
 		{
-			runImport( dev, src, input.nodeList, temp, L, stream, header, boxNodes, leafNodes );
+			runImport( dev, src, input.nodeList, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
 			return;
 		}
 		if ( nMax == 1 )
@@ -281,7 +281,7 @@ void buildGeometry(
 		AabbListSource src{ static_cast<const uint8_t*>( a.aabbs ), a.aabbStride };
 		if ( import )
 		{
-			runImport( dev, src, input.nodeList, temp, L, stream, header, boxNodes, leafNodes );
+			runImport( dev, src, input.nodeList, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
 			return;
 		}
 		if ( nMax == 1 )
@@ -349,6 +349,14 @@ void buildScene(
 	const uint32_t work = std::max( n, input.frameCount );
 	initSceneKernel<<<DivideRoundUp( work, 256u ), 256, 0, stream>>>(
 		ctl, header, boxNodes, instNodes, records, frames, S.total, src, n, input.instanceFrames, input.frameType == hiprtFrameTypeMatrix );
+	if ( isImport( options ) )
+	{
+		// custom top-level BVH: one leaf per instance (the instance-node array is sized by the instance count)
+		if ( input.nodeList.nodeCount != n || input.nodeList.leafNodes == nullptr || ( n > 1 && input.nodeList.internalNodes == nullptr ) )
+			throw std::runtime_error( "custom scene BVH import needs a node list with exactly one leaf per instance" );
+		runImport( dev, src, input.nodeList, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
+		return;
+	}
 	if ( n == 1 )
 	{
 		singletonKernel<InstanceSource><<<1, 1, 0, stream>>>( src, &header->primNodeCount, boxNodes, instNodes );
