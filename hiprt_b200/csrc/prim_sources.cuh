@@ -4,6 +4,7 @@
 #pragma once
 #include "device_util.cuh"
 #include "transform_util.cuh"
+#include <hiprt/hiprt_b200_frame.h>
 
 namespace hiprt
 {
@@ -151,6 +152,8 @@ struct AabbListSource
 // root node of the box of their 8 transformed corners (reference: InstanceList.h:104-121,
 // Transform.h:496-517); leaf = 64-byte InstanceNode holding the world->object matrix
 // (BvhNode.h:1142-1182). Frames have been converted to SRT form by initSceneKernel.
+__device__ __forceinline__ motion::Frame toMotionFrame( const DFrame& f ) { return motion::Frame{ f.rotation, f.scale, f.shear, f.translation, f.time }; }
+
 struct InstanceSource
 {
 	static constexpr uint32_t LeafType = InstanceType;
@@ -184,20 +187,33 @@ struct InstanceSource
 		const uint32_t	childCount = reinterpret_cast<const uint32_t*>( root )[30];
 		DBox			out		   = emptyBox();
 		const uint32_t	nFrames	   = max( h.frameCount, 1u );
-		for ( uint32_t f = 0; f < nFrames; ++f ) // animated instances: union over the key frames
+		// Animated instances are bounded over their motion as the reference does (Transform::boundPointMotion,
+		// Transform.h:461-494): every key frame plus three interpolated poses (t = 1/4, 1/2, 3/4) between consecutive keys.
+		constexpr uint32_t Steps = 3;
+		for ( uint32_t f = 0; f < nFrames; ++f )
 		{
-			const DFrame fr	   = frame( h.frameIndex + f );
-			const bool	 ident = frameIsIdentity( fr );
-#pragma unroll
-			for ( uint32_t c = 0; c < 4; ++c )
+			const DFrame key = frame( h.frameIndex + f );
+			for ( uint32_t step = 0; step <= ( f + 1 < nFrames ? Steps : 0u ); ++step )
 			{
-				if ( c >= childCount || child[c] == InvalidValue ) continue;
-				const float3 lo = make_float3( b[6 * c], b[6 * c + 1], b[6 * c + 2] ), hi = make_float3( b[6 * c + 3], b[6 * c + 4], b[6 * c + 5] );
-#pragma unroll
-				for ( uint32_t k = 0; k < 8; ++k )
+				DFrame fr = key;
+				if ( step > 0 )
 				{
-					const float3 corner = make_float3( ( k & 4 ) ? hi.x : lo.x, ( k & 2 ) ? hi.y : lo.y, ( k & 1 ) ? hi.z : lo.z );
-					growBox( out, ident ? corner : frameTransformPoint( fr, corner ) );
+					const DFrame		next = frame( h.frameIndex + f + 1 );
+					const motion::Frame m	 = motion::interpolate( toMotionFrame( key ), toMotionFrame( next ), float( step ) * ( 1.0f / float( Steps + 1 ) ) );
+					fr						 = DFrame{ m.rotation, m.scale, m.shear, m.translation, 0.0f };
+				}
+				const bool ident = frameIsIdentity( fr );
+#pragma unroll
+				for ( uint32_t c = 0; c < 4; ++c )
+				{
+					if ( c >= childCount || child[c] == InvalidValue ) continue;
+					const float3 lo = make_float3( b[6 * c], b[6 * c + 1], b[6 * c + 2] ), hi = make_float3( b[6 * c + 3], b[6 * c + 4], b[6 * c + 5] );
+#pragma unroll
+					for ( uint32_t k = 0; k < 8; ++k )
+					{
+						const float3 corner = make_float3( ( k & 4 ) ? hi.x : lo.x, ( k & 2 ) ? hi.y : lo.y, ( k & 1 ) ? hi.z : lo.z );
+						growBox( out, ident ? corner : frameTransformPoint( fr, corner ) );
+					}
 				}
 			}
 		}
@@ -210,12 +226,21 @@ struct InstanceSource
 		const hiprtTransformHeader h	= header( p );
 		const hiprtInstance		   inst = instances[p];
 		const DFrame			   fr	= frame( h.frameIndex );
-		const bool				   ident = frameIsIdentity( fr );
-		float					   m[3][4] = { { 1, 0, 0, 0 }, { 0, 1, 0, 0 }, { 0, 0, 1, 0 } };
-		if ( !ident ) frameInverseMatrix( fr, m );
+		// static = exactly one key frame (UserInstanceNode::init, BvhNode.h:1152-1168); an animated instance keeps its key-frame
+		// range {frameIndex, frameCount} in the first eight bytes instead of a matrix and is never flagged identity
+		const bool isStatic = h.frameCount <= 1;
+		const bool ident	= isStatic && frameIsIdentity( fr );
+		float	   m[3][4]	= { { 1, 0, 0, 0 }, { 0, 1, 0, 0 }, { 0, 0, 1, 0 } };
+		if ( isStatic && !ident ) frameInverseMatrix( fr, m );
+		if ( !isStatic )
+		{
+			m[0][0] = __uint_as_float( h.frameIndex ), m[0][1] = __uint_as_float( h.frameCount );
+			m[1][1] = 0.0f, m[2][2] = 0.0f;
+		}
 		const uint32_t mask = masks ? masks[p] : FullRayMask;
 		// bits: primIndex:24 | type:1 | static:1 | identity:1
-		const uint32_t bits = ( p & 0xFFFFFFu ) | ( uint32_t( inst.type == hiprtInstanceTypeScene ) << 24 ) | ( 1u << 25 ) | ( uint32_t( ident ) << 26 );
+		const uint32_t bits =
+			( p & 0xFFFFFFu ) | ( uint32_t( inst.type == hiprtInstanceTypeScene ) << 24 ) | ( uint32_t( isStatic ) << 25 ) | ( uint32_t( ident ) << 26 );
 		const uint64_t ptr	= reinterpret_cast<uint64_t>( inst.geometry );
 		float4*		   dst	= reinterpret_cast<float4*>( static_cast<InstanceNode*>( leafArray ) + leafAddr );
 		dst[0]				= make_float4( m[0][0], m[0][1], m[0][2], m[0][3] );

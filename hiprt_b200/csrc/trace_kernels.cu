@@ -532,6 +532,16 @@ void traceGeometry(
 // Arithmetic (transform, slab, triangle) is that of the generic hiprtSceneTraversalT, winner = min (t, instanceID, primID).
 constexpr uint32_t InstanceExitMarker = 0xFFFFFFFEu; // instance-typed index no scene can hold (2^24 instance limit)
 
+// world -> object ray of an instance leaf: inverse matrix for static instances; animated ones (key-frame range in the node)
+// are traversed in their pose at time 0 -- a hiprtRay carries no time; kernels that trace at other times are user kernels
+// built on hiprtSceneTraversal*( ..., time ) of hiprt_device.h
+__device__ __forceinline__ hiprtRay instanceRayToObject( const SceneHeader* scene, const InstanceNode* in, uint32_t bits, const hiprtRay& ray )
+{
+	if ( ( bits >> 25 ) & 1u ) return transformRayToObject( in, ray );
+	const uint2 range = __ldg( reinterpret_cast<const uint2*>( in ) );
+	return motion::transformRay( motion::frameAt( scene->frames, range.x, range.y, 0.0f ), ray );
+}
+
 template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum>
 __device__ __forceinline__ void traceSceneWarp(
 	const SceneHeader* __restrict__ scene,
@@ -651,7 +661,7 @@ __device__ __forceinline__ void traceSceneWarp(
 						if ( !( ( meta.w >> 26 ) & 1u ) )
 						{
 							const float maxT = ray.maxT;
-							ray				 = transformRayToObject( in, ray );
+							ray				 = instanceRayToObject( scene, in, meta.w, ray );
 							ray.maxT		 = maxT;
 							invD			 = rcp3( ray.direction );
 						}
@@ -706,7 +716,7 @@ __device__ __forceinline__ void traceSceneWarp(
 		const uint4			meta = __ldg( reinterpret_cast<const uint4*>( in ) + 3 );
 		const GeomHeader*	g	 = reinterpret_cast<const GeomHeader*>( ( uint64_t( meta.y ) << 32 ) | meta.x );
 		hiprtRay			objectRay = loadRay( rays, index );
-		if ( !( ( meta.w >> 26 ) & 1u ) ) objectRay = transformRayToObject( in, objectRay );
+		if ( !( ( meta.w >> 26 ) & 1u ) ) objectRay = instanceRayToObject( scene, in, meta.w, objectRay );
 		objectRay.maxT	= maxT0;
 		hit.instanceID	= meta.w & 0xFFFFFFu;
 		intersectPairTriangle( reinterpret_cast<const TrianglePairNode*>( g->primNodes ), bestRef >> 1, bestRef & 1u, objectRay, hit );

@@ -20,6 +20,7 @@
 #include <hiprt/hiprt_types.h>
 #include <hiprt/hiprt_vec.h>
 #include <hiprt/hiprt_b200_layout.h>
+#include <hiprt/hiprt_b200_frame.h>
 
 #ifndef HIPRT_SHARED_STACK_STRIDE
 #define HIPRT_SHARED_STACK_STRIDE 32
@@ -699,7 +700,11 @@ class hiprtSceneTraversalT
 	{
 		const uint32_t bits = __ldg( reinterpret_cast<const uint32_t*>( in ) + 15 );
 		if ( ( bits >> 25 ) & 1u ) return hiprt::transformRayToObject( in, ray );
-		return hiprt::transformRayToObject( in, ray ); // animated instances: static pose of frame 0 (motion blur: next)
+		// animated instance (hiprt_device_impl.h:989-993): the node holds the key-frame range instead of a matrix; the pose
+		// at the ray's time is interpolated and origin / origin + direction are carried through its inverse
+		const uint2				   range = __ldg( reinterpret_cast<const uint2*>( in ) ); // hiprtTransformHeader {frameIndex, frameCount}
+		const hiprt::motion::Frame f	 = hiprt::motion::frameAt( m_scene->frames, range.x, range.y, m_time );
+		return hiprt::motion::transformRay( f, ray );
 	}
 
 	HIPRT_DEVICE void enterGeometry(
@@ -858,3 +863,96 @@ class hiprtSceneTraversalAnyHitCustomStack
   public:
 	using hiprtSceneTraversalT<hiprtStack, hiprtInstanceStack, hiprtTraversalTerminateAtAnyHit>::hiprtSceneTraversalT;
 };
+
+// ================================================================================================
+// Transform queries (reference: hiprt_device.h:508-583, hiprt_device_impl.h:1775-1927). Points use the frame of the
+// instance at `time`; vectors are normal-like (inverse transpose of the scale / shear part).
+namespace hiprt
+{
+HIPRT_DEVICE HIPRT_INLINE motion::Frame instanceFrameAt( const SceneHeader* scene, uint32_t instanceID, float time )
+{
+	const InstanceRecord rec = scene->instances[instanceID];
+	return motion::frameAt( scene->frames, rec.frameIndex, rec.frameCount, time );
+}
+} // namespace hiprt
+
+HIPRT_DEVICE HIPRT_INLINE float3 hiprtPointObjectToWorld( const float3& point, hiprtScene scene, uint32_t instanceID, float time = 0.0f )
+{
+	return hiprt::motion::transformPoint( hiprt::instanceFrameAt( reinterpret_cast<const hiprt::SceneHeader*>( scene ), instanceID, time ), point );
+}
+HIPRT_DEVICE HIPRT_INLINE float3 hiprtPointWorldToObject( const float3& point, hiprtScene scene, uint32_t instanceID, float time = 0.0f )
+{
+	return hiprt::motion::invTransformPoint( hiprt::instanceFrameAt( reinterpret_cast<const hiprt::SceneHeader*>( scene ), instanceID, time ), point );
+}
+HIPRT_DEVICE HIPRT_INLINE float3 hiprtVectorObjectToWorld( const float3& vector, hiprtScene scene, uint32_t instanceID, float time = 0.0f )
+{
+	return hiprt::motion::transformVector( hiprt::instanceFrameAt( reinterpret_cast<const hiprt::SceneHeader*>( scene ), instanceID, time ), vector );
+}
+HIPRT_DEVICE HIPRT_INLINE float3 hiprtVectorWorldToObject( const float3& vector, hiprtScene scene, uint32_t instanceID, float time = 0.0f )
+{
+	return hiprt::motion::invTransformVector( hiprt::instanceFrameAt( reinterpret_cast<const hiprt::SceneHeader*>( scene ), instanceID, time ), vector );
+}
+
+// Multi-level instancing: instanceIDs[k] selects the instance at level k; the chain ends at the first instance of a geometry.
+// Object -> world applies the innermost level first, world -> object the outermost (hiprt_device_impl.h:1819-1927).
+namespace hiprt
+{
+template <bool Point>
+HIPRT_DEVICE HIPRT_INLINE float3 objectToWorldLevels( float3 x, hiprtScene scene, const uint32_t ( &instanceIDs )[hiprtMaxInstanceLevels], float time )
+{
+	const SceneHeader* levels[hiprtMaxInstanceLevels];
+	const SceneHeader* header = reinterpret_cast<const SceneHeader*>( scene );
+	int32_t			   depth  = 0;
+	for ( uint32_t i = 0; i < hiprtMaxInstanceLevels; ++i )
+	{
+		levels[i]				 = header;
+		const InstanceRecord rec = header->instances[instanceIDs[i]];
+		++depth;
+		if ( rec.type != hiprtInstanceTypeScene ) break;
+		header = rec.scene;
+	}
+	for ( int32_t j = depth - 1; j >= 0; --j )
+	{
+		const InstanceRecord rec = levels[j]->instances[instanceIDs[j]];
+		const motion::Frame	 f	 = motion::frameAt( levels[j]->frames, rec.frameIndex, rec.frameCount, time );
+		x						 = Point ? motion::transformPoint( f, x ) : motion::transformVector( f, x );
+	}
+	return x;
+}
+
+template <bool Point>
+HIPRT_DEVICE HIPRT_INLINE float3 worldToObjectLevels( float3 x, hiprtScene scene, const uint32_t ( &instanceIDs )[hiprtMaxInstanceLevels], float time )
+{
+	const SceneHeader* header = reinterpret_cast<const SceneHeader*>( scene );
+	for ( uint32_t i = 0; i < hiprtMaxInstanceLevels; ++i )
+	{
+		const InstanceRecord rec = header->instances[instanceIDs[i]];
+		const motion::Frame	 f	 = motion::frameAt( header->frames, rec.frameIndex, rec.frameCount, time );
+		x						 = Point ? motion::invTransformPoint( f, x ) : motion::invTransformVector( f, x );
+		if ( rec.type != hiprtInstanceTypeScene ) break;
+		header = rec.scene;
+	}
+	return x;
+}
+} // namespace hiprt
+
+HIPRT_DEVICE HIPRT_INLINE float3
+hiprtPointObjectToWorld( const float3& point, hiprtScene scene, const uint32_t ( &instanceIDs )[hiprtMaxInstanceLevels], float time = 0.0f )
+{
+	return hiprt::objectToWorldLevels<true>( point, scene, instanceIDs, time );
+}
+HIPRT_DEVICE HIPRT_INLINE float3
+hiprtPointWorldToObject( const float3& point, hiprtScene scene, const uint32_t ( &instanceIDs )[hiprtMaxInstanceLevels], float time = 0.0f )
+{
+	return hiprt::worldToObjectLevels<true>( point, scene, instanceIDs, time );
+}
+HIPRT_DEVICE HIPRT_INLINE float3
+hiprtVectorObjectToWorld( const float3& vector, hiprtScene scene, const uint32_t ( &instanceIDs )[hiprtMaxInstanceLevels], float time = 0.0f )
+{
+	return hiprt::objectToWorldLevels<false>( vector, scene, instanceIDs, time );
+}
+HIPRT_DEVICE HIPRT_INLINE float3
+hiprtVectorWorldToObject( const float3& vector, hiprtScene scene, const uint32_t ( &instanceIDs )[hiprtMaxInstanceLevels], float time = 0.0f )
+{
+	return hiprt::worldToObjectLevels<false>( vector, scene, instanceIDs, time );
+}

@@ -96,3 +96,30 @@ extern "C" __global__ void sceneKernel( hiprtScene scene, const hiprtRay* rays, 
 	hiprtSceneTraversalClosest tr( scene, rays[i], mask );
 	hits[i] = tr.getNextHit();
 }
+
+// motion blur: every ray is traced at the same `time` (an application would carry a time per ray in its own ray payload)
+extern "C" __global__ void motionSceneKernel( hiprtScene scene, const hiprtRay* rays, hiprtHit* hits, uint32_t numRays, float time )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= numRays ) return;
+	hiprtSceneTraversalClosest tr( scene, rays[i], hiprtFullRayMask, hiprtTraversalHintDefault, nullptr, nullptr, 0, time );
+	hits[i] = tr.getNextHit();
+}
+
+// transform queries of hiprt_device.h for one instance: out[4 * i + {0,1,2,3}] = point object->world, that point back to
+// object space, vector object->world, that vector back to object space
+extern "C" __global__ void transformQueryKernel( hiprtScene scene, uint32_t instanceID, const float3* in, float3* out, uint32_t count, float time )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= count ) return;
+	const float3 pw = hiprtPointObjectToWorld( in[i], scene, instanceID, time );
+	const float3 vw = hiprtVectorObjectToWorld( in[i], scene, instanceID, time );
+	out[4 * i + 0]	= pw;
+	out[4 * i + 1]	= hiprtPointWorldToObject( pw, scene, instanceID, time );
+	out[4 * i + 2]	= vw;
+	out[4 * i + 3]	= hiprtVectorWorldToObject( vw, scene, instanceID, time );
+	// the multi-level overloads with a single level must agree
+	const uint32_t ids[hiprtMaxInstanceLevels] = { instanceID, hiprtInvalidValue, hiprtInvalidValue, hiprtInvalidValue };
+	const float3   pw2 = hiprtPointObjectToWorld( in[i], scene, ids, time );
+	if ( pw2.x != pw.x || pw2.y != pw.y || pw2.z != pw.z ) out[4 * i + 0] = make_float3( 1e30f, 1e30f, 1e30f );
+}
