@@ -658,6 +658,10 @@ void orderChildren( const Box4Node& node, V3 o, V3 invD, float maxT, uint32_t re
 // tieMode 0: the reference's scalar rule (a later-visited hit with t <= maxT replaces; inside a
 // pair triangle 1 replaces triangle 0 only when strictly nearer). tieMode 1: order-independent
 // rule min over (t, primID), which is what the B200 kernels implement.
+// box visits of traceClosest in which no child was hit (statistic for tools/simt_model.py: an upper bound of what culling popped
+// nodes by their stored entry distance could save)
+static uint64_t g_fruitlessBoxVisits = 0;
+
 hiprtHit traceClosest( const BvhView& bvh, const hiprtRay& inRay, int tieMode, uint32_t* boxVisits, uint32_t* leafVisits )
 {
 	hiprtRay			  ray  = inRay;
@@ -679,6 +683,7 @@ hiprtHit traceClosest( const BvhView& bvh, const hiprtRay& inRay, int tieMode, u
 				node = res[0];
 			else
 			{
+				++g_fruitlessBoxVisits;
 				node = stack.back();
 				stack.pop_back();
 			}
@@ -1190,6 +1195,13 @@ void orc_geometry_trace( void* h, const hiprtRay* rays, uint32_t n, hiprtHit* hi
 	for ( uint32_t i = 0; i < n; ++i )
 		hits[i] = traceClosest( v, rays[i], tieMode, &bv, &lv );
 	if ( visits ) visits[0] = bv, visits[1] = lv;
+}
+
+uint64_t orc_fruitless_box_visits()
+{
+	const uint64_t v	 = g_fruitlessBoxVisits;
+	g_fruitlessBoxVisits = 0;
+	return v;
 }
 
 // Per-ray visit counts (box nodes, leaves) of the closest-hit traversal: input of the SIMT-efficiency model
