@@ -260,10 +260,24 @@ class Context
 		std::lock_guard<std::mutex> lock( m_mutex );
 		m_geomKind[geometry] = triangles;
 	}
+	// (batch builds register 100 000 geometries per call: one lock, one rehash)
+	void noteGeometryKinds( hiprtGeometry* geometries, const hiprtGeometryBuildInput* inputs, uint32_t count )
+	{
+		std::lock_guard<std::mutex> lock( m_mutex );
+		m_geomKind.reserve( m_geomKind.size() + count );
+		for ( uint32_t i = 0; i < count; ++i )
+			m_geomKind[geometries[i]] = inputs[i].type == hiprtPrimitiveTypeTriangleMesh;
+	}
 	void forgetGeometry( void* geometry )
 	{
 		std::lock_guard<std::mutex> lock( m_mutex );
 		m_geomKind.erase( geometry );
+	}
+	void forgetGeometries( hiprtGeometry* geometries, uint32_t count )
+	{
+		std::lock_guard<std::mutex> lock( m_mutex );
+		for ( uint32_t i = 0; i < count; ++i )
+			m_geomKind.erase( geometries[i] );
 	}
 	// Geometries this context did not build (e.g. written by another library with the same format): the header
 	// word is read back once per call, after the work queued on `stream`.
@@ -422,11 +436,9 @@ hiprtError hiprtDestroyGeometries( hiprtContext context, uint32_t numGeometries,
 	for ( uint32_t i = 0; i < numGeometries; ++i )
 		if ( !geometries[i] ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
+		ctx( context )->forgetGeometries( geometries, numGeometries );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
-		{
-			ctx( context )->forgetGeometry( geometries[i] );
 			ctx( context )->releaseFromPool( geometries[i] );
-		}
 	} );
 }
 
@@ -460,8 +472,7 @@ hiprtError hiprtBuildGeometries(
 		Context* c = ctx( context );
 		checkBuildFlags( c, buildOptions );
 		cudaStream_t s = static_cast<cudaStream_t>( stream );
-		for ( uint32_t i = 0; i < numGeometries; ++i )
-			c->noteGeometryKind( geometriesOut[i], buildInputs[i].type == hiprtPrimitiveTypeTriangleMesh );
+		c->noteGeometryKinds( geometriesOut, buildInputs, numGeometries );
 		if ( buildOperation == hiprtBuildOperationUpdate )
 		{
 			for ( uint32_t i = 0; i < numGeometries; ++i )
@@ -469,8 +480,18 @@ hiprtError hiprtBuildGeometries(
 			return;
 		}
 		// inputs small enough for the batch builder are built together first (Context.cpp:153-168)
+		uint32_t batched = 0;
+		for ( uint32_t i = 0; i < numGeometries; ++i )
+			batched += usesBatch( geometryPrimCount( buildInputs[i] ), buildOptions ) ? 1u : 0u;
+		if ( batched == numGeometries )
+		{
+			// the common case of a pure batch: the caller's arrays go to the device as they are
+			buildGeometriesBatch( c->info(), buildInputs, numGeometries, buildOptions, temporaryBuffer, s, reinterpret_cast<void* const*>( geometriesOut ) );
+			return;
+		}
 		std::vector<hiprtGeometryBuildInput> batchInputs;
 		std::vector<void*>					 batchOut;
+		batchInputs.reserve( batched ), batchOut.reserve( batched );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
 			if ( usesBatch( geometryPrimCount( buildInputs[i] ), buildOptions ) )
 			{
