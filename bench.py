@@ -32,6 +32,8 @@ WORKLOADS = {
     # name: (mesh factory, camera eye, look-at, light)
     "c2_sphere_1M": dict(mesh=("sphere", 1000, 500), eye=(0.0, 0.0, 3.0), look=(0.0, 0.0, 0.0), light=(2.0, 4.0, 3.0), flags="fast"),
     "c3_terrain_10M": dict(mesh=("terrain", 2236), eye=(0.5, 0.6, -0.6), look=(0.5, 0.0, 0.5), light=(2.0, 4.0, 3.0), flags="fast"),
+    # C3 as BASELINE.json words it: PreferBalancedBuild (H-PLOC) + 16-spp ambient-occlusion rays (incoherent any-hit rays, maxT = 0.05)
+    "c3_terrain_10M_ao": dict(mesh=("terrain", 2236), eye=(0.5, 0.6, -0.6), look=(0.5, 0.0, 0.5), light=(2.0, 4.0, 3.0), flags="balanced", secondary="ao"),
     "small_sphere_40k": dict(mesh=("sphere", 200, 100), eye=(0.0, 0.0, 3.0), look=(0.0, 0.0, 0.0), light=(2.0, 4.0, 3.0), flags="fast"),
 }
 METRIC = "Mrays/s (primary closest-hit + shadow any-hit, 1920x1080); build Mtris/s under 'build'"
@@ -117,7 +119,16 @@ class ClockSampler:
                 "samples": len(sm), "source": "NVML, 5 ms period over the timed regions"}
 
 
-def embree_arm(verts, idx, primary, light, steps, warmup, threads):
+def secondary_rays(wl, primary, hits, spp):
+    """The any-hit rays of a step: one shadow ray per hit pixel, or `spp` cosine-hemisphere AO rays per hit pixel."""
+    from hiprt_b200 import scenes
+
+    if wl.get("secondary") == "ao":
+        return scenes.ao_rays(primary, hits, spp=spp)
+    return scenes.shadow_rays(primary, hits, wl["light"])[0]
+
+
+def embree_arm(verts, idx, primary, wl, steps, warmup, threads, spp=16):
     """Reference CPU arm: Embree 4.3 build (LOW = Morton, the counterpart of PreferFastBuild) and
     rtcIntersect1/rtcOccluded1 over all host threads. Falls back to the single-threaded oracle port."""
     from hiprt_b200 import scenes
@@ -132,7 +143,7 @@ def embree_arm(verts, idx, primary, light, steps, warmup, threads):
         s.release()
     scene = emb.EmbreeScene(verts, idx, quality=0, threads=threads)
     hits, _ = scene.trace(primary, kind=2)
-    shadow, _ = scenes.shadow_rays(primary, hits, light)
+    shadow = secondary_rays(wl, primary, hits, spp)
     times = []
     for it in range(warmup + steps):
         _, ms_p = scene.trace(primary, kind=2, want_hits=False)
@@ -167,6 +178,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_sphere_1M", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ao-spp", type=int, default=16, help="AO rays per hit pixel of the *_ao workloads")
     ap.add_argument("--with-hiprt-reference", action="store_true", help="also time the reference's own GPU kernels (oracle/_ref)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -187,7 +199,7 @@ def main():
         if rank != 0:
             return 0
         primary = scenes.pinhole_rays(WIDTH, HEIGHT, wl["eye"], wl["look"])[scenes.tile_order(WIDTH, HEIGHT)]
-        r = embree_arm(verts, idx, primary, wl["light"], args.steps, args.warmup, host_threads)
+        r = embree_arm(verts, idx, primary, wl, args.steps, args.warmup, host_threads, args.ao_spp)
         kind = "reference"
         if r is None:
             r = oracle_port_arm(verts, idx, primary)
@@ -222,7 +234,7 @@ def main():
     torch.cuda.set_device(local_rank)
     ctx = api.Context(local_rank)
     dev = ctx.device
-    flags = api.FAST_BUILD
+    flags = api.BALANCED_BUILD if wl.get("flags") == "balanced" else api.FAST_BUILD
 
     d_verts = torch.from_numpy(verts).to(dev)
     d_idx = torch.from_numpy(idx.view(np.int32)).to(dev)
@@ -238,7 +250,7 @@ def main():
     primary = scenes.pinhole_rays(WIDTH, HEIGHT, eye, wl["look"])[scenes.tile_order(WIDTH, HEIGHT)]
     d_primary = ctx.rays_to_device(primary)
     hits0 = ctx.hits_to_host(ctx.trace(geom, d_primary))
-    shadow, _ = scenes.shadow_rays(primary, hits0, wl["light"])
+    shadow = secondary_rays(wl, primary, hits0, args.ao_spp)
     d_shadow = ctx.rays_to_device(shadow)
     n_primary, n_shadow = len(primary), len(shadow)
     n_rays = n_primary + n_shadow
@@ -343,7 +355,9 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": args.workload, "triangles": n_tris, "primitives_after_pairing": n_prims, "build": "PreferFastBuild (LBVH)",
+            "config": {"workload": args.workload, "triangles": n_tris, "primitives_after_pairing": n_prims,
+                       "build": "PreferBalancedBuild (H-PLOC)" if flags == api.BALANCED_BUILD else "PreferFastBuild (LBVH)",
+                       "secondary_rays": f"{args.ao_spp}-spp ambient occlusion (any-hit, maxT 0.05)" if wl.get("secondary") == "ao" else "one shadow ray per hit pixel (any-hit)",
                        "resolution": [WIDTH, HEIGHT], "rays_per_step_per_gpu": n_rays, "primary_rays": n_primary, "shadow_rays": n_shadow,
                        "l2": "256 MiB flush write before every timed step", "bvh": "replicated per GPU", "sharding": "one frame-sized ray batch per GPU",
                        "ray_order": "8x4 pixel tiles (the reference's tests launch 8x8 / 2-D blocks); same order for every arm"},
@@ -366,7 +380,7 @@ def main():
             "wall_s_timed_region": round(wall_s, 3),
         }
         if world == 1 and not args.no_cpu_baseline:
-            r = embree_arm(verts, idx, primary, wl["light"], min(args.steps, 10), 2, host_threads)
+            r = embree_arm(verts, idx, primary, wl, min(args.steps, 10), 2, host_threads, args.ao_spp)
             if r is not None:
                 line["cpu_baseline"] = {"value": round(r["mrays"], 3), "unit": "Mrays/s", "cores": host_threads, "kind": "reference",
                                         "sample": f"full frame ({r['rays']} rays/step) x {min(args.steps, 10)} steps on Embree 4.3 bundled with the reference",
@@ -397,12 +411,21 @@ def main():
                 own_p = best_of(lambda: ctx.trace(geom, d_primary, d_hits_p, api.CLOSEST_HIT))
                 own_s = best_of(lambda: ctx.trace(geom, d_shadow, d_hits_s, api.ANY_HIT))
                 own_b = best_of(lambda: ctx.build_geometry(inp, geom_h, temp, flags))
+                # the reference's traversal kernel through THIS repo's structure (the formats are byte-compatible): same BVH, their kernel
+                try:
+                    _, x_p = ref.trace_geometry(geom_h, primary, kind=2, reps=6)
+                    _, x_s = ref.trace_geometry(geom_h, shadow, kind=1, reps=6)
+                    cross = {"mrays_per_s": round(n_rays / (x_p + x_s) / 1e3, 2), "primary_ms": round(x_p, 4), "secondary_ms": round(x_s, 4)}
+                except Exception as e:
+                    cross = {"unavailable": str(e)[:120]}
                 line["hiprt_reference_gpu"] = {"mrays_per_s": round(n_rays / (ms_p + ms_s) / 1e3, 2), "build_mtris_per_s": round(n_tris / rg.build_ms / 1e3, 2),
                                                "build_ms": round(rg.build_ms, 4), "primary_ms": round(ms_p, 4), "shadow_ms": round(ms_s, 4),
                                                "protocol": "warm L2, best of 5 launches (oracle/ref/ref_harness.cpp)",
                                                "this_repo_same_protocol": {"mrays_per_s": round(n_rays / (own_p + own_s) / 1e3, 2), "primary_ms": round(own_p, 4),
                                                                            "shadow_ms": round(own_s, 4), "build_mtris_per_s": round(n_tris / own_b / 1e3, 2)},
-                                               "note": "unmodified HIPRT v3.1.0 kernels via Orochi/CUDA on this GPU (oracle/_ref)"}
+                                               "hiprt_kernel_on_this_repos_bvh": cross,
+                                               "note": "unmodified HIPRT v3.1.0 kernels via Orochi/CUDA on this GPU (oracle/_ref); its own build is "
+                                                       "always PreferFastBuild (its H-PLOC does not run on sm_100)"}
             except Exception as e:  # the reference is optional infrastructure
                 line["hiprt_reference_gpu"] = {"unavailable": str(e)[:200]}
         print(json.dumps(line))

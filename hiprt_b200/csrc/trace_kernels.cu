@@ -234,7 +234,11 @@ __device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxN
 }
 
 // Traversal of one ray per lane; every lane of the warp must call it (warp votes inside), `live` = has a ray.
-template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum>
+// Refill == 0: traces ray `index` of the lane and returns when the whole warp is done.
+// Refill  > 0: lane-granular persistent threads -- whenever at least `Refill` lanes are idle (their ray is finished) those
+// lanes write their hits and fetch the next rays from `workCounter`, the others keep their state; returns when the ray
+// buffer is exhausted and every lane is done. Pays off for incoherent rays only (see the kernel below).
+template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum, uint32_t Refill = 0>
 __device__ __forceinline__ void traceTrianglesWarp(
 	const Box4Node* __restrict__ boxNodes,
 	const TrianglePairNode* __restrict__ leaves,
@@ -242,30 +246,45 @@ __device__ __forceinline__ void traceTrianglesWarp(
 	hiprtHit* __restrict__ hits,
 	uint32_t		index,
 	bool			live,
-	uint32_t* const stackBase )
+	uint32_t* const stackBase,
+	uint32_t*		workCounter = nullptr,
+	uint32_t		numRays		= 0 )
 {
 	constexpr uint32_t TotalDepth = 64; // the reference's private stack size
 	uint32_t		   localStack[TotalDepth - SharedDepth];
 	uint32_t		   top = 0;
 
-	hiprtRay	 ray	  = loadRay( rays, live ? index : 0u );
-	const float3 invD	  = rcp3( ray.direction );
-	const float	 maxT0	  = ray.maxT;
-	uint32_t	 bestRef  = InvalidValue; // (leaf address << 1) | triangle of the pair
-	uint32_t	 bestPrim = InvalidValue;
-	bool		 overflow = false;
-	uint32_t	 node	  = live ? RootIndex : InvalidValue;
+	hiprtRay ray	  = loadRay( rays, live ? index : 0u );
+	float3	 invD	  = rcp3( ray.direction );
+	float	 maxT0	  = ray.maxT;
+	uint32_t bestRef  = InvalidValue; // (leaf address << 1) | triangle of the pair
+	uint32_t bestPrim = InvalidValue;
+	bool	 overflow = false;
+	uint32_t node	  = live ? RootIndex : InvalidValue;
 
 	// direction octant of the warp, or GeneralOctant when its rays disagree / have a zero, denormal-reciprocal or
 	// non-finite direction component
-	uint32_t octant = ( ray.direction.x < 0.0f ? 1u : 0u ) | ( ray.direction.y < 0.0f ? 2u : 0u ) | ( ray.direction.z < 0.0f ? 4u : 0u );
-	{
+	uint32_t octant = GeneralOctant;
+	auto	 chooseOctant = [&]() {
+		const uint32_t mine = ( ray.direction.x < 0.0f ? 1u : 0u ) | ( ray.direction.y < 0.0f ? 2u : 0u ) | ( ray.direction.z < 0.0f ? 4u : 0u );
 		const bool regular = isfinite( invD.x ) && isfinite( invD.y ) && isfinite( invD.z ) && invD.x != 0.0f && invD.y != 0.0f && invD.z != 0.0f &&
 							 isfinite( ray.origin.x ) && isfinite( ray.origin.y ) && isfinite( ray.origin.z );
-		const uint32_t first = __shfl_sync( FullMask, octant, 0 );
-		if ( !__all_sync( FullMask, !live || ( regular && octant == first ) ) ) octant = GeneralOctant;
-		else octant = first;
-	}
+		const uint32_t liveLanes = __ballot_sync( FullMask, live );
+		const uint32_t first	 = __shfl_sync( FullMask, mine, liveLanes ? __ffs( liveLanes ) - 1 : 0 );
+		octant					 = __all_sync( FullMask, !live || ( regular && mine == first ) ) ? first : GeneralOctant;
+	};
+	if ( Refill == 0 ) chooseOctant();
+
+	// result of the lane's finished ray: uv mapping and normal by re-running the reference-order test on the winning triangle
+	auto finish = [&]() {
+		hiprtHit hit;
+		if ( bestRef != InvalidValue && !overflow )
+		{
+			ray.maxT = maxT0;
+			intersectPairTriangle( leaves, bestRef >> 1, bestRef & 1u, ray, hit );
+		}
+		storeHit( hits, index, hit );
+	};
 
 	auto pop = [&]() -> uint32_t {
 		if ( top == 0 ) return InvalidValue;
@@ -273,8 +292,50 @@ __device__ __forceinline__ void traceTrianglesWarp(
 		return top < SharedDepth ? stackBase[top * 32u] : localStack[top - SharedDepth];
 	};
 
-	while ( __any_sync( FullMask, node != InvalidValue ) )
+	bool exhausted = false; // (Refill) the ray buffer has been handed out completely
+	while ( true )
 	{
+		if constexpr ( Refill != 0 )
+		{
+			const bool	   idle		= node == InvalidValue;
+			const uint32_t idleMask = __ballot_sync( FullMask, idle );
+			if ( idleMask == FullMask || ( !exhausted && uint32_t( __popc( idleMask ) ) >= Refill ) )
+			{
+				if ( idle && live )
+				{
+					finish();
+					live = false;
+				}
+				if ( !exhausted )
+				{
+					const uint32_t count = __popc( idleMask );
+					uint32_t	   base	 = 0;
+					if ( ( threadIdx.x & 31u ) == 0 ) base = atomicAdd( workCounter, count );
+					base	  = __shfl_sync( FullMask, base, 0 );
+					exhausted = base + count >= numRays;
+					const uint32_t mine = base + __popc( idleMask & ( ( 1u << ( threadIdx.x & 31u ) ) - 1u ) );
+					if ( idle && mine < numRays )
+					{
+						index	 = mine;
+						ray		 = loadRay( rays, index );
+						invD	 = rcp3( ray.direction );
+						maxT0	 = ray.maxT;
+						bestRef	 = InvalidValue;
+						bestPrim = InvalidValue;
+						overflow = false;
+						top		 = 0;
+						node	 = RootIndex;
+						live	 = true;
+					}
+				}
+				if ( !__any_sync( FullMask, node != InvalidValue ) ) break;
+			}
+		}
+		else
+		{
+			if ( !__any_sync( FullMask, node != InvalidValue ) ) break;
+		}
+
 		// ---- box phase
 		while ( true )
 		{
@@ -368,21 +429,17 @@ __device__ __forceinline__ void traceTrianglesWarp(
 		}
 	}
 
-	if ( !live ) return;
-	hiprtHit hit;
-	if ( bestRef != InvalidValue && !overflow )
-	{
-		ray.maxT = maxT0;
-		intersectPairTriangle( leaves, bestRef >> 1, bestRef & 1u, ray, hit );
-	}
-	storeHit( hits, index, hit );
+	if ( Refill == 0 && live ) finish();
 }
 
 // Persistent = the grid only fills the machine and every warp keeps fetching batches of 32 consecutive rays from a
 // global counter: ray costs are heavy-tailed (silhouette rays visit 10x the mean number of nodes), and a block-per-128-rays
 // grid holds a block slot until its slowest warp is done while the other three warp slots sit empty.
-template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent>
-__global__ void __launch_bounds__( Block ) traceTrianglesKernel(
+// Refill > 0 (persistent only): a warp whose fetched batch is INCOHERENT (mixed direction octants: AO / diffuse bounces)
+// keeps that batch and from then on refills idle lanes one by one; ncu shows 15 of 32 lanes active on 8-spp AO rays without
+// it. Coherent batches (primary, shadow rays) stay warp-granular: refilling them lane by lane was measured 12-18 % slower.
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill = 0>
+__global__ void __launch_bounds__( Block, Refill != 0 ? 1024u / Block : 1u ) traceTrianglesKernel(
 	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, uint32_t* workCounter )
 {
 	__shared__ uint32_t sStack[Block * SharedDepth];
@@ -399,7 +456,22 @@ __global__ void __launch_bounds__( Block ) traceTrianglesKernel(
 			if ( lane == 0 ) base = atomicAdd( workCounter, 32u );
 			base = __shfl_sync( FullMask, base, 0 );
 			if ( base >= numRays ) return;
-			traceTrianglesWarp<Type, SharedDepth, BoxQuorum>( boxNodes, leaves, rays, hits, base + lane, base + lane < numRays, stackBase );
+			const uint32_t index = base + lane;
+			const bool	   live	 = index < numRays;
+			if constexpr ( Refill != 0 )
+			{
+				// direction octant of the lane's ray (the two 16-byte loads are repeated inside the traversal: L1 hits)
+				const float4   r1	  = __ldg( reinterpret_cast<const float4*>( rays + ( live ? index : base ) ) + 1 );
+				const uint32_t mine	  = ( r1.x < 0.0f ? 1u : 0u ) | ( r1.y < 0.0f ? 2u : 0u ) | ( r1.z < 0.0f ? 4u : 0u );
+				const uint32_t first  = __shfl_sync( FullMask, mine, 0 );
+				const bool	   coherent = __all_sync( FullMask, mine == first );
+				if ( !coherent )
+				{
+					traceTrianglesWarp<Type, SharedDepth, BoxQuorum, Refill>( boxNodes, leaves, rays, hits, index, live, stackBase, workCounter, numRays );
+					return; // the refilling traversal drains the ray buffer
+				}
+			}
+			traceTrianglesWarp<Type, SharedDepth, BoxQuorum>( boxNodes, leaves, rays, hits, index, live, stackBase );
 		}
 	}
 	else
@@ -457,10 +529,10 @@ static void launchGeometry( hiprtGeometry geom, const hiprtRay* rays, uint32_t n
 }
 
 // Tuning variants (HIPRT_B200_TRACE_VARIANT): block size / shared stack depth / box-phase quorum / persistent warps.
-template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent>
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill>
 static void launchTrianglesT( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
 {
-	auto kernel = traceTrianglesKernel<Type, Block, SharedDepth, BoxQuorum, Persistent>;
+	auto kernel = traceTrianglesKernel<Type, Block, SharedDepth, BoxQuorum, Persistent, Refill>;
 	if constexpr ( Persistent )
 	{
 		static int blocksPerSm = 0; // same value for every caller: a benign race
@@ -473,14 +545,14 @@ static void launchTrianglesT( hiprtGeometry geom, const hiprtRay* rays, uint32_t
 		kernel<<<DivideRoundUp( numRays, Block ), Block, 0, stream>>>( geom, rays, numRays, hits, workCounter );
 }
 
-template <uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent>
+template <uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill = 0>
 static void launchTriangles(
 	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, bool any, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
 {
 	if ( any )
-		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, Block, SharedDepth, BoxQuorum, Persistent>( geom, rays, numRays, hits, workCounter, smCount, stream );
+		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, Block, SharedDepth, BoxQuorum, Persistent, Refill>( geom, rays, numRays, hits, workCounter, smCount, stream );
 	else
-		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, Block, SharedDepth, BoxQuorum, Persistent>( geom, rays, numRays, hits, workCounter, smCount, stream );
+		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, Block, SharedDepth, BoxQuorum, Persistent, Refill>( geom, rays, numRays, hits, workCounter, smCount, stream );
 }
 
 void traceGeometry(
@@ -501,7 +573,11 @@ void traceGeometry(
 		case 13: HIPRT_B200_TRI( 64, 32, 16, false )
 		case 21: HIPRT_B200_TRI( 64, 32, 16, true )
 		case 25: HIPRT_B200_TRI( 128, 16, 16, true )
-		default: HIPRT_B200_TRI( 128, 32, 16, true )
+		case 40: launchTriangles<128, 32, 16, true, 4>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
+		case 41: launchTriangles<128, 32, 16, true, 8>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
+		case 42: launchTriangles<128, 32, 16, true, 16>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
+		case 43: launchTriangles<128, 32, 16, true, 1>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
+		default: launchTriangles<128, 32, 16, true, 8>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
 		}
 #undef HIPRT_B200_TRI
 	}

@@ -15,6 +15,7 @@ for w in $what; do
     ncu_full) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"traceTrianglesKernel" -s 2 -c 2 -o $out/trace_c2 python tools/profile_trace.py c2_sphere_1M 2 > $out/ncu_full.log 2>&1 ;;
     ncu_build) timeout 600 ncu --set full --clock-control none --import-source on -k regex:"Kernel|onesweepPass" -s 11 -c 11 -o $out/build_c3 python tools/profile_build.py c3_terrain_10M 0 2 > $out/ncu_build.log 2>&1
                timeout 600 ncu --set full --clock-control none --import-source on -k regex:"hplocKernel" -s 1 -c 1 -o $out/hploc_c3 python tools/profile_build.py c3_terrain_10M 2 2 > $out/ncu_hploc.log 2>&1 ;;
+    c3ao)     timeout 900 python bench.py --steps 5 --warmup 3 --workload c3_terrain_10M_ao --with-hiprt-reference > $out/bench_c3_ao.json 2> $out/bench_c3_ao.err ;;
     scene)    timeout 300 python tools/bench_scene.py > $out/scene_c4.json 2> $out/scene_c4.err ;;
   esac
 done
