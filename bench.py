@@ -102,7 +102,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.001)
 
     def stop(self):
         if self.thread is None:
@@ -116,7 +116,7 @@ class ClockSampler:
         self.thread.join(timeout=2)
         sm = sorted(s[0] for s in self.samples)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(sm), "source": "NVML, 5 ms period over the timed regions"}
+                "samples": len(sm), "source": "NVML, ~1 ms period over the timed regions"}
 
 
 def secondary_rays(wl, primary, hits, spp):
