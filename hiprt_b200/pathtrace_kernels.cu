@@ -2,6 +2,10 @@
 // hiprtBuildTraceKernels exactly like an application's own kernels (NVRTC, <hiprt/hiprt_device.h> prepended).
 // One thread per live path: a miss adds the sky to the path's pixel slot (one writer per slot and launch, no atomics on
 // the image), a hit scatters a cosine-distributed ray from the hit point and appends it to the next wavefront.
+#if !defined( __CUDACC_RTC__ ) // offline compile (nvcc -I include): NVRTC gets the header and dispatchers from hiprtBuildTraceKernels
+#define HIPRT_B200_DEFAULT_FUNC_TABLE
+#include <hiprt/hiprt_device.h>
+#endif
 
 __device__ __forceinline__ float hashU01( unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long d )
 {
