@@ -50,11 +50,12 @@ def make_mesh(spec):
     raise ValueError(spec)
 
 
-def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one primary-ray launch, from the committed ncu capture (profiles/)."""
+def ncu_traffic(workload, key="trace_closest_dram_bytes"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one primary-ray launch (or, with another key, the ncu counters that show
+    what the kernel is actually bound by), from the committed ncu capture (profiles/)."""
     p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     try:
-        return json.load(open(p)).get(workload, {}).get("trace_closest_dram_bytes")
+        return json.load(open(p)).get(workload, {}).get(key)
     except Exception:
         return None
 
@@ -366,7 +367,7 @@ def main():
                       "achieved_gbs": round(sum(algo.values()) / (build_ms_avg * 1e-3) / 1e9, 1),
                       "frac_of_hbm_peak": round(sum(algo.values()) / (build_ms_avg * 1e-3) / 1e9 / peak, 4), "phases": build_roofline},
             "roofline": {"kernel": "traceTrianglesKernel<closest> (primary rays)", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": ncu_traffic(args.workload), "peak_source": peak_src,
+                         "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": ncu_traffic(args.workload), "ncu": ncu_traffic(args.workload, "trace_closest_ncu"), "peak_source": peak_src,
                          "launch_ms": round(prim_ms_avg, 4),
                          "note": "80 B/ray compulsory I/O (32 B hiprtRay in + 48 B hiprtHit out) x rays / launch time; traversal is bound by "
                                  "L1TEX wavefronts and dependent-load latency, not HBM: see DESIGN.md section 3 and profiles/ "
