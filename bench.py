@@ -367,7 +367,8 @@ def main():
                       "achieved_gbs": round(sum(algo.values()) / (build_ms_avg * 1e-3) / 1e9, 1),
                       "frac_of_hbm_peak": round(sum(algo.values()) / (build_ms_avg * 1e-3) / 1e9 / peak, 4), "phases": build_roofline},
             "roofline": {"kernel": "traceTrianglesKernel<closest> (primary rays)", "bound": "hbm", "achieved": round(achieved, 2), "peak": peak,
-                         "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": ncu_traffic(args.workload), "ncu": ncu_traffic(args.workload, "trace_closest_ncu"), "peak_source": peak_src,
+                         "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": ncu_traffic(args.workload), "ncu": ncu_traffic(args.workload, "trace_closest_ncu"),
+                         "cache_level": ncu_traffic(args.workload, "oracle_visits"), "peak_source": peak_src,
                          "launch_ms": round(prim_ms_avg, 4),
                          "note": "80 B/ray compulsory I/O (32 B hiprtRay in + 48 B hiprtHit out) x rays / launch time; traversal is bound by "
                                  "L1TEX wavefronts and dependent-load latency, not HBM: see DESIGN.md section 3 and profiles/ "
