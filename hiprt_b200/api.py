@@ -166,6 +166,7 @@ SIGNATURES = {
     # additions (include/hiprt/hiprt_b200.h)
     "hiprtB200TraceGeometry": [_vp, _vp, _vp, _u32, _vp, C.c_int, _vp],
     "hiprtB200TraceScene": [_vp, _vp, _vp, _u32, _vp, C.c_int, _u32, _vp],
+    "hiprtB200TraceSceneAtTime": [_vp, _vp, _vp, _vp, C.c_float, _u32, _vp, C.c_int, _u32, _vp],
     "hiprtB200TraceGeometryHost": [_vp, _vp, _vp, _u32, _vp, C.c_int, _vp],
     "hiprtB200TraceSceneHost": [_vp, _vp, _vp, _u32, _vp, C.c_int, _u32, _vp],
     "hiprtB200GetTempLayout": [_sz, _sz, _P(_sz), _u32],
@@ -420,6 +421,16 @@ class Context:
         else:
             self._check(lib().hiprtB200TraceGeometry(self.h, handle, _ptr(rays), n, _ptr(hits), kind, _stream_handle(stream)),
                         "hiprtB200TraceGeometry")
+        return hits
+
+    def trace_scene_at_time(self, scene, rays, times=None, time=0.0, hits=None, kind=CLOSEST_HIT, mask=0xFFFFFFFF, stream=None):
+        """Scene trace with motion blur: `times` = float32 device tensor (one time per ray) or None (every ray at `time`)."""
+        t = self.torch
+        n = rays.numel() * rays.element_size() // 32
+        if hits is None:
+            hits = t.empty((n, 12), dtype=t.int32, device=self.device)
+        self._check(lib().hiprtB200TraceSceneAtTime(self.h, scene.h, _ptr(rays), _ptr(times) if times is not None else None, C.c_float(time), n,
+                                                    _ptr(hits), kind, mask, _stream_handle(stream)), "hiprtB200TraceSceneAtTime")
         return hits
 
     def trace_host(self, geom_or_scene, rays_np, hits_np=None, kind=CLOSEST_HIT, mask=0xFFFFFFFF, stream=None):

@@ -971,6 +971,27 @@ hiprtError hiprtB200TraceScene(
 	} );
 }
 
+hiprtError hiprtB200TraceSceneAtTime(
+	hiprtContext	   context,
+	hiprtScene		   scene,
+	const hiprtRay*	   rays,
+	const float*	   times,
+	float			   time,
+	uint32_t		   numRays,
+	hiprtHit*		   hits,
+	hiprtTraversalType type,
+	hiprtRayMask	   mask,
+	hiprtApiStream	   stream )
+{
+	if ( !context || !scene || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		traceScene(
+			scene, rays, numRays, hits, type, mask, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ), times,
+			time );
+		checkCuda( cudaGetLastError(), "trace launch" );
+	} );
+}
+
 hiprtError hiprtB200TraceGeometryHost(
 	hiprtContext context, hiprtGeometry geometry, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtApiStream stream )
 {

@@ -9,7 +9,8 @@ namespace hiprt
 // triangles: the geometry holds triangle pairs (fast kernel) rather than custom primitives (generic kernel)
 void traceGeometry(
 	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream );
+// times: optional device array of one time per ray (motion blur); nullptr = every ray at `time`
 void traceScene(
 	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, uint32_t* workCounter, uint32_t smCount,
-	cudaStream_t stream );
+	cudaStream_t stream, const float* times = nullptr, float time = 0.0f );
 } // namespace hiprt

@@ -483,7 +483,7 @@ __global__ void __launch_bounds__( Block, Refill != 0 ? 1024u / Block : 1u ) tra
 
 template <hiprtTraversalType Type>
 __global__ void __launch_bounds__( TraceBlock ) traceSceneKernel(
-	hiprtScene scene, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, hiprtRayMask mask )
+	hiprtScene scene, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, hiprtRayMask mask, const float* __restrict__ times, float time )
 {
 	__shared__ uint32_t sStack[TraceBlock * SharedStackDepth];
 	const uint32_t		index = blockIdx.x * TraceBlock + threadIdx.x;
@@ -495,7 +495,9 @@ __global__ void __launch_bounds__( TraceBlock ) traceSceneKernel(
 	hiprtRay				ray;
 	ray.origin = make_float3( r0.x, r0.y, r0.z ), ray.minT = r0.w;
 	ray.direction = make_float3( r1.x, r1.y, r1.z ), ray.maxT = r1.w;
-	hiprtSceneTraversalT<HybridStack, hiprtEmptyInstanceStack, Type> tr( scene, ray, stack, noInstanceStack, mask );
+	if ( times ) time = __ldg( times + index );
+	hiprtSceneTraversalT<HybridStack, hiprtEmptyInstanceStack, Type> tr(
+		scene, ray, stack, noInstanceStack, mask, hiprtTraversalHintDefault, nullptr, nullptr, 0, time );
 	const hiprtHit hit = tr.getNextHit();
 	float4*		   hp  = reinterpret_cast<float4*>( hits + index );
 	hp[0] = make_float4( __uint_as_float( hit.instanceIDs[0] ), __uint_as_float( hit.instanceIDs[1] ), __uint_as_float( hit.instanceIDs[2] ), __uint_as_float( hit.instanceIDs[3] ) );
@@ -609,13 +611,12 @@ void traceGeometry(
 constexpr uint32_t InstanceExitMarker = 0xFFFFFFFEu; // instance-typed index no scene can hold (2^24 instance limit)
 
 // world -> object ray of an instance leaf: inverse matrix for static instances; animated ones (key-frame range in the node)
-// are traversed in their pose at time 0 -- a hiprtRay carries no time; kernels that trace at other times are user kernels
-// built on hiprtSceneTraversal*( ..., time ) of hiprt_device.h
-__device__ __forceinline__ hiprtRay instanceRayToObject( const SceneHeader* scene, const InstanceNode* in, uint32_t bits, const hiprtRay& ray )
+// are posed at the ray's time (hiprtB200TraceSceneAtTime; the plain entry points trace at time 0)
+__device__ __forceinline__ hiprtRay instanceRayToObject( const SceneHeader* scene, const InstanceNode* in, uint32_t bits, const hiprtRay& ray, float time )
 {
 	if ( ( bits >> 25 ) & 1u ) return transformRayToObject( in, ray );
 	const uint2 range = __ldg( reinterpret_cast<const uint2*>( in ) );
-	return motion::transformRay( motion::frameAt( scene->frames, range.x, range.y, 0.0f ), ray );
+	return motion::transformRay( motion::frameAt( scene->frames, range.x, range.y, time ), ray );
 }
 
 template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum>
@@ -626,7 +627,8 @@ __device__ __forceinline__ void traceSceneWarp(
 	uint32_t		index,
 	bool			live,
 	hiprtRayMask	rayMask,
-	uint32_t* const stackBase )
+	uint32_t* const stackBase,
+	float			time )
 {
 	constexpr uint32_t TotalDepth = 64;
 	uint32_t		   localStack[TotalDepth - SharedDepth];
@@ -737,7 +739,7 @@ __device__ __forceinline__ void traceSceneWarp(
 						if ( !( ( meta.w >> 26 ) & 1u ) )
 						{
 							const float maxT = ray.maxT;
-							ray				 = instanceRayToObject( scene, in, meta.w, ray );
+							ray				 = instanceRayToObject( scene, in, meta.w, ray, time );
 							ray.maxT		 = maxT;
 							invD			 = rcp3( ray.direction );
 						}
@@ -792,7 +794,7 @@ __device__ __forceinline__ void traceSceneWarp(
 		const uint4			meta = __ldg( reinterpret_cast<const uint4*>( in ) + 3 );
 		const GeomHeader*	g	 = reinterpret_cast<const GeomHeader*>( ( uint64_t( meta.y ) << 32 ) | meta.x );
 		hiprtRay			objectRay = loadRay( rays, index );
-		if ( !( ( meta.w >> 26 ) & 1u ) ) objectRay = instanceRayToObject( scene, in, meta.w, objectRay );
+		if ( !( ( meta.w >> 26 ) & 1u ) ) objectRay = instanceRayToObject( scene, in, meta.w, objectRay, time );
 		objectRay.maxT	= maxT0;
 		hit.instanceID	= meta.w & 0xFFFFFFu;
 		intersectPairTriangle( reinterpret_cast<const TrianglePairNode*>( g->primNodes ), bestRef >> 1, bestRef & 1u, objectRay, hit );
@@ -802,7 +804,8 @@ __device__ __forceinline__ void traceSceneWarp(
 
 template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum>
 __global__ void __launch_bounds__( Block ) traceSceneFastKernel(
-	hiprtScene scene, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, hiprtRayMask mask, uint32_t* workCounter )
+	hiprtScene scene, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, hiprtRayMask mask, uint32_t* workCounter,
+	const float* __restrict__ times, float time )
 {
 	__shared__ uint32_t sStack[Block * SharedDepth];
 	uint32_t* const		stackBase = sStack + ( threadIdx.x & 31u ) + ( threadIdx.x >> 5 ) * 32u * SharedDepth;
@@ -813,13 +816,16 @@ __global__ void __launch_bounds__( Block ) traceSceneFastKernel(
 		if ( lane == 0 ) base = atomicAdd( workCounter, 32u );
 		base = __shfl_sync( FullMask, base, 0 );
 		if ( base >= numRays ) return;
+		const float rayTime = ( times && base + lane < numRays ) ? __ldg( times + base + lane ) : time;
 		traceSceneWarp<Type, SharedDepth, BoxQuorum>(
-			reinterpret_cast<const SceneHeader*>( scene ), rays, hits, base + lane, base + lane < numRays, mask, stackBase );
+			reinterpret_cast<const SceneHeader*>( scene ), rays, hits, base + lane, base + lane < numRays, mask, stackBase, rayTime );
 	}
 }
 
 template <hiprtTraversalType Type>
-static void launchSceneFast( hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtRayMask mask, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
+static void launchSceneFast(
+	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtRayMask mask, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream,
+	const float* times, float time )
 {
 	constexpr uint32_t Block = 128;
 	auto			   kernel = traceSceneFastKernel<Type, Block, 32, 16>;
@@ -827,27 +833,27 @@ static void launchSceneFast( hiprtScene scene, const hiprtRay* rays, uint32_t nu
 	if ( blocksPerSm == 0 ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSm, kernel, int( Block ), 0 );
 	cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), stream );
 	const uint32_t blocks = std::min( DivideRoundUp( numRays, Block ), smCount * uint32_t( std::max( blocksPerSm, 1 ) ) );
-	kernel<<<blocks, Block, 0, stream>>>( scene, rays, numRays, hits, mask, workCounter );
+	kernel<<<blocks, Block, 0, stream>>>( scene, rays, numRays, hits, mask, workCounter, times, time );
 }
 
 void traceScene(
 	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, uint32_t* workCounter, uint32_t smCount,
-	cudaStream_t stream )
+	cudaStream_t stream, const float* times, float time )
 {
 	if ( numRays == 0 ) return;
 	if ( traceVariant() != 1 )
 	{
 		if ( type == hiprtTraversalTerminateAtAnyHit )
-			launchSceneFast<hiprtTraversalTerminateAtAnyHit>( scene, rays, numRays, hits, mask, workCounter, smCount, stream );
+			launchSceneFast<hiprtTraversalTerminateAtAnyHit>( scene, rays, numRays, hits, mask, workCounter, smCount, stream, times, time );
 		else
-			launchSceneFast<hiprtTraversalTerminateAtClosestHit>( scene, rays, numRays, hits, mask, workCounter, smCount, stream );
+			launchSceneFast<hiprtTraversalTerminateAtClosestHit>( scene, rays, numRays, hits, mask, workCounter, smCount, stream, times, time );
 		return;
 	}
 
 	const uint32_t blocks = DivideRoundUp( numRays, TraceBlock );
 	if ( type == hiprtTraversalTerminateAtAnyHit )
-		traceSceneKernel<hiprtTraversalTerminateAtAnyHit><<<blocks, TraceBlock, 0, stream>>>( scene, rays, numRays, hits, mask );
+		traceSceneKernel<hiprtTraversalTerminateAtAnyHit><<<blocks, TraceBlock, 0, stream>>>( scene, rays, numRays, hits, mask, times, time );
 	else
-		traceSceneKernel<hiprtTraversalTerminateAtClosestHit><<<blocks, TraceBlock, 0, stream>>>( scene, rays, numRays, hits, mask );
+		traceSceneKernel<hiprtTraversalTerminateAtClosestHit><<<blocks, TraceBlock, 0, stream>>>( scene, rays, numRays, hits, mask, times, time );
 }
 } // namespace hiprt

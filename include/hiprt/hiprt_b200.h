@@ -33,6 +33,21 @@ HIPRT_API hiprtError hiprtB200TraceScene(
 	hiprtRayMask	   mask,
 	hiprtApiStream	   stream );
 
+// Motion blur through the library kernel: `times` is a DEVICE array of one float per ray (the reference passes the time to the
+// traversal object's constructor, hiprt_device.h:415-440; a hiprtRay itself carries none). times == nullptr traces every ray at
+// `time`. Instances with several key frames are posed at the ray's time, static instances are unaffected.
+HIPRT_API hiprtError hiprtB200TraceSceneAtTime(
+	hiprtContext	   context,
+	hiprtScene		   scene,
+	const hiprtRay*	   rays,
+	const float*	   times,
+	float			   time,
+	uint32_t		   numRays,
+	hiprtHit*		   hits,
+	hiprtTraversalType traversalType,
+	hiprtRayMask	   mask,
+	hiprtApiStream	   stream );
+
 // Same with HOST buffers: copies the rays to the device, traces, copies the hits back and
 // synchronises the stream (the end-to-end path measured by bench.py's "e2e").
 HIPRT_API hiprtError hiprtB200TraceGeometryHost(

@@ -174,3 +174,37 @@ def test_transform_queries(ctx):
         np.testing.assert_allclose(out[:, 3], pts, rtol=5e-5, atol=5e-5)
     scene.destroy()
     geom.destroy()
+
+
+def test_library_entry_point_traces_at_a_time(ctx):
+    """hiprtB200TraceSceneAtTime (uniform time, and one time per ray) against the user kernel built on hiprtSceneTraversalClosest( ..., time )."""
+    geom, scene, _ = build_animated_scene(ctx)
+    t = ctx.torch
+    (fn,) = build_kernels(ctx, ["motionSceneKernel"])
+    rays = scenes.pinhole_rays(256, 160, (0.5, 1.0, 17.0), (0.5, 0.0, 0.0))
+    d_rays = ctx.rays_to_device(rays)
+    per_time = {}
+    for time in (0.0, 0.35, 0.8):
+        d_hits = t.zeros((len(rays), 12), dtype=t.int32, device=ctx.device)
+        Launcher().launch(fn, len(rays), 64, [scene.h, dev_ptr(d_rays), dev_ptr(d_hits), C.c_uint32(len(rays)), C.c_float(time)])
+        t.cuda.synchronize()
+        want = ctx.hits_to_host(d_hits)
+        got = ctx.hits_to_host(ctx.trace_scene_at_time(scene, d_rays, time=time))
+        assert (want["primID"] != api.INVALID).mean() > 0.015
+        assert np.array_equal(got["primID"], want["primID"]) and np.array_equal(got["instanceIDs"][:, 0], want["instanceIDs"][:, 0])
+        hit = want["primID"] != api.INVALID
+        assert np.array_equal(got["t"][hit], want["t"][hit])
+        per_time[time] = want
+    # one time per ray: ray k is traced at times[k]
+    choice = np.arange(len(rays)) % 3
+    times = np.array([0.0, 0.35, 0.8], np.float32)[choice]
+    got = ctx.hits_to_host(ctx.trace_scene_at_time(scene, d_rays, times=to_dev(ctx, times)))
+    for k, time in enumerate((0.0, 0.35, 0.8)):
+        sel = choice == k
+        assert np.array_equal(got["primID"][sel], per_time[time]["primID"][sel])
+        assert np.array_equal(got["instanceIDs"][sel, 0], per_time[time]["instanceIDs"][sel, 0])
+    # and any-hit agrees on occlusion
+    occl = ctx.hits_to_host(ctx.trace_scene_at_time(scene, d_rays, time=0.35, kind=api.ANY_HIT))
+    assert np.array_equal(occl["primID"] != api.INVALID, per_time[0.35]["primID"] != api.INVALID)
+    scene.destroy()
+    geom.destroy()
