@@ -201,6 +201,21 @@ class Geometry:
         return counts, prims, ts
 
 
+def motion_pose(srt_frames, time, ray=None):
+    """Key-frame interpolation of the oracle: (3x4 object->world matrix of the pose at `time`, world ray carried into the
+    instance or None). srt_frames: float32 [n, 12] hiprtFrameSRT rows."""
+    f = np.ascontiguousarray(srt_frames, np.float32).reshape(-1, 12)
+    m = np.zeros(12, np.float32)
+    rin = rout = None
+    if ray is not None:
+        rin = np.ascontiguousarray(ray, RAY_DTYPE).reshape(1)
+        rout = np.zeros(1, RAY_DTYPE)
+    L = lib()
+    L.orc_motion_pose.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_motion_pose(_p(f), len(f), C.c_float(time), _p(m), _p(rin), _p(rout))
+    return m.reshape(3, 4), (None if rout is None else rout[0])
+
+
 def lbvh_topology(sorted_keys, sorted_boxes, leaf_type=0):
     k = np.ascontiguousarray(sorted_keys, np.uint32)
     b = np.ascontiguousarray(sorted_boxes, np.float32).reshape(-1, 2, 3)

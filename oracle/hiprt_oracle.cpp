@@ -904,6 +904,65 @@ V3 frameTransform( const Frame& f, V3 p )
 	return r + f.trans;
 }
 
+// ---- key-frame (motion blur) transforms: Quaternion.h:110-190 (qtDot, qtNormalize, qtMix), Transform.h:178-240 (SRTFrame::interpolate,
+// invTransform), :417-449 (Transform::interpolateFrames, transformRay)
+inline float qdot( Quat a, Quat b ) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+inline Quat	 qnormalize( Quat q )
+{
+	const float len = sqrtf( qdot( q, q ) );
+	return Quat{ q.x / len, q.y / len, q.z / len, q.w / len };
+}
+Quat qmix( Quat v0, Quat v1, float t )
+{
+	v0		= qnormalize( v0 );
+	v1		= qnormalize( v1 );
+	float d = qdot( v0, v1 );
+	if ( d < 0.0f ) v1 = Quat{ -v1.x, -v1.y, -v1.z, -v1.w }, d = -d;
+	if ( d > 0.9995f ) return qnormalize( Quat{ v0.x + ( v1.x - v0.x ) * t, v0.y + ( v1.y - v0.y ) * t, v0.z + ( v1.z - v0.z ) * t, v0.w + ( v1.w - v0.w ) * t } );
+	const float theta0 = acosf( d ), theta = theta0 * t;
+	const float s0 = cosf( theta ) - d * sinf( theta ) / sinf( theta0 ), s1 = sinf( theta ) / sinf( theta0 );
+	return Quat{ v0.x * s0 + v1.x * s1, v0.y * s0 + v1.y * s1, v0.z * s0 + v1.z * s1, v0.w * s0 + v1.w * s1 };
+}
+
+Frame frameInterpolate( const Frame& f0, const Frame& f1, float t )
+{
+	Frame f;
+	f.scale = f0.scale * ( 1.0f - t ) + f1.scale * t;
+	f.shear = f0.shear * ( 1.0f - t ) + f1.shear * t;
+	f.trans = f0.trans * ( 1.0f - t ) + f1.trans * t;
+	f.rot	= qmix( f0.rot, f1.rot, t );
+	return f;
+}
+
+// pose of an instance with `count` key frames at `time` (Transform::interpolateFrames)
+Frame frameAt( const Frame* frames, uint32_t count, float time )
+{
+	if ( count == 0 || frames == nullptr ) return Frame();
+	Frame f0 = frames[0];
+	if ( count == 1 || time == 0.0f || time <= f0.time ) return f0;
+	Frame f1 = frames[count - 1];
+	if ( time >= f1.time ) return f1;
+	for ( uint32_t i = 1; i < count; ++i )
+	{
+		f1 = frames[i];
+		if ( time >= f0.time && time <= f1.time ) break;
+		f0 = f1;
+	}
+	return frameInterpolate( f0, f1, ( time - f0.time ) / ( f1.time - f0.time ) );
+}
+
+// world -> object of a point (SRTFrame::invTransform; the shear terms read the ORIGINAL point's z, as the reference does)
+V3 frameInvTransform( const Frame& f, V3 p )
+{
+	if ( f.identity() ) return p;
+	V3 r = p - f.trans;
+	r	 = qrotate( Quat{ -f.rot.x, -f.rot.y, -f.rot.z, f.rot.w }, r );
+	r	 = mk( r.x / f.scale.x, r.y / f.scale.y, r.z / f.scale.z );
+	r.y -= p.z * f.shear.z / f.scale.y;
+	r.x -= ( f.shear.x * r.y + f.shear.y * r.z ) / f.scale.x;
+	return r;
+}
+
 void frameInverseMatrix( const Frame& f, float out[3][4] )
 {
 	float Q[3][3];
@@ -1195,6 +1254,39 @@ void orc_geometry_trace( void* h, const hiprtRay* rays, uint32_t n, hiprtHit* hi
 	for ( uint32_t i = 0; i < n; ++i )
 		hits[i] = traceClosest( v, rays[i], tieMode, &bv, &lv );
 	if ( visits ) visits[0] = bv, visits[1] = lv;
+}
+
+// Key-frame interpolation for the motion-blur tests. frames: hiprtFrameSRT rows (12 floats: axis-angle rotation, scale, translation,
+// time, pad). matrixOut: 3x4 object -> world matrix of the interpolated pose (hiprt_device_impl.h:1980-2005);
+// rayOut: the world ray carried into the instance (Transform::transformRay: origin and origin + direction through the inverse).
+void orc_motion_pose( const float* srtFrames, uint32_t count, float time, float* matrixOut, const hiprtRay* rayIn, hiprtRay* rayOut )
+{
+	std::vector<Frame> frames( count );
+	for ( uint32_t i = 0; i < count; ++i )
+		frames[i] = frameFromSRT( srtFrames + 12 * size_t( i ) );
+	const Frame f = frameAt( frames.data(), count, time );
+	if ( matrixOut )
+	{
+		float Q[3][3];
+		qToMatrix( f.rot, Q );
+		for ( int i = 0; i < 3; ++i )
+		{
+			matrixOut[4 * i + 0] = Q[i][0] * f.scale.x;
+			matrixOut[4 * i + 1] = Q[i][1] * f.scale.y + Q[i][0] * f.shear.x;
+			matrixOut[4 * i + 2] = Q[i][2] * f.scale.z + Q[i][1] * f.shear.z + Q[i][0] * f.shear.y;
+		}
+		matrixOut[3] = f.trans.x, matrixOut[7] = f.trans.y, matrixOut[11] = f.trans.z;
+	}
+	if ( rayIn && rayOut )
+	{
+		*rayOut = *rayIn;
+		if ( !f.identity() )
+		{
+			const V3 o = rayIn->origin, d = rayIn->direction;
+			const V3 oo = frameInvTransform( f, o ), e = frameInvTransform( f, o + d );
+			rayOut->origin = oo, rayOut->direction = e - oo;
+		}
+	}
 }
 
 uint64_t orc_fruitless_box_visits()
