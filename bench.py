@@ -7,6 +7,11 @@ rays) and BVH build Mtris/s -- on config C2 (1M-triangle tessellated sphere, Pre
     python bench.py --impl reference --gpus N ...             # the reference's CPU arm (Embree 4.3
                                                               # bundled with the reference, all host threads)
 
+Other workloads (--workload): c3_terrain_10M (10M-triangle terrain, same ray mix), c3_terrain_10M_ao (C3 as BASELINE.json words it:
+PreferBalancedBuild + 16-spp ambient-occlusion rays). --with-hiprt-reference adds the unmodified HIPRT kernels on the same GPU
+(oracle/_ref), timed under their own protocol next to this repo's kernels under that protocol. Scene (C4), batch (C5) and
+path-tracing (C5) numbers come from tools/bench_scene.py, tools/bench_batch.py, tools/bench_pathtrace.py.
+
 A "step" is one frame: every primary ray traced closest-hit plus one shadow ray per hit pixel
 traced any-hit, rays resident in HBM (`value`), or pushed from / pulled back to pinned host
 memory through the C-ABI's host-buffer entry point (`e2e`). The BVH build is timed separately
