@@ -100,3 +100,29 @@ def validate_wide_bvh(boxes, leaves, prim_count_expected=None):
     root_ext = hi[0] - lo[0]
     root_area = 2 * (root_ext[0] * root_ext[1] + root_ext[0] * root_ext[2] + root_ext[1] * root_ext[2])
     return float(np.where(valid, area, 0).sum() / max(root_area, 1e-30))
+
+
+def cornell_obj_scene():
+    """The cornellBox.obj scene of the reference's ObjTestCases (hiprtTest.cpp:1026-1300): one geometry per OBJ shape, one
+    instance per geometry with the identity frame; instanceID = shape index, primID = face index inside the shape."""
+    d = np.load(os.path.join(GOLDEN, "cornell_obj.npz"))
+    verts = d["vertices"]
+    geoms = [orc.Geometry(verts, d[f"tris_{k}"]) for k in range(int(d["shape_count"]))]
+    scene = orc.Scene(geoms, np.arange(len(geoms)), None)
+    return scene, geoms
+
+
+def obj_camera_rays(width=512, height=512, translation=(0.0, 2.5, 5.8), fov=45.0 * np.pi / 180.0):
+    """generateRay of the reference's test/shared.h:151-168 with the TestCornellBox camera (hiprtTest.h:256-261: rotation
+    angle 0, so holDir = +x, upDir = -y, viewDir = -z), pixel offset 0.5."""
+    x = np.arange(width, dtype=f32)[None, :].repeat(height, 0)
+    y = np.arange(height, dtype=f32)[:, None].repeat(width, 1)
+    sx, sy = f32(0.024) * f32(width / height), f32(0.024)
+    px = (x + f32(0.5)) / f32(width) - f32(0.5)
+    py = (y + f32(0.5)) / f32(height) - f32(0.5)
+    dz = f32(sy / f32(2.0 * np.tan(f32(fov) / f32(2.0))))
+    d = np.stack([px * sx, -(py * sy), np.full_like(px, -dz)], -1).astype(f32)
+    ln = np.sqrt((d * d).sum(-1, dtype=f32), dtype=f32)
+    d = (d / ln[..., None]).astype(f32)
+    o = np.broadcast_to(np.asarray(translation, f32), d.shape)
+    return orc.make_rays(o.reshape(-1, 3), d.reshape(-1, 3))

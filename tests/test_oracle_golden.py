@@ -57,3 +57,97 @@ def test_closest_hit_tie_modes_agree_off_ties():
     # where they differ the two candidates are at exactly the same distance
     assert np.all(a["t"][~same] == b["t"][~same])
     assert same.mean() > 0.99
+
+
+# ---- the cornellBox.obj family (test/main.cpp:465-520, test/kernels/PrimaryRayKernel.h): closest-hit primary rays through a
+# two-level scene, coloured by primitive / instance id, hit distance, barycentrics and normal. These images pin, pixel by
+# pixel, WHICH primitive and instance the reference reports, its t, its uv convention and its normal orientation.
+def _obj_hits():
+    scene, geoms = H.cornell_obj_scene()
+    hits = scene.trace(H.obj_camera_rays(), tie_mode=0)
+    return hits, hits["primID"] != orc.INVALID
+
+
+def _check(img, name, max_bad=0.003):
+    ok, bad, mx = H.image_matches(img.reshape(512, 512, 4), H.load_golden_image(name), max_bad_frac=max_bad)
+    assert ok, (name, bad, mx)
+    return bad
+
+
+def test_prim_ids_cornell_box_matches_reference_image():
+    hits, hit = _obj_hits()
+    prim, inst = hits["primID"], hits["instanceIDs"][:, 0]
+    img = np.zeros((len(hits), 4), np.uint8)
+    img[:, 0] = np.where(hit, H.tea16(prim, np.zeros_like(prim))[0] % 255, 0)
+    img[:, 1] = np.where(hit, H.tea16(inst, np.zeros_like(inst))[0] % 255, 0)
+    img[:, 2] = np.where(hit, H.tea16(inst, prim)[0] % 255, 0)
+    img[:, 3] = 255
+    bad = _check(img, "PrimIdsCornellBox")
+    assert bad < 0.001, bad  # ids are all-or-nothing per pixel: only silhouette pixels may differ
+
+
+def test_hit_dist_cornell_box_matches_reference_image():
+    hits, hit = _obj_hits()
+    v = np.clip((hits["t"] / np.float32(50.0) * np.float32(255)).astype(np.int64), 0, 255)
+    img = np.zeros((len(hits), 4), np.uint8)
+    img[:, :3] = np.where(hit, v, 0)[:, None]
+    img[:, 3] = 255
+    _check(img, "HitDistCornellBox")
+
+
+def test_uvs_cornell_box_matches_reference_image():
+    hits, hit = _obj_hits()
+    img = np.zeros((len(hits), 4), np.uint8)
+    img[:, 0] = np.where(hit, np.clip((hits["uv"][:, 0] * np.float32(255)).astype(np.int64), 0, 255), 0)
+    img[:, 1] = np.where(hit, np.clip((hits["uv"][:, 1] * np.float32(255)).astype(np.int64), 0, 255), 0)
+    img[:, 3] = 255
+    _check(img, "UvsCornellBox")
+
+
+def test_normals_cornell_box_matches_reference_image():
+    hits, hit = _obj_hits()
+    n = hits["normal"].astype(np.float32)
+    ln = np.sqrt((n * n).sum(1))
+    n = n / np.maximum(ln, 1e-30)[:, None]  # identity instance frames: object-to-world leaves the vector unchanged
+    img = np.zeros((len(hits), 4), np.uint8)
+    img[:, :3] = np.where(hit[:, None], ((n + np.float32(1.0)) * np.float32(0.5) * np.float32(255)).astype(np.int64), 0)
+    img[:, 3] = 255
+    _check(img, "NormalsCornellBox")
+
+
+def test_pair_triangles_matches_reference_image():
+    # test/main.cpp:1122-1215 + PairTrianglesKernel: three stacked triangles (iota indices: nothing pairs), any-hit iterator
+    # drained, one colour channel per primitive
+    v = np.array([[0, 0, 1], [1, 0, 1], [0.5, 1, 1], [0, 0, 0.5], [1, 0, 0.5], [0.5, 1, 0.5], [0, 0, 0], [1, 0, 0], [0.5, 1, 0]], np.float32)
+    g = orc.Geometry(v, np.arange(9, dtype=np.uint32).reshape(3, 3))
+    counts, prims, _ = g.trace_all(H.ortho_rays(), max_per_ray=4)
+    assert counts.max() <= 3
+    img = np.zeros((512 * 512, 4), np.uint32)
+    for k in range(prims.shape[1]):
+        valid = prims[:, k] != orc.INVALID
+        for p in range(3):
+            img[:, p] += np.where(valid & (prims[:, k] == p), 255, 0).astype(np.uint32)
+    img = np.minimum(img, 255)
+    img[:, 3] = 255
+    _check(img.astype(np.uint8), "PairTriangles")
+
+
+def test_scene_intersection_singleton_matches_reference_image():
+    # test/main.cpp:1387-1480 + SceneIntersectionSingleton kernel: two triangles, one instance scaled by 0.5 (hiprtFrameSRT)
+    s = 0.5
+    v = np.array([[0.5, s, 0], [0.5 + s * 0.86, -s * 0.5, 0], [0.5 - s * 0.86, -s * 0.5, 0],
+                  [-0.5, s, 0], [-0.5 + s * 0.86, -s * 0.5, 0], [-0.5 - s * 0.86, -s * 0.5, 0]], np.float32)
+    g = orc.Geometry(v, np.arange(6, dtype=np.uint32).reshape(2, 3))
+    frame = np.array([[0, 0, 1, 0, 0.5, 0.5, 0.5, 0, 0, 0, 0, 0]], np.float32)  # rotation (axis, angle 0), scale, translation, time
+    scene = orc.Scene([g], [0], frame, 0)
+    w = h = 512
+    x = (np.arange(w, dtype=np.float32) / np.float32(w))[None, :].repeat(h, 0)
+    y = (np.arange(h, dtype=np.float32) / np.float32(h))[:, None].repeat(w, 1)
+    o = np.stack([x - np.float32(0.5), y - np.float32(0.5), np.full_like(x, -1.0)], -1).reshape(-1, 3)
+    rays = orc.make_rays(o, np.broadcast_to(np.array([0, 0, 1], np.float32), o.shape), max_t=1000.0)
+    hit = scene.trace(rays)["primID"] != orc.INVALID
+    img = np.zeros((w * h, 4), np.uint8)
+    img[:, 0] = np.where(hit, (x.reshape(-1) * np.float32(255)).astype(np.uint8), 0)
+    img[:, 1] = np.where(hit, (y.reshape(-1) * np.float32(255)).astype(np.uint8), 0)
+    img[:, 3] = 255
+    _check(img, "SceneIntersectionSingleton")
