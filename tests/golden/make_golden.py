@@ -39,19 +39,22 @@ def parse_cornell_header():
 def parse_obj(path):
     """Minimal OBJ reader: per-'g'/'o' shape triangle lists, fan-triangulated, indices into a
     global vertex array (what tinyobjloader gives the reference tests)."""
-    verts, shapes, cur = [], [], None
+    verts, shapes, cur, material = [], [], None, None
     for line in open(path):
         p = line.split()
         if not p:
             continue
+        if p[0] == "usemtl":
+            material = p[1]
+            continue
         if p[0] == "v":
             verts.append([float(x) for x in p[1:4]])
         elif p[0] in ("g", "o"):
-            cur = {"name": " ".join(p[1:]), "tris": []}
+            cur = {"name": " ".join(p[1:]), "tris": [], "mats": []}
             shapes.append(cur)
         elif p[0] == "f":
             if cur is None:
-                cur = {"name": "default", "tris": []}
+                cur = {"name": "default", "tris": [], "mats": []}
                 shapes.append(cur)
             ids = []
             for tok in p[1:]:
@@ -59,6 +62,7 @@ def parse_obj(path):
                 ids.append(i - 1 if i > 0 else len(verts) + i)
             for k in range(1, len(ids) - 1):
                 cur["tris"].append([ids[0], ids[k], ids[k + 1]])
+                cur["mats"].append(material)
     shapes = [s for s in shapes if s["tris"]]
     return np.array(verts, np.float32), shapes
 
@@ -83,9 +87,18 @@ def main():
 
     v, shapes = parse_obj(os.path.join(REF, "test/common/meshes/cornellbox/cornellBox.obj"))
     out = {"vertices": v, "shape_count": np.array(len(shapes))}
+    # diffuse colour per face (cornellBox.mtl, Kd): what PrimaryRayKernel<VisualizeColor> paints (PrimaryRayKernel.h:43-56)
+    kd, name = {}, None
+    for line in open(os.path.join(REF, "test/common/meshes/cornellbox/cornellBox.mtl")):
+        q = line.split()
+        if q and q[0] == "newmtl":
+            name = q[1]
+        elif q and q[0] == "Kd":
+            kd[name] = [float(x) for x in q[1:4]]
     for i, s in enumerate(shapes):
         out[f"tris_{i}"] = np.array(s["tris"], np.uint32)
-        print("shape", i, s["name"], len(s["tris"]))
+        out[f"diffuse_{i}"] = np.array([kd[m] for m in s["mats"]], np.float32)
+        print("shape", i, s["name"], len(s["tris"]), sorted(set(s["mats"])))
     np.savez_compressed(os.path.join(HERE, "cornell_obj.npz"), **out)
 
 

@@ -102,14 +102,23 @@ def validate_wide_bvh(boxes, leaves, prim_count_expected=None):
     return float(np.where(valid, area, 0).sum() / max(root_area, 1e-30))
 
 
-def cornell_obj_scene():
+def cornell_obj_scene(srt_frame=None):
     """The cornellBox.obj scene of the reference's ObjTestCases (hiprtTest.cpp:1026-1300): one geometry per OBJ shape, one
-    instance per geometry with the identity frame; instanceID = shape index, primID = face index inside the shape."""
+    instance per geometry, all with the identity frame or the same hiprtFrameSRT (12 floats: axis-angle rotation, scale,
+    translation, time, pad); instanceID = shape index, primID = face index inside the shape."""
     d = np.load(os.path.join(GOLDEN, "cornell_obj.npz"))
     verts = d["vertices"]
-    geoms = [orc.Geometry(verts, d[f"tris_{k}"]) for k in range(int(d["shape_count"]))]
-    scene = orc.Scene(geoms, np.arange(len(geoms)), None)
+    n = int(d["shape_count"])
+    geoms = [orc.Geometry(verts, d[f"tris_{k}"]) for k in range(n)]
+    frames = None if srt_frame is None else np.tile(np.asarray(srt_frame, np.float32).reshape(1, 12), (n, 1))
+    scene = orc.Scene(geoms, np.arange(n), frames, 0)
     return scene, geoms
+
+
+def cornell_obj_face_colours():
+    """Diffuse colour (Kd of cornellBox.mtl) per (shape, face): list of float32 [faces, 3]."""
+    d = np.load(os.path.join(GOLDEN, "cornell_obj.npz"))
+    return [d[f"diffuse_{k}"] for k in range(int(d["shape_count"]))]
 
 
 def obj_camera_rays(width=512, height=512, translation=(0.0, 2.5, 5.8), fov=45.0 * np.pi / 180.0):

@@ -1,5 +1,6 @@
 """Pin the CPU oracle against the reference's own golden images (CPU only)."""
 import numpy as np
+import pytest
 
 from oracle import binding as orc
 from tests import helpers as H
@@ -151,3 +152,29 @@ def test_scene_intersection_singleton_matches_reference_image():
     img[:, 1] = np.where(hit, (y.reshape(-1) * np.float32(255)).astype(np.uint8), 0)
     img[:, 3] = 255
     _check(img, "SceneIntersectionSingleton")
+
+
+def _colour_image(hits):
+    hit = hits["primID"] != orc.INVALID
+    colours = H.cornell_obj_face_colours()
+    img = np.zeros((len(hits), 4), np.uint8)
+    inst, prim = hits["instanceIDs"][:, 0], hits["primID"]
+    for k, c in enumerate(colours):
+        sel = hit & (inst == k)
+        img[sel, :3] = (c[prim[sel]] * np.float32(255)).astype(np.uint8)
+    img[:, 3] = 255
+    return img
+
+
+@pytest.mark.parametrize("name, frame", [
+    ("PrimaryRayCornellBox", None),
+    ("TranslateCornellBox", [0, 0, 1, 0, 1, 1, 1, 0, 0, -5, 0, 0]),
+    ("ScaleCornellBox", [0, 0, 1, 0, 2, 2, 2, 0, 0, 0, 0, 0]),
+    ("RotateCornellBox", [0, 1, 0, 0.5, 1, 1, 1, 0, 0, -3, 0, 0]),
+])
+def test_instanced_cornell_box_colour_images_match_reference(name, frame):
+    """test/main.cpp:252-300,465-475: every instance of the OBJ scene carries the same hiprtFrameSRT (translation / scale /
+    rotation about y); painted with the face's diffuse colour. Pins the oracle's instance transform against the reference's."""
+    scene, _ = H.cornell_obj_scene(frame)
+    hits = scene.trace(H.obj_camera_rays(), tie_mode=0)
+    _check(_colour_image(hits), name)
