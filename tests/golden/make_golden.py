@@ -76,7 +76,7 @@ def main():
     names = [
         "MinimumCornellBox", "MeshIntersection", "PairTriangles", "PrimIdsCornellBox", "HitDistCornellBox",
         "UvsCornellBox", "PrimaryRayCornellBox", "NormalsCornellBox", "SceneIntersection", "SceneIntersectionSingleton",
-        "TranslateCornellBox", "ScaleCornellBox", "RotateCornellBox", "Cutout", "CustomIntersection",
+        "TranslateCornellBox", "ScaleCornellBox", "RotateCornellBox", "Cutout", "CustomIntersection", "MotionBlur",
     ]
     imgs = {}
     for n in names:

@@ -41,3 +41,46 @@ def test_motion_ray_transform_is_the_inverse_of_the_pose():
         np.testing.assert_allclose(local["origin"], inv @ (ray["origin"] - t), rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(local["direction"], inv @ ray["direction"], rtol=1e-4, atol=1e-4)
         assert local["maxT"] == ray["maxT"] and local["minT"] == ray["minT"]
+
+
+def test_motion_blur_matches_reference_image():
+    """The reference's MotionBlur test (test/main.cpp:1995-2180, MotionBlurKernel HiprtTestKernel.h:328-359): two single-triangle
+    instances with 3 and 2 hiprtFrameSRT key frames (translation and rotation about z), 32 time samples per pixel, closest hit,
+    colour per instance, gamma 2.2. Pins the oracle's key-frame interpolation (orc_motion_pose) against the reference's image."""
+    from tests import helpers as H
+
+    s, off, pi = 0.15, 0.3, np.float32(np.pi)
+    tri = np.array([[s * np.sin(0.0), s * np.cos(0.0), 0.0], [s * np.sin(pi * 2 / 3), s * np.cos(pi * 2 / 3), 0.0],
+                    [s * np.sin(pi * 4 / 3), s * np.cos(pi * 4 / 3), 0.0]], np.float32)
+    geom = orc.Geometry(tri, np.array([[0, 1, 2]], np.uint32))
+    srt = lambda tr, angle, time: [0, 0, 1, angle, 1, 1, 1, tr[0], tr[1], tr[2], time, 0]
+    keys = [np.array([srt((-0.25, -off, 0), 0.0, 0.0), srt((0.0, -off, 0), 0.0, 0.35), srt((0.25, -off, 0), pi * 0.25, 1.0)], np.float32),
+            np.array([srt((0.0, off, 0), 0.0, 0.0), srt((0.0, off, 0), pi * 0.5, 1.0)], np.float32)]
+    w = h = 512
+    x = (np.arange(w, dtype=np.float32) / np.float32(w))[None, :].repeat(h, 0) - np.float32(0.5)
+    y = (np.arange(h, dtype=np.float32) / np.float32(h))[:, None].repeat(w, 1) - np.float32(0.5)
+    o = np.stack([x, y, np.full_like(x, -1.0)], -1).reshape(-1, 3)
+    d = np.broadcast_to(np.array([0, 0, 1], np.float32), o.shape)
+    colours = np.array([[1.0, 0.0, 0.5], [0.0, 0.5, 1.0]], np.float32)
+    acc = np.zeros((w * h, 3), np.float32)
+    samples = 32
+    for i in range(samples):
+        time = np.float32(i) / np.float32(samples)
+        best_t = np.full(w * h, np.inf, np.float32)
+        best_inst = np.full(w * h, -1, np.int64)
+        for inst in range(2):
+            m, _ = orc.motion_pose(keys[inst], float(time))
+            a_inv = np.linalg.inv(m[:, :3].astype(np.float64))
+            oo = ((o.astype(np.float64) - m[:, 3].astype(np.float64)) @ a_inv.T).astype(np.float32)
+            dd = (d.astype(np.float64) @ a_inv.T).astype(np.float32)
+            hits = geom.trace(orc.make_rays(oo, dd), tie_mode=0)
+            closer = (hits["primID"] != orc.INVALID) & (hits["t"] < best_t)
+            best_t[closer], best_inst[closer] = hits["t"][closer], inst
+        hit = best_inst >= 0
+        acc[hit] += colours[best_inst[hit]]
+    col = np.power(acc / np.float32(samples), np.float32(1.0 / 2.2))
+    img = np.zeros((w * h, 4), np.uint8)
+    img[:, :3] = (col * np.float32(255)).astype(np.uint8)
+    img[:, 3] = 255
+    ok, bad, mx = H.image_matches(img.reshape(h, w, 4), H.load_golden_image("MotionBlur"))
+    assert ok, (bad, mx)
