@@ -76,7 +76,7 @@ def main():
     names = [
         "MinimumCornellBox", "MeshIntersection", "PairTriangles", "PrimIdsCornellBox", "HitDistCornellBox",
         "UvsCornellBox", "PrimaryRayCornellBox", "NormalsCornellBox", "SceneIntersection", "SceneIntersectionSingleton",
-        "TranslateCornellBox", "ScaleCornellBox", "RotateCornellBox", "Cutout", "CustomIntersection", "MotionBlur",
+        "TranslateCornellBox", "ScaleCornellBox", "RotateCornellBox", "Cutout", "CustomIntersection", "MotionBlur", "Shear",
     ]
     imgs = {}
     for n in names:

@@ -178,3 +178,26 @@ def test_instanced_cornell_box_colour_images_match_reference(name, frame):
     scene, _ = H.cornell_obj_scene(frame)
     hits = scene.trace(H.obj_camera_rays(), tie_mode=0)
     _check(_colour_image(hits), name)
+
+
+def test_shear_matches_reference_image():
+    # test/main.cpp:1902-1993 + SceneIntersectionSingleton kernel: an indexed quad (two triangles: too few to pair) instanced with a
+    # hiprtFrameMatrix that shears x by y: exercises the matrix -> scale / shear / rotation decomposition of the scene build
+    off = 0.25
+    v = np.array([[-off, -off, 0], [-off, off, 0], [off, off, 0], [off, -off, 0]], np.float32)
+    g = orc.Geometry(v, np.array([[0, 1, 2], [0, 2, 3]], np.uint32))
+    m = np.zeros((1, 16), np.float32)
+    m[0, [0, 5, 10]] = 1.0
+    m[0, 1] = 1.0  # matrix[0][1]
+    scene = orc.Scene([g], [0], m, 1)
+    w = h = 512
+    x = (np.arange(w, dtype=np.float32) / np.float32(w))[None, :].repeat(h, 0)
+    y = (np.arange(h, dtype=np.float32) / np.float32(h))[:, None].repeat(w, 1)
+    o = np.stack([x - np.float32(0.5), y - np.float32(0.5), np.full_like(x, -1.0)], -1).reshape(-1, 3)
+    rays = orc.make_rays(o, np.broadcast_to(np.array([0, 0, 1], np.float32), o.shape), max_t=1000.0)
+    hit = scene.trace(rays)["primID"] != orc.INVALID
+    img = np.zeros((w * h, 4), np.uint8)
+    img[:, 0] = np.where(hit, (x.reshape(-1) * np.float32(255)).astype(np.uint8), 0)
+    img[:, 1] = np.where(hit, (y.reshape(-1) * np.float32(255)).astype(np.uint8), 0)
+    img[:, 3] = 255
+    _check(img, "Shear")
