@@ -201,3 +201,24 @@ def test_shear_matches_reference_image():
     img[:, 1] = np.where(hit, (y.reshape(-1) * np.float32(255)).astype(np.uint8), 0)
     img[:, 3] = 255
     _check(img, "Shear")
+
+
+def test_cutout_matches_reference_image():
+    """test/main.cpp:1219-1290 + CutoutKernel / cutoutFilter (HiprtTestKernel.h:88-100,216-235): a unit quad of two triangles,
+    closest hit with a hit filter that cuts a 16x16 checkerboard out of texture coordinates interpolated from hit.uv per
+    primID. The filter only lets a hit through when uv follows the CALLER's vertex order -- this pins the barycentric convention
+    (and primID assignment) the oracle reports, including for the second triangle of a quad."""
+    v = np.array([[0, 0, 0], [0, 1, 0], [1, 1, 0], [1, 0, 0]], np.float32)
+    g = orc.Geometry(v, np.array([[0, 1, 2], [0, 2, 3]], np.uint32))
+    hits = g.trace(H.ortho_rays(), tie_mode=0)
+    hit = hits["primID"] != orc.INVALID
+    u, w_ = hits["uv"][:, 0], hits["uv"][:, 1]
+    # texCoord[primID] = (1-u-v) * t0 + u * t1 + v * t2 with (t0,t1,t2) = ((0,0),(0,1),(1,1)) for triangle 0, ((0,0),(1,1),(1,0)) for 1
+    tx = np.where(hits["primID"] == 0, w_, u + w_).astype(np.float32)
+    ty = np.where(hits["primID"] == 0, u + w_, u).astype(np.float32)
+    rejected = ((np.float32(16.0) * tx).astype(np.uint32) + (np.float32(16.0) * ty).astype(np.uint32)) & 1
+    visible = hit & (rejected == 0)
+    img = np.zeros((512 * 512, 4), np.uint8)
+    img[:, :3] = np.where(visible, 255, 0)[:, None]
+    img[:, 3] = 255
+    _check(img, "Cutout")
