@@ -305,6 +305,34 @@ class Context:
     def destroy_geometry(self, geom):
         self._check(lib().hiprtDestroyGeometry(self.h, geom), "hiprtDestroyGeometry")
 
+    def compact_geometry(self, geom, stream=None):
+        """hiprtCompactGeometry: moves the geometry into an allocation of exactly the used size; `geom` (raw handle) is freed."""
+        out = C.c_void_p()
+        self._check(lib().hiprtCompactGeometry(self.h, _stream_handle(stream), geom, C.byref(out)), "hiprtCompactGeometry")
+        return out
+
+    def compact_scene(self, scene, stream=None):
+        out = C.c_void_p()
+        self._check(lib().hiprtCompactScene(self.h, _stream_handle(stream), scene, C.byref(out)), "hiprtCompactScene")
+        return out
+
+    def save_geometry(self, geom, filename):
+        self._check(lib().hiprtSaveGeometry(self.h, geom, os.fsencode(filename)), "hiprtSaveGeometry")
+
+    def load_geometry(self, filename):
+        out = C.c_void_p()
+        self._check(lib().hiprtLoadGeometry(self.h, C.byref(out), os.fsencode(filename)), "hiprtLoadGeometry")
+        return out
+
+    def export_aabb(self, geom_or_scene):
+        """hiprtExportGeometryAabb / hiprtExportSceneAabb -> (min xyz, max xyz) as float32 arrays."""
+        lo, hi = Float3(), Float3()
+        is_scene = isinstance(geom_or_scene, Scene)
+        fn = lib().hiprtExportSceneAabb if is_scene else lib().hiprtExportGeometryAabb
+        handle = geom_or_scene.h if hasattr(geom_or_scene, "h") else geom_or_scene
+        self._check(fn(self.h, handle, C.byref(lo), C.byref(hi)), "hiprtExportSceneAabb" if is_scene else "hiprtExportGeometryAabb")
+        return np.array([lo.x, lo.y, lo.z], np.float32), np.array([hi.x, hi.y, hi.z], np.float32)
+
     def enable_build_profile(self, on=True):
         self._check(lib().hiprtB200EnableBuildProfile(self.h, int(on)), "hiprtB200EnableBuildProfile")
 

@@ -77,10 +77,21 @@ def main():
         "MinimumCornellBox", "MeshIntersection", "PairTriangles", "PrimIdsCornellBox", "HitDistCornellBox",
         "UvsCornellBox", "PrimaryRayCornellBox", "NormalsCornellBox", "SceneIntersection", "SceneIntersectionSingleton",
         "TranslateCornellBox", "ScaleCornellBox", "RotateCornellBox", "Cutout", "CustomIntersection", "MotionBlur", "Shear",
+        "BvhUpdateCornellBox", "RayMaskCornellBox", "Rebuild0", "Rebuild1", "Update0", "Update1", "MotionBlurSlerp",
+        "SceneIntersectionMlas", "AoRayCornellBox", "ShadowRayCornellBox",
+        # byte-identical copies of images above (checked below): the reference renders them through other builders / the
+        # import and save-load paths and validates against the same picture
+        "BvhFastCornellBox", "BvhBalancedCornellBox", "BvhHighQCornellBox", "CustomBvhImport", "BvhIoApi",
     ]
+    same_as = {"BvhFastCornellBox": "PrimaryRayCornellBox", "BvhBalancedCornellBox": "PrimaryRayCornellBox",
+               "BvhHighQCornellBox": "PrimaryRayCornellBox", "CustomBvhImport": "MinimumCornellBox", "BvhIoApi": "MinimumCornellBox"}
     imgs = {}
     for n in names:
         im = np.array(Image.open(os.path.join(REF, "test/references", n + ".png")).convert("RGBA"))
+        if n in same_as:
+            assert np.array_equal(im, imgs[same_as[n]]), n  # recorded as an alias, not stored twice
+            print(n, "==", same_as[n])
+            continue
         imgs[n] = im
         print(n, im.shape)
     np.savez_compressed(os.path.join(HERE, "golden_images.npz"), **imgs)

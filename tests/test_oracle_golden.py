@@ -6,26 +6,36 @@ from oracle import binding as orc
 from tests import helpers as H
 
 
-def test_minimum_cornell_box_matches_reference_image():
-    # reference test: test/main.cpp:532-619 (any-hit iterator drained, colours summed)
-    verts, mats, diffuse = H.cornell_box()
-    idx = np.arange(96, dtype=np.uint32).reshape(-1, 3)
-    g = orc.Geometry(verts, idx)
-    assert g.prim_count == 32  # iota indices share no vertex index: nothing pairs
-    rays = H.cornell_rays()
-    counts, prims, _ = g.trace_all(rays, max_per_ray=16)
-    assert counts.max() <= 16
+def minimum_cornell_image(prims):
+    """CornellBoxKernel (HiprtTestKernel.h:118-165): a third of the diffuse colour of every primitive along the ray, summed.
+    prims: uint32 [rays, k] primitive ids of all hits of a ray, INVALID-padded."""
+    _, mats, diffuse = H.cornell_box()
     col = (np.float32(1.0 / 3.0) * diffuse * np.float32(255)).astype(np.uint32)  # per material
-    img = np.zeros((len(rays), 4), np.uint32)
+    img = np.zeros((len(prims), 4), np.uint32)
     for k in range(prims.shape[1]):
         valid = prims[:, k] != orc.INVALID
         c = col[mats[np.where(valid, prims[:, k], 0)]]
         img[:, :3] += np.where(valid[:, None], c, 0)
     img = np.minimum(img, 255)
     img[:, 3] = 255
-    ok, bad, mx = H.image_matches(img.reshape(512, 512, 4), H.load_golden_image("MinimumCornellBox"))
-    assert ok, (bad, mx)
-    assert bad == 0.0, (bad, mx)
+    return img
+
+
+def test_minimum_cornell_box_matches_reference_image():
+    # reference test: test/main.cpp:532-619 (any-hit iterator drained, colours summed)
+    verts, _, _ = H.cornell_box()
+    idx = np.arange(96, dtype=np.uint32).reshape(-1, 3)
+    g = orc.Geometry(verts, idx)
+    assert g.prim_count == 32  # iota indices share no vertex index: nothing pairs
+    rays = H.cornell_rays()
+    counts, prims, _ = g.trace_all(rays, max_per_ray=16)
+    assert counts.max() <= 16
+    img = minimum_cornell_image(prims)
+    # CustomBvhImport.png and BvhIoApi.png are byte-identical copies of this image (tests/golden/make_golden.py)
+    for name in ("MinimumCornellBox", "CustomBvhImport", "BvhIoApi"):
+        ok, bad, mx = H.image_matches(img.reshape(512, 512, 4), H.load_golden_image(name))
+        assert ok, (bad, mx)
+        assert bad == 0.0, (bad, mx)
 
 
 def test_mesh_intersection_matches_reference_image():
@@ -166,11 +176,23 @@ def _colour_image(hits):
     return img
 
 
+def _accumulated_angle(steps):
+    a = np.float32(0.0)
+    for _ in range(steps):
+        a = np.float32(float(a) + 0.1)  # `float angle; angle += 0.1` of the reference's loop
+    return float(a)
+
+
+BVH_UPDATE_ANGLE = _accumulated_angle(7)
+
+
 @pytest.mark.parametrize("name, frame", [
     ("PrimaryRayCornellBox", None),
     ("TranslateCornellBox", [0, 0, 1, 0, 1, 1, 1, 0, 0, -5, 0, 0]),
     ("ScaleCornellBox", [0, 0, 1, 0, 2, 2, 2, 0, 0, 0, 0, 0]),
     ("RotateCornellBox", [0, 1, 0, 0.5, 1, 1, 1, 0, 0, -3, 0, 0]),
+    # test/main.cpp:301-343: the last of eight scenes rotated in steps of 0.1 (float accumulation of the double 0.1: 0.70000005)
+    ("BvhUpdateCornellBox", [0, 1, 0, BVH_UPDATE_ANGLE, 1, 1, 1, 0, 0, -3, 0, 0]),
 ])
 def test_instanced_cornell_box_colour_images_match_reference(name, frame):
     """test/main.cpp:252-300,465-475: every instance of the OBJ scene carries the same hiprtFrameSRT (translation / scale /
@@ -178,6 +200,46 @@ def test_instanced_cornell_box_colour_images_match_reference(name, frame):
     scene, _ = H.cornell_obj_scene(frame)
     hits = scene.trace(H.obj_camera_rays(), tie_mode=0)
     _check(_colour_image(hits), name)
+
+
+def test_ray_mask_cornell_box_matches_reference_image():
+    """RayMaskCornellBox.png: the OBJ scene set up with enableRayMask (hiprtTest.cpp:1215-1218: every even shape gets instance
+    mask 0, the others ~0) and traced with hiprtFullRayMask: masked instances must vanish (the light, the ceiling, the left wall
+    and the short box), and what was behind them shows."""
+    d = np.load(H.os.path.join(H.GOLDEN, "cornell_obj.npz"))
+    n = int(d["shape_count"])
+    geoms = [orc.Geometry(d["vertices"], d[f"tris_{k}"]) for k in range(n)]
+    masks = np.array([0 if k % 2 == 0 else 0xFFFFFFFF for k in range(n)], np.uint32)
+    scene = orc.Scene(geoms, np.arange(n), None, 0, masks=masks)
+    hits = scene.trace(H.obj_camera_rays(), tie_mode=0)
+    assert not np.isin(hits["instanceIDs"][hits["primID"] != orc.INVALID, 0], [0, 2, 4, 6]).any()
+    _check(_colour_image(hits), "RayMaskCornellBox")
+
+
+REBUILD_VERTICES = np.array([[0.15, 0.40, 0.0], [0.35, 0.40, 0.0], [0.25, 0.60, 0.0],
+                             [0.65, 0.40, 0.0], [0.85, 0.40, 0.0], [0.75, 0.60, 0.0]], np.float32)
+
+
+def mesh_intersection_image(hit, w=512, h=512):
+    """MeshIntersectionKernel (HiprtTestKernel.h): red / green = pixel position where the ray hits, black elsewhere."""
+    x = np.arange(w, dtype=np.float32)[None, :].repeat(h, 0).reshape(-1)
+    y = np.arange(h, dtype=np.float32)[:, None].repeat(w, 1).reshape(-1)
+    img = np.zeros((w * h, 4), np.uint8)
+    img[:, 0] = np.where(hit, (x / np.float32(w) * np.float32(255)).astype(np.uint8), 0)
+    img[:, 1] = np.where(hit, (y / np.float32(h) * np.float32(255)).astype(np.uint8), 0)
+    img[:, 3] = 255
+    return img
+
+
+@pytest.mark.parametrize("names, first_vertex", [(("Rebuild0", "Update0"), 0), (("Rebuild1", "Update1"), 3)])
+def test_rebuild_and_update_images_match_reference(names, first_vertex):
+    """test/main.cpp:2515-2653: one triangle, its three vertices overwritten and the geometry rebuilt (Rebuild) or refitted
+    (Update): both must show the triangle at its new place. The oracle has no update operation (a refit of a one-leaf tree is
+    the rebuild); this pins the pictures the GPU tests hold hiprtBuildOperationUpdate to (tests/test_gpu_golden.py)."""
+    g = orc.Geometry(REBUILD_VERTICES[first_vertex:first_vertex + 3], np.array([[0, 1, 2]], np.uint32))
+    hit = g.trace(H.ortho_rays(), tie_mode=0)["primID"] != orc.INVALID
+    for name in names:
+        assert _check(mesh_intersection_image(hit), name) < 0.001
 
 
 def test_shear_matches_reference_image():
