@@ -23,6 +23,17 @@ __device__ bool intersectSphere( const hiprtRay& ray, const void* data, void* pa
 	return true;
 }
 
+// custom primitive of the reference's scene tests (intersectCircle, HiprtTestKernel.h:62-79): a disc of radius 0.1 around
+// (centres[primID], 0.5) in the plane z = 1, for rays that travel along +z; data = one float (the x of the centre) per primitive
+__device__ bool intersectCircle( const hiprtRay& ray, const void* data, void*, hiprtHit& hit )
+{
+	const float dx = reinterpret_cast<const float*>( data )[hit.primID] - ray.origin.x;
+	const float dy = 0.5f - ray.origin.y;
+	if ( sqrtf( dx * dx + dy * dy ) >= 0.1f ) return false;
+	hit.t = ( 1.0f - ray.origin.z ) / ray.direction.z;
+	return true;
+}
+
 // hit filter ("cutout"): returns true to REJECT the hit (reference convention); data = one float threshold
 __device__ bool cutoutFilter( const hiprtRay&, const void* data, void*, const hiprtHit& hit )
 {
@@ -61,6 +72,34 @@ extern "C" __global__ void allHitsKernel(
 		if ( tr.getCurrentState() != hiprtTraversalStateHit ) break;
 		if ( n < maxPerRay ) prims[i * maxPerRay + n] = h.primID, ts[i * maxPerRay + n] = h.t;
 		++n;
+	}
+	counts[i] = n;
+}
+
+// every hit of a (possibly multi-level) scene through the re-entrant any-hit iterator, custom primitives through the function
+// table: per hit the primitive and the instance ids of the first two levels (cf. SceneIntersectionKernel, HiprtTestKernel.h:286-326)
+extern "C" __global__ void sceneAllHitsKernel(
+	hiprtScene scene, hiprtFuncTable table, const hiprtRay* rays, uint32_t numRays, uint32_t maxPerRay, uint32_t* counts, uint32_t* prims,
+	uint32_t* inst0, uint32_t* inst1 )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= numRays ) return;
+	hiprtSceneTraversalAnyHit tr( scene, rays[i], hiprtFullRayMask, hiprtTraversalHintDefault, nullptr, table );
+	uint32_t				  n = 0;
+	while ( true )
+	{
+		const hiprtHit h = tr.getNextHit();
+		if ( h.hasHit() )
+		{
+			if ( n < maxPerRay )
+			{
+				prims[i * maxPerRay + n] = h.primID;
+				inst0[i * maxPerRay + n] = h.instanceIDs[0];
+				inst1[i * maxPerRay + n] = h.instanceIDs[1];
+			}
+			++n;
+		}
+		if ( tr.getCurrentState() != hiprtTraversalStateHit ) break;
 	}
 	counts[i] = n;
 }

@@ -179,3 +179,106 @@ def test_bounding_box_export_and_unimplemented_entry_points(ctx):
     scene.destroy()
     for g in geoms:
         g.destroy()
+
+
+# ---- custom primitives and multi-level scenes (test/main.cpp:1296-1385 CustomIntersection, :1485-1670 SceneIntersection,
+# :1672-1900 SceneIntersectionMlas): three discs as an AABB list with a custom intersection function, three triangles, both
+# instanced in one scene; that scene instanced twice in a top-level scene
+CIRCLE_BOXES = np.array([[0.15, 0.40, 0.35, 0.60], [0.40, 0.40, 0.60, 0.60], [0.65, 0.40, 0.85, 0.60]], np.float32)
+SCENE_TRIANGLES = np.array([[0.15, 0.40, 0], [0.35, 0.40, 0], [0.25, 0.60, 0], [0.40, 0.40, 0], [0.60, 0.40, 0], [0.50, 0.60, 0],
+                            [0.65, 0.40, 0], [0.85, 0.40, 0], [0.75, 0.60, 0]], np.float32)
+
+
+def unit_square_rays(w=512, h=512):
+    x = (np.arange(w, dtype=np.float32) / np.float32(w))[None, :].repeat(h, 0)
+    y = (np.arange(h, dtype=np.float32) / np.float32(h))[:, None].repeat(w, 1)
+    o = np.stack([x, y, np.full_like(x, -1.0)], -1).reshape(-1, 3)
+    return orc.make_rays(o, np.broadcast_to(np.array([0, 0, 1], np.float32), o.shape), max_t=1000.0)
+
+
+class CircleFixture:
+    """The discs' geometry (boxes at height z), the function table with their centres, and the compiled kernels."""
+
+    def __init__(self, ctx, z, wide_stride):
+        lo = np.concatenate([CIRCLE_BOXES[:, :2], np.full((3, 1), z, np.float32)], 1)
+        hi = np.concatenate([CIRCLE_BOXES[:, 2:], np.full((3, 1), z, np.float32)], 1)
+        pad = np.zeros((3, 1), np.float32)
+        boxes = np.concatenate([lo, pad, hi, pad], 1) if wide_stride else np.concatenate([lo, hi], 1)  # float4 or float3 pairs
+        self.ctx = ctx
+        self.inp = ctx.aabb_input(to_dev(ctx, boxes), geom_type=0)
+        self.temp = ctx.alloc_temp(ctx.geometry_temp_size(self.inp))
+        self.geom = ctx.create_geometry(self.inp)
+        ctx.build_geometry(self.inp, self.geom, self.temp)
+        self.fn_scene, self.fn_closest = build_kernels(ctx, ["sceneAllHitsKernel", "customKernel"], [("intersectCircle", None)], num_geom_types=1)
+        self.centres = to_dev(ctx, np.array([0.25, 0.5, 0.75], np.float32))
+        self.table = C.c_void_p()
+        ctx._check(api.lib().hiprtCreateFuncTable(ctx.h, 1, 1, C.byref(self.table)), "hiprtCreateFuncTable")
+        ctx._check(api.lib().hiprtSetFuncTable(ctx.h, self.table, 0, 0, api.FuncDataSet(self.centres.data_ptr(), None)), "hiprtSetFuncTable")
+
+    def close(self):
+        api.lib().hiprtDestroyFuncTable(self.ctx.h, self.table)
+        self.ctx.destroy_geometry(self.geom)
+
+
+def scene_all_hits_image(ctx, fx, scene, max_per=8):
+    """SceneIntersectionKernel's picture: every hit adds the colour of (innermost instance, primitive) to the pixel, in the
+    image's own uint8 arithmetic (wraps)."""
+    t = ctx.torch
+    rays = unit_square_rays()
+    n, d_rays = len(rays), ctx.rays_to_device(rays)
+    d_counts = t.zeros(n, dtype=t.int32, device=ctx.device)
+    d_out = [t.full((n, max_per), -1, dtype=t.int32, device=ctx.device) for _ in range(3)]
+    Launcher().launch(fx.fn_scene, n, 64, [scene.h, fx.table, dev_ptr(d_rays), C.c_uint32(n), C.c_uint32(max_per), dev_ptr(d_counts)] + [dev_ptr(d) for d in d_out])
+    t.cuda.synchronize()
+    counts = d_counts.cpu().numpy()
+    assert counts.max() <= max_per
+    prims, inst0, inst1 = (d.cpu().numpy().view(np.uint32) for d in d_out)
+    colours = np.array([[[1, 0, 0], [0, 1, 0], [0, 0, 1]], [[0, 1, 1], [1, 0, 1], [1, 1, 0]]], np.uint8) * np.uint8(255)
+    img = np.zeros((n, 4), np.uint8)
+    img[:, 3] = 255
+    for k in range(max_per):
+        valid = k < counts
+        inner = np.where(inst1[:, k] != api.INVALID, inst1[:, k], inst0[:, k])
+        c = colours[np.where(valid, inner, 0), np.where(valid, prims[:, k], 0)]
+        img[:, :3] += np.where(valid[:, None], c, 0).astype(np.uint8)  # uint8 wrap-around, as `image[...] += color` does
+    return img, counts, inst0, inst1
+
+
+def test_custom_intersection_image_from_the_gpu(ctx):
+    fx = CircleFixture(ctx, z=0.0, wide_stride=False)
+    t = ctx.torch
+    rays = unit_square_rays()
+    n, d_rays = len(rays), ctx.rays_to_device(rays)
+    d_hits = t.zeros((n, 12), dtype=t.int32, device=ctx.device)
+    d_payload = t.zeros(1, dtype=t.int32, device=ctx.device)
+    Launcher().launch(fx.fn_closest, n, 64, [fx.geom, fx.table, dev_ptr(d_rays), dev_ptr(d_hits), C.c_uint32(n), dev_ptr(d_payload)])
+    t.cuda.synchronize()
+    prim = ctx.hits_to_host(d_hits)["primID"]
+    colours = np.array([[255, 0], [0, 255], [255, 255], [0, 0]], np.uint8)  # intersectCircle's payload colours; last = miss
+    img = np.zeros((n, 4), np.uint8)
+    img[:, :2] = colours[np.where(prim == api.INVALID, 3, prim)]
+    img[:, 3] = 255
+    assert (prim != api.INVALID).sum() > 3 * 5000  # three discs of radius 0.1 on a 512 x 512 unit square: ~8200 pixels each
+    G._check(img, "CustomIntersection")
+    fx.close()
+
+
+def test_scene_intersection_and_multi_level_images_from_the_gpu(ctx):
+    fx = CircleFixture(ctx, z=1.0, wide_stride=True)
+    tris = ctx.build(to_dev(ctx, SCENE_TRIANGLES), to_dev(ctx, np.arange(9, dtype=np.uint32).reshape(3, 3)))
+    srt = lambda dy: [0, 0, 1, 0, 1, 1, 1, 0, dy, 0, 0, 0]
+    mid = ctx.build_scene([fx.geom, tris], np.array([srt(0.05), srt(-0.05)], np.float32), frame_type=api.FRAME_SRT)
+    img, counts, inst0, inst1 = scene_all_hits_image(ctx, fx, mid)
+    assert (inst1[counts > 0, 0] == api.INVALID).all()  # one level: only instanceIDs[0] is set
+    G._check(img, "SceneIntersection")
+
+    top = ctx.build_scene([mid, mid], np.array([srt(0.12), srt(-0.12)], np.float32), frame_type=api.FRAME_SRT,
+                          instance_types=[api.INSTANCE_SCENE, api.INSTANCE_SCENE])
+    img, counts, inst0, inst1 = scene_all_hits_image(ctx, fx, top)
+    hit = counts > 0
+    assert hit.any() and (inst0[hit, 0] <= 1).all() and (inst1[hit, 0] <= 1).all()  # top-level instance, then the one inside it
+    G._check(img, "SceneIntersectionMlas")
+    top.destroy()
+    mid.destroy()
+    tris.destroy()
+    fx.close()
