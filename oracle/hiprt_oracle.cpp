@@ -21,6 +21,7 @@
 #include <deque>
 #include <limits>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include <hiprt/hiprt_b200_layout.h>
@@ -683,7 +684,7 @@ hiprtHit traceClosest( const BvhView& bvh, const hiprtRay& inRay, int tieMode, u
 				node = res[0];
 			else
 			{
-				++g_fruitlessBoxVisits;
+				if ( boxVisits ) ++g_fruitlessBoxVisits; // statistic runs are single-threaded (they pass counters)
 				node = stack.back();
 				stack.pop_back();
 			}
@@ -1122,6 +1123,40 @@ hiprtHit traceSceneClosest( const SceneObj& s, const hiprtRay& worldRay, uint32_
 
 // =================================================================================================
 // C interface (ctypes)
+// hiprtHit leaves the deeper instance ids, and uv / normal of a miss, uninitialised (as the reference's does): give the words a
+// fixed value so that two runs of the oracle compare equal byte for byte.
+static hiprtHit canonical( hiprtHit h, bool scene )
+{
+	if ( !scene ) h.instanceIDs[0] = InvalidValue;
+	for ( uint32_t l = 1; l < hiprtMaxInstanceLevels; ++l )
+		h.instanceIDs[l] = InvalidValue;
+	if ( !h.hasHit() ) h.uv = { 0.0f, 0.0f }, h.normal = { 0.0f, 0.0f, 0.0f };
+	return h;
+}
+
+// Rays are independent: the plain trace entry points split them over the host's cores (test infrastructure only; the per-ray
+// arithmetic is untouched, so results do not depend on the thread count).
+template <typename F>
+static void forEachRay( uint32_t n, F&& body )
+{
+	const uint32_t threads = std::max( 1u, std::min( std::thread::hardware_concurrency(), n / 512u ) );
+	if ( threads <= 1 )
+	{
+		for ( uint32_t i = 0; i < n; ++i )
+			body( i );
+		return;
+	}
+	std::vector<std::thread> pool;
+	const uint32_t			 chunk = ( n + threads - 1 ) / threads;
+	for ( uint32_t t = 0; t < threads; ++t )
+		pool.emplace_back( [&, t] {
+			for ( uint32_t i = t * chunk, e = std::min( n, ( t + 1 ) * chunk ); i < e; ++i )
+				body( i );
+		} );
+	for ( std::thread& th : pool )
+		th.join();
+}
+
 extern "C" {
 
 // Pair triangles of an indexed mesh; pairsOut holds 2*triCount uint32. Returns the pair count.
@@ -1250,10 +1285,15 @@ void orc_geometry_trace( void* h, const hiprtRay* rays, uint32_t n, hiprtHit* hi
 {
 	Geometry& g = *static_cast<Geometry*>( h );
 	BvhView	  v{ g.wide.boxes.data(), g.leaves.data() };
-	uint32_t  bv = 0, lv = 0;
+	if ( !visits )
+	{
+		forEachRay( n, [&]( uint32_t i ) { hits[i] = canonical( traceClosest( v, rays[i], tieMode, nullptr, nullptr ), false ); } );
+		return;
+	}
+	uint32_t bv = 0, lv = 0;
 	for ( uint32_t i = 0; i < n; ++i )
-		hits[i] = traceClosest( v, rays[i], tieMode, &bv, &lv );
-	if ( visits ) visits[0] = bv, visits[1] = lv;
+		hits[i] = canonical( traceClosest( v, rays[i], tieMode, &bv, &lv ), false );
+	visits[0] = bv, visits[1] = lv;
 }
 
 // Key-frame interpolation for the motion-blur tests. frames: hiprtFrameSRT rows (12 floats: axis-angle rotation, scale, translation,
@@ -1513,8 +1553,7 @@ void orc_scene_set_inv_matrices( void* h, const float* invMatrices )
 void orc_scene_trace( void* h, const hiprtRay* rays, uint32_t n, hiprtHit* hits, uint32_t rayMask, int tieMode )
 {
 	SceneObj& s = *static_cast<SceneObj*>( h );
-	for ( uint32_t i = 0; i < n; ++i )
-		hits[i] = traceSceneClosest( s, rays[i], rayMask, tieMode );
+	forEachRay( n, [&]( uint32_t i ) { hits[i] = canonical( traceSceneClosest( s, rays[i], rayMask, tieMode ), true ); } );
 }
 
 } // extern "C"

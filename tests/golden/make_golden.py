@@ -99,16 +99,19 @@ def main():
     v, shapes = parse_obj(os.path.join(REF, "test/common/meshes/cornellbox/cornellBox.obj"))
     out = {"vertices": v, "shape_count": np.array(len(shapes))}
     # diffuse colour per face (cornellBox.mtl, Kd): what PrimaryRayKernel<VisualizeColor> paints (PrimaryRayKernel.h:43-56)
-    kd, name = {}, None
+    kd, ke, name = {}, {}, None
     for line in open(os.path.join(REF, "test/common/meshes/cornellbox/cornellBox.mtl")):
         q = line.split()
         if q and q[0] == "newmtl":
             name = q[1]
         elif q and q[0] == "Kd":
             kd[name] = [float(x) for x in q[1:4]]
+        elif q and q[0] == "Ke":
+            ke[name] = [float(x) for x in q[1:4]]  # emission: Material::light() (test/shared.h:75) = "is an area light"
     for i, s in enumerate(shapes):
         out[f"tris_{i}"] = np.array(s["tris"], np.uint32)
         out[f"diffuse_{i}"] = np.array([kd[m] for m in s["mats"]], np.float32)
+        out[f"emission_{i}"] = np.array([ke[m] for m in s["mats"]], np.float32)
         print("shape", i, s["name"], len(s["tris"]), sorted(set(s["mats"])))
     np.savez_compressed(os.path.join(HERE, "cornell_obj.npz"), **out)
 

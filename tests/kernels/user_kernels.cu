@@ -162,3 +162,91 @@ extern "C" __global__ void transformQueryKernel( hiprtScene scene, uint32_t inst
 	const float3   pw2 = hiprtPointObjectToWorld( in[i], scene, ids, time );
 	if ( pw2.x != pw.x || pw2.y != pw.y || pw2.z != pw.z ) out[4 * i + 0] = make_float3( 1e30f, 1e30f, 1e30f );
 }
+
+// ---- Monte-Carlo kernels for the golden-image tests (tests/test_gpu_golden.py). The random numbers are this file's own
+// (a PCG output function over an LCG state): the pictures are compared statistically, not sample by sample.
+__device__ float uniform01( uint32_t& state )
+{
+	state	   = state * 747796405u + 2891336453u;
+	uint32_t w = ( ( state >> ( ( state >> 28u ) + 4u ) ) ^ state ) * 277803737u;
+	w		   = ( w >> 22u ) ^ w;
+	return float( w >> 8 ) * ( 1.0f / 16777216.0f );
+}
+
+__device__ float3 unit( float3 v )
+{
+	const float s = rsqrtf( v.x * v.x + v.y * v.y + v.z * v.z );
+	return make_float3( v.x * s, v.y * s, v.z * s );
+}
+
+// Ambient occlusion as the reference's AoRayKernel renders it (test/kernels/AoRayKernel.h:40-131): a pinhole camera at `eye`
+// looking down -z (sensor 0.024 high, y down), `spp` primary closest-hit rays per pixel with one random offset for x and y,
+// from every hit that is not on an emissive instance `aoSamples` cosine-weighted any-hit rays of length `aoRadius` starting at
+// 99 % of the hit distance; unoccluded[pixel] counts the rays that escape. Instance frames are taken to be the identity
+// (hit.normal is used as the world-space normal).
+extern "C" __global__ void aoKernel(
+	hiprtScene scene, uint32_t width, uint32_t height, float eyeX, float eyeY, float eyeZ, float focal, uint32_t spp, uint32_t aoSamples,
+	float aoRadius, uint32_t emissiveInstances, uint32_t* unoccluded )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= width * height ) return;
+	const uint32_t x = i % width, y = i / width;
+	uint32_t	   rng = i * 9781u + 0x68bc21ebu;
+	uniform01( rng );
+	uint32_t	   count = 0;
+	const float	   sensorH = 0.024f, sensorW = 0.024f * ( float( width ) / float( height ) );
+	for ( uint32_t p = 0; p < spp; ++p )
+	{
+		const float offset = uniform01( rng );
+		hiprtRay	ray;
+		ray.origin	  = make_float3( eyeX, eyeY, eyeZ );
+		ray.direction = unit( make_float3(
+			( ( float( x ) + offset ) / float( width ) - 0.5f ) * sensorW, -( ( float( y ) + offset ) / float( height ) - 0.5f ) * sensorH, -focal ) );
+		hiprtSceneTraversalClosest tr( scene, ray );
+		const hiprtHit			   hit = tr.getNextHit();
+		if ( !hit.hasHit() || ( ( emissiveInstances >> hit.instanceID ) & 1u ) ) continue;
+		float3 n = hit.normal;
+		if ( ray.direction.x * n.x + ray.direction.y * n.y + ray.direction.z * n.z > 0.0f ) n = make_float3( -n.x, -n.y, -n.z );
+		n = unit( n );
+		// orthonormal basis around n
+		const float3 a = fabsf( n.x ) > 0.5f ? make_float3( 0.0f, 1.0f, 0.0f ) : make_float3( 1.0f, 0.0f, 0.0f );
+		const float3 t = unit( make_float3( a.y * n.z - a.z * n.y, a.z * n.x - a.x * n.z, a.x * n.y - a.y * n.x ) );
+		const float3 b = make_float3( n.y * t.z - n.z * t.y, n.z * t.x - n.x * t.z, n.x * t.y - n.y * t.x );
+		const float	 s = hit.t * 0.99f;
+		hiprtRay	 ao;
+		ao.origin = make_float3( ray.origin.x + s * ray.direction.x, ray.origin.y + s * ray.direction.y, ray.origin.z + s * ray.direction.z );
+		ao.maxT	  = aoRadius;
+		for ( uint32_t k = 0; k < aoSamples; ++k )
+		{
+			const float phi = 6.28318530718f * uniform01( rng ), r2 = uniform01( rng );
+			const float r = sqrtf( r2 ), h = sqrtf( 1.0f - r2 ), cu = r * cosf( phi ), cv = r * sinf( phi );
+			ao.direction = unit( make_float3( cu * t.x + cv * b.x + h * n.x, cu * t.y + cv * b.y + h * n.y, cu * t.z + cv * b.z + h * n.z ) );
+			hiprtSceneTraversalAnyHit shadow( scene, ao );
+			if ( !shadow.getNextHit().hasHit() ) ++count;
+		}
+	}
+	unoccluded[i] = count;
+}
+
+// The reference's MotionBlurSlerpKernel (HiprtTestKernel.h:361-405): one jittered ray per pixel from (0, 0, 5) through a
+// 2 x 2 * 1.576494 window at z = 0, traced at `samples` random times; hits[pixel] counts the times at which it hits.
+extern "C" __global__ void motionSamplesKernel( hiprtScene scene, hiprtFuncTable table, uint32_t width, uint32_t height, uint32_t samples, uint32_t* hits )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= width * height ) return;
+	uint32_t rng = i * 2654435761u + 12345u;
+	uniform01( rng );
+	const float dx = 2.0f * ( float( i % width ) + uniform01( rng ) ) / float( width ) - 1.0f;
+	const float dy = 2.0f * ( float( i / width ) + uniform01( rng ) ) / float( height ) - 1.0f;
+	hiprtRay	ray;
+	ray.origin	  = make_float3( 0.0f, 0.0f, 5.0f );
+	ray.direction = unit( make_float3( dx * 1.576494f, dy * 1.576494f, -5.0f ) );
+	uint32_t count = 0;
+	for ( uint32_t s = 0; s < samples; ++s )
+	{
+		const float				   time = uniform01( rng );
+		hiprtSceneTraversalClosest tr( scene, ray, hiprtFullRayMask, hiprtTraversalHintDefault, nullptr, table, 0, time );
+		if ( tr.getNextHit().hasHit() ) ++count;
+	}
+	hits[i] = count;
+}

@@ -27,6 +27,18 @@ def ctx():
     c.close()
 
 
+_KERNELS = {}
+
+
+def kernels(ctx, func_names, name_sets=None, num_geom_types=0):
+    """hiprtBuildTraceKernels once per (functions, function-table layout) for the whole module: every call compiles the test
+    kernels' source with NVRTC."""
+    key = (tuple(func_names), tuple(name_sets or ()), num_geom_types)
+    if key not in _KERNELS:
+        _KERNELS[key] = build_kernels(ctx, list(func_names), name_sets, num_geom_types=num_geom_types)
+    return _KERNELS[key]
+
+
 def gpu_obj_hits(ctx, srt_frame=None, flags=api.FAST_BUILD, masks=None, compact=False):
     d = np.load(H.os.path.join(H.GOLDEN, "cornell_obj.npz"))
     n = int(d["shape_count"])
@@ -106,7 +118,7 @@ def test_minimum_cornell_box_built_compacted_reloaded_and_batch_built(ctx, tmp_p
     verts, _, _ = H.cornell_box()
     d_verts = to_dev(ctx, verts)
     d_idx = to_dev(ctx, np.arange(96, dtype=np.uint32).reshape(-1, 3))
-    (fn_all,) = build_kernels(ctx, ["allHitsKernel"])
+    fn_all, _ = kernels(ctx, ("allHitsKernel", "aoKernel"))
     rays = H.cornell_rays()
     d_rays, n = ctx.rays_to_device(rays), len(rays)
 
@@ -209,7 +221,7 @@ class CircleFixture:
         self.temp = ctx.alloc_temp(ctx.geometry_temp_size(self.inp))
         self.geom = ctx.create_geometry(self.inp)
         ctx.build_geometry(self.inp, self.geom, self.temp)
-        self.fn_scene, self.fn_closest = build_kernels(ctx, ["sceneAllHitsKernel", "customKernel"], [("intersectCircle", None)], num_geom_types=1)
+        self.fn_scene, self.fn_closest = kernels(ctx, ("sceneAllHitsKernel", "customKernel"), [("intersectCircle", None)], num_geom_types=1)
         self.centres = to_dev(ctx, np.array([0.25, 0.5, 0.75], np.float32))
         self.table = C.c_void_p()
         ctx._check(api.lib().hiprtCreateFuncTable(ctx.h, 1, 1, C.byref(self.table)), "hiprtCreateFuncTable")
@@ -282,3 +294,72 @@ def test_scene_intersection_and_multi_level_images_from_the_gpu(ctx):
     mid.destroy()
     tris.destroy()
     fx.close()
+
+
+def test_ao_ray_cornell_box_image_from_the_gpu(ctx):
+    """test/main.cpp:426-441 + AoRayKernel.h: the workload shape of the headline metric (primary closest-hit + incoherent
+    any-hit AO rays) rendered by a user kernel through hiprtSceneTraversalClosest / AnyHit. 128 x 32 rays per pixel against the
+    reference's 512 x 32: a pixel's standard error is <= 2 grey levels, the image tolerance (10) is 5 sigma."""
+    t = ctx.torch
+    d = np.load(H.os.path.join(H.GOLDEN, "cornell_obj.npz"))
+    n = int(d["shape_count"])
+    d_verts = to_dev(ctx, d["vertices"])
+    geoms = [ctx.build(d_verts, to_dev(ctx, d[f"tris_{k}"])) for k in range(n)]
+    scene = ctx.build_scene(geoms)
+    emissive = sum(1 << k for k in range(n) if d[f"emission_{k}"].sum() > 0)
+    assert emissive == 1  # the area light is shape 0
+    _, fn = kernels(ctx, ("allHitsKernel", "aoKernel"))
+    w = h = 512
+    spp, ao_samples = 128, 32
+    focal = np.float32(np.float32(0.024) / np.float32(2.0 * np.tan(np.float32(45.0 * np.pi / 180.0) / np.float32(2.0))))
+    d_out = t.zeros(w * h, dtype=t.int32, device=ctx.device)
+    Launcher().launch(fn, w * h, 64, [scene.h, C.c_uint32(w), C.c_uint32(h), C.c_float(0.0), C.c_float(2.5), C.c_float(5.8), C.c_float(float(focal)),
+                                      C.c_uint32(spp), C.c_uint32(ao_samples), C.c_float(1.4), C.c_uint32(emissive), dev_ptr(d_out)])
+    t.cuda.synchronize()
+    grey = (d_out.cpu().numpy().astype(np.float64) / (spp * ao_samples) * 255.0).astype(np.uint8)
+    img = np.zeros((w * h, 4), np.uint8)
+    img[:, :3] = grey[:, None]
+    img[:, 3] = 255
+    golden = H.load_golden_image("AoRayCornellBox").reshape(-1, 4)
+    bias = (grey.astype(np.int64) - golden[:, 0].astype(np.int64)).mean()
+    assert abs(bias) < 0.4, bias
+    G._check(img, "AoRayCornellBox")
+    scene.destroy()
+    for g in geoms:
+        g.destroy()
+
+
+def test_motion_blur_slerp_image_from_the_gpu(ctx):
+    """test/main.cpp:2375-2513 + MotionBlurSlerpKernel: one custom sphere (geomType 1 of 2) instanced with two hiprtFrameMatrix
+    key frames, the identity at time 0 and diag(-1, -1, 1) at time 1 -- half a turn about z that only the decomposition into a
+    rotation + slerp renders as an arc (a linear blend of the matrices would collapse the sphere onto the axis)."""
+    t = ctx.torch
+    box = np.array([[-1.5, -0.5, -0.5, -0.5, 0.5, 0.5]], np.float32)
+    inp = ctx.aabb_input(to_dev(ctx, box), geom_type=1)
+    temp = ctx.alloc_temp(ctx.geometry_temp_size(inp))
+    geom = ctx.create_geometry(inp)
+    ctx.build_geometry(inp, geom, temp)
+    m0, m1 = np.zeros(16, np.float32), np.zeros(16, np.float32)  # hiprtFrameMatrix: float matrix[3][4], float time, 3 pad
+    m0[[0, 5, 10]] = 1.0
+    m1[[0, 5]], m1[10], m1[12] = -1.0, 1.0, 1.0
+    scene = ctx.build_scene([geom], np.stack([m0, m1]), frame_type=api.FRAME_MATRIX, transform_headers=np.array([[0, 2]], np.uint32))
+    (fn,) = kernels(ctx, ("motionSamplesKernel",), [(None, None), ("intersectSphere", None)], num_geom_types=2)
+    spheres = to_dev(ctx, np.array([[-1.0, 0.0, 0.0, 0.5]], np.float32))
+    table = C.c_void_p()
+    ctx._check(api.lib().hiprtCreateFuncTable(ctx.h, 2, 1, C.byref(table)), "hiprtCreateFuncTable")
+    ctx._check(api.lib().hiprtSetFuncTable(ctx.h, table, 1, 0, api.FuncDataSet(spheres.data_ptr(), None)), "hiprtSetFuncTable")
+    w = h = 512
+    samples = 8192
+    d_out = t.zeros(w * h, dtype=t.int32, device=ctx.device)
+    Launcher().launch(fn, w * h, 64, [scene.h, table, C.c_uint32(w), C.c_uint32(h), C.c_uint32(samples), dev_ptr(d_out)])
+    t.cuda.synchronize()
+    frac = (d_out.cpu().numpy().astype(np.float32) / np.float32(samples))[:, None]
+    colour = frac * np.array([0.9, 0.1, 0.1], np.float32) + (np.float32(1.0) - frac) * np.float32(0.1)
+    img = np.zeros((w * h, 4), np.uint8)
+    img[:, :3] = (np.power(colour, np.float32(1.0 / 2.2)) * np.float32(255)).astype(np.uint8)
+    img[:, 3] = 255
+    assert 0.05 < (frac > 0).mean() < 0.6
+    G._check(img, "MotionBlurSlerp")
+    api.lib().hiprtDestroyFuncTable(ctx.h, table)
+    scene.destroy()
+    ctx.destroy_geometry(geom)
