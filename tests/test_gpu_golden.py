@@ -93,10 +93,16 @@ def test_ray_mask_cornell_obj_image_from_the_gpu(ctx):
     G._check(G._colour_image(gpu_obj_hits(ctx, masks=masks)), "RayMaskCornellBox")
 
 
+def same_hits(a, b):
+    """Bit-identical hit records (a miss leaves uv / normal unwritten, as in the reference: only its primID is compared)."""
+    hit = a["primID"] != api.INVALID
+    return np.array_equal(a["primID"], b["primID"]) and all(a[f][hit].tobytes() == b[f][hit].tobytes() for f in ("t", "uv", "normal"))
+
+
 def test_compacted_geometries_and_scene_trace_like_the_originals(ctx):
     plain = gpu_obj_hits(ctx)
     compacted = gpu_obj_hits(ctx, compact=True)
-    assert plain.tobytes() == compacted.tobytes()
+    assert same_hits(plain, compacted) and np.array_equal(plain["instanceIDs"][:, 0], compacted["instanceIDs"][:, 0])
     G._check(G._colour_image(compacted), "PrimaryRayCornellBox")
 
 
@@ -135,13 +141,13 @@ def test_minimum_cornell_box_built_compacted_reloaded_and_batch_built(ctx, tmp_p
     ctx.save_geometry(geom.h, path)
     loaded = ctx.load_geometry(path)
     check(loaded, "BvhIoApi")
-    assert ctx.hits_to_host(ctx.trace(loaded, d_rays)).tobytes() == closest.tobytes()
+    assert same_hits(ctx.hits_to_host(ctx.trace(loaded, d_rays)), closest)
     ctx.destroy_geometry(loaded)
 
     geom.h = ctx.compact_geometry(geom.h)
     assert int(geom.header()["size"]) == 64 + int(geom.header()["boxNodeCount"]) * 128 + int(geom.header()["primNodeCount"]) * 64
     check(geom.h, "MinimumCornellBox")
-    assert ctx.hits_to_host(ctx.trace(geom, d_rays)).tobytes() == closest.tobytes()
+    assert same_hits(ctx.hits_to_host(ctx.trace(geom, d_rays)), closest)
     geom.destroy()
 
     batch = ctx.build_geometries([ctx.mesh_input(d_verts, d_idx)], batch_max=512)
