@@ -171,6 +171,7 @@ SIGNATURES = {
     "hiprtB200TraceSceneHost": [_vp, _vp, _vp, _u32, _vp, C.c_int, _u32, _vp],
     "hiprtB200GetTempLayout": [_sz, _sz, _P(_sz), _u32],
     "hiprtB200GetDeviceHeaders": [_P(_P(C.c_char_p)), _P(_P(C.c_char_p))],
+    "hiprtB200LinkTraceKernels": [C.c_int, C.c_int, C.c_char_p, C.c_char_p, _sz, _u32, _u32, _P(FuncNameSet), _vp, _P(_sz), C.c_char_p, _sz],
     "hiprtB200GetLastErrorString": [_vp],
     "hiprtB200CopyToHost": [_vp, _vp, _vp, _sz],
     "hiprtB200EnableBuildProfile": [_vp, C.c_int],

@@ -921,10 +921,27 @@ hiprtError hiprtBuildTraceKernels(
 }
 
 hiprtError hiprtBuildTraceKernelsFromBitcode(
-	hiprtContext context, uint32_t, const char**, const char*, const char*, size_t, uint32_t, uint32_t, hiprtFuncNameSet*, hiprtApiFunction*, bool )
+	hiprtContext	  context,
+	uint32_t		  numFunctions,
+	const char**	  funcNames,
+	const char*		  moduleName,
+	const char*		  bitcodeBinary,
+	size_t			  bitcodeBinarySize,
+	uint32_t		  numGeomTypes,
+	uint32_t		  numRayTypes,
+	hiprtFuncNameSet* funcNameSets,
+	hiprtApiFunction* functionsOut,
+	bool			  cache )
 {
-	// AMD bitcode linking has no CUDA counterpart here; user kernels go through hiprtBuildTraceKernels.
-	return context ? hiprtErrorNotImplemented : hiprtErrorInvalidParameter;
+	if ( !context || numFunctions == 0 || funcNames == nullptr || bitcodeBinary == nullptr || bitcodeBinarySize == 0 || functionsOut == nullptr )
+		return hiprtErrorInvalidParameter;
+	(void)cache; // linked modules are cached in memory
+	return guarded( context, [&] {
+		Context* c = ctx( context );
+		compiler::buildTraceKernelsFromBitcode(
+			c->ccMajor(), c->ccMinor(), numFunctions, funcNames, moduleName ? moduleName : "hiprt_user_module", bitcodeBinary, bitcodeBinarySize,
+			numGeomTypes, numRayTypes, funcNameSets, functionsOut );
+	} );
 }
 
 hiprtError hiprtSetCacheDirPath( hiprtContext context, const char* path )
@@ -1027,6 +1044,39 @@ hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount,
 }
 
 uint32_t hiprtB200GetDeviceHeaders( const char*** namesOut, const char*** sourcesOut ) { return compiler::deviceHeaders( namesOut, sourcesOut ); }
+
+hiprtError hiprtB200LinkTraceKernels(
+	int				  ccMajor,
+	int				  ccMinor,
+	const char*		  moduleName,
+	const char*		  bitcodeBinary,
+	size_t			  bitcodeBinarySize,
+	uint32_t		  numGeomTypes,
+	uint32_t		  numRayTypes,
+	hiprtFuncNameSet* funcNameSets,
+	void*			  cubinOut,
+	size_t*			  cubinSizeInOut,
+	char*			  logOut,
+	size_t			  logCapacity )
+{
+	if ( !bitcodeBinary || bitcodeBinarySize == 0 || !cubinSizeInOut ) return hiprtErrorInvalidParameter;
+	try
+	{
+		const std::vector<char> cubin = compiler::linkTraceKernels(
+			ccMajor, ccMinor, bitcodeBinary, bitcodeBinarySize, moduleName ? moduleName : "hiprt_user_module", numGeomTypes, numRayTypes, funcNameSets );
+		const size_t capacity = *cubinSizeInOut;
+		*cubinSizeInOut		  = cubin.size();
+		if ( cubinOut == nullptr ) return hiprtSuccess; // size query
+		if ( capacity < cubin.size() ) return hiprtErrorInvalidParameter;
+		memcpy( cubinOut, cubin.data(), cubin.size() );
+		return hiprtSuccess;
+	}
+	catch ( const std::exception& e )
+	{
+		if ( logOut && logCapacity ) snprintf( logOut, logCapacity, "%s", e.what() );
+		return hiprtErrorInternal;
+	}
+}
 
 const char* hiprtB200GetLastErrorString( hiprtContext context ) { return context ? ctx( context )->lastError() : ""; }
 

@@ -7,6 +7,7 @@
 #include <hiprt/hiprt_types.h>
 
 #include <stdexcept>
+#include <vector>
 
 namespace hiprt
 {
@@ -36,6 +37,26 @@ void buildTraceKernels(
 	hiprtFuncNameSet* funcNameSets,
 	hiprtApiFunction* functionsOut,
 	hiprtApiModule*	  moduleOut );
+
+// Offline-compiled user kernels (reference: Compiler::buildKernelsFromBitcode, Compiler.cpp:338-470): `bitcode` is the caller's
+// relocatable device code for this architecture (nvcc -dc: cubin, PTX, fatbin or LTO-IR) built against <hiprt/hiprt_device.h>
+// with intersectFunc / filterFunc left undefined; they are generated here from the function-name table, compiled as relocatable
+// code and linked in with nvJitLink. linkTraceKernels is the device-independent half (needs no GPU): the linked cubin.
+std::vector<char> linkTraceKernels(
+	int ccMajor, int ccMinor, const char* bitcode, size_t bitcodeSize, const char* moduleName, uint32_t numGeomTypes, uint32_t numRayTypes, hiprtFuncNameSet* funcNameSets );
+
+void buildTraceKernelsFromBitcode(
+	int				  ccMajor,
+	int				  ccMinor,
+	uint32_t		  numFunctions,
+	const char**	  funcNames,
+	const char*		  moduleName,
+	const char*		  bitcode,
+	size_t			  bitcodeSize,
+	uint32_t		  numGeomTypes,
+	uint32_t		  numRayTypes,
+	hiprtFuncNameSet* funcNameSets,
+	hiprtApiFunction* functionsOut );
 
 // embedded copy of include/hiprt/*.h needed by device code (generated at build time)
 uint32_t deviceHeaders( const char*** namesOut, const char*** sourcesOut );

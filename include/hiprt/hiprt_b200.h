@@ -78,6 +78,26 @@ HIPRT_API hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTria
 // for callers that NVRTC-compile their own kernels. Returns the number of headers.
 HIPRT_API uint32_t hiprtB200GetDeviceHeaders( const char*** namesOut, const char*** sourcesOut );
 
+// The device-independent half of hiprtBuildTraceKernelsFromBitcode (reference: Compiler::buildKernelsFromBitcode,
+// hiprt/impl/Compiler.cpp:338-470), usable without a GPU or a context: generates the intersectFunc / filterFunc dispatchers for
+// the function-name table, compiles them as relocatable code for sm_<ccMajor><ccMinor>[a] and links them with the caller's
+// relocatable device code (nvcc -dc against <hiprt/hiprt_device.h>: cubin, PTX, fatbin or LTO-IR) through nvJitLink. Writes the
+// linked cubin (cuModuleLoadData-ready) to cubinOut; *cubinSizeInOut is the capacity on entry and the cubin size on return
+// (cubinOut == NULL: size query). On failure the compiler / linker log is copied to logOut.
+HIPRT_API hiprtError hiprtB200LinkTraceKernels(
+	int				  ccMajor,
+	int				  ccMinor,
+	const char*		  moduleName,
+	const char*		  bitcodeBinary,
+	size_t			  bitcodeBinarySize,
+	uint32_t		  numGeomTypes,
+	uint32_t		  numRayTypes,
+	hiprtFuncNameSet* funcNameSets,
+	void*			  cubinOut,
+	size_t*			  cubinSizeInOut,
+	char*			  logOut,
+	size_t			  logCapacity );
+
 HIPRT_API const char* hiprtB200GetLastErrorString( hiprtContext context );
 
 // Per-phase timing of the most recent build on this context (CUDA events on the build stream;
