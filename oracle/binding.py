@@ -52,6 +52,10 @@ INVALID = 0xFFFFFFFF
 FLT_MAX = np.float32(3.402823466e38)
 
 
+# int fn(const hiprtRay* ray, uint32_t geomType, void* user, hiprtHit* hit): the oracle's stand-in for a hiprtFuncTable entry
+CUSTOM_INTERSECT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p)
+
+
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
     src = os.path.join(_HERE, "hiprt_oracle.cpp")
@@ -96,6 +100,11 @@ def lib():
         L.orc_scene_read.argtypes = [vp, i32, vp]
         L.orc_scene_trace.argtypes = [vp, vp, u32, vp, u32, i32]
         L.orc_scene_set_inv_matrices.argtypes = [vp, vp]
+        L.orc_scene_create_multilevel.argtypes = [vp, u32, vp, vp, i32, vp, u32, vp]
+        L.orc_scene_create_multilevel.restype = vp
+        L.orc_geometry_create_aabbs.argtypes = [vp, u32, u32, u32]
+        L.orc_geometry_create_aabbs.restype = vp
+        L.orc_trace_general.argtypes = [vp, i32, vp, u32, u32, i32, CUSTOM_INTERSECT_FN, vp, u32, vp, vp]
         _lib = L
     return _lib
 
@@ -201,18 +210,18 @@ class Geometry:
         return counts, prims, ts
 
 
-def motion_pose(srt_frames, time, ray=None):
+def motion_pose(srt_frames, time, ray=None, frame_type=0):
     """Key-frame interpolation of the oracle: (3x4 object->world matrix of the pose at `time`, world ray carried into the
-    instance or None). srt_frames: float32 [n, 12] hiprtFrameSRT rows."""
-    f = np.ascontiguousarray(srt_frames, np.float32).reshape(-1, 12)
+    instance or None). srt_frames: float32 [n, 12] hiprtFrameSRT rows (frame_type 0) or [n, 16] hiprtFrameMatrix rows (1)."""
+    f = np.ascontiguousarray(srt_frames, np.float32).reshape(-1, 16 if frame_type == 1 else 12)
     m = np.zeros(12, np.float32)
     rin = rout = None
     if ray is not None:
         rin = np.ascontiguousarray(ray, RAY_DTYPE).reshape(1)
         rout = np.zeros(1, RAY_DTYPE)
     L = lib()
-    L.orc_motion_pose.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.orc_motion_pose(_p(f), len(f), C.c_float(time), _p(m), _p(rin), _p(rout))
+    L.orc_motion_pose_typed.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_motion_pose_typed(_p(f), len(f), frame_type, C.c_float(time), _p(m), _p(rin), _p(rout))
     return m.reshape(3, 4), (None if rout is None else rout[0])
 
 
@@ -247,6 +256,53 @@ def canonicalize(box_nodes, leaves):
 INSTANCE_NODE_DTYPE = np.dtype([("invMatrix", "<f4", (3, 4)), ("pointer", "<u8"), ("mask", "<u4"), ("bits", "<u4")])
 
 
+class AabbGeometry:
+    """Custom primitives: an AABB list (float32 [n, 6] min xyz, max xyz) built by the oracle's LBVH pipeline with custom leaves.
+    Hits come from the intersection function passed to trace_general."""
+
+    def __init__(self, aabbs, geom_type=0):
+        self.aabbs = np.ascontiguousarray(aabbs, np.float32).reshape(-1, 6)
+        self.h = lib().orc_geometry_create_aabbs(_p(self.aabbs), len(self.aabbs), 24, geom_type)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                lib().orc_geometry_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def trace_general(obj, rays, intersect=None, ray_mask=0xFFFFFFFF, tie_mode=1, max_per_ray=0):
+    """Closest hit (max_per_ray == 0: HIT_DTYPE [n]) or every hit along each ray in visiting order (max_per_ray > 0:
+    (counts [n], HIT_DTYPE [n, max_per_ray])) through a Geometry, AabbGeometry or (multi-level) Scene. intersect(ray, geom_type,
+    prim_id) -> None or t is the custom-primitive intersection function: `ray` is a RAY_DTYPE record in the primitive's object
+    space."""
+    rays = np.ascontiguousarray(rays, RAY_DTYPE)
+    n = len(rays)
+
+    def callback(ray_ptr, geom_type, _user, hit_ptr):
+        ray = np.ctypeslib.as_array(C.cast(ray_ptr, C.POINTER(C.c_uint8)), (32,)).view(RAY_DTYPE)[0]
+        hit = np.ctypeslib.as_array(C.cast(hit_ptr, C.POINTER(C.c_uint8)), (48,)).view(HIT_DTYPE)
+        t = intersect(ray, geom_type, int(hit["primID"][0]))
+        if t is None:
+            return 0
+        hit["t"][0] = t
+        return 1
+
+    fn = CUSTOM_INTERSECT_FN(callback) if intersect is not None else C.cast(None, CUSTOM_INTERSECT_FN)
+    is_scene = int(isinstance(obj, Scene))
+    if max_per_ray == 0:
+        hits = np.zeros(n, HIT_DTYPE)
+        lib().orc_trace_general(obj.h, is_scene, _p(rays), n, ray_mask, tie_mode, fn, None, 0, None, _p(hits))
+        return hits
+    counts = np.zeros(n, np.uint32)
+    hits = np.zeros((n, max_per_ray), HIT_DTYPE)
+    hits["primID"] = INVALID
+    lib().orc_trace_general(obj.h, is_scene, _p(rays), n, ray_mask, tie_mode, fn, None, max_per_ray, _p(counts), _p(hits))
+    return counts, hits
+
+
 class Scene:
     """Two-level scene of the oracle: instances of oracle Geometry objects, one frame per instance
     (frame_type 0: hiprtFrameSRT rows of 12 floats, 1: hiprtFrameMatrix rows of 16 floats)."""
@@ -258,8 +314,10 @@ class Scene:
         self.frames = None if frames is None else np.ascontiguousarray(frames, np.float32).reshape(n, 16 if frame_type == 1 else 12)
         self.masks = None if masks is None else np.ascontiguousarray(masks, np.uint32)
         handles = (C.c_void_p * len(self.geometries))(*[g.h for g in self.geometries])
-        self.h = lib().orc_scene_create(handles, len(self.geometries), _p(self.geometry_of_instance), _p(self.frames), frame_type,
-                                        _p(self.masks), n)
+        # an entry of `geometries` may itself be a Scene: it is then instanced as hiprtInstanceTypeScene (multi-level instancing)
+        nested = np.array([isinstance(g, Scene) for g in self.geometries], np.uint32)
+        self.h = lib().orc_scene_create_multilevel(handles, len(self.geometries), _p(self.geometry_of_instance), _p(self.frames),
+                                                   frame_type, _p(self.masks), n, _p(nested))
 
     def __del__(self):
         try:

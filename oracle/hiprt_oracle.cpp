@@ -498,6 +498,7 @@ struct Geometry
 {
 	uint32_t					  primCount = 0;
 	uint32_t					  leafType	= TriangleType;
+	uint32_t					  geomType	= InvalidValue; // user geometry type of custom primitives (hiprtGeometryBuildInput::geomType)
 	std::vector<uint32_t>		  pairs;	 // 2 per primitive (triangle meshes)
 	std::vector<TrianglePairNode> primNodes; // per primitive, input order
 	std::vector<Box>			  primBoxes; // per primitive, input order
@@ -986,7 +987,8 @@ void frameInverseMatrix( const Frame& f, float out[3][4] )
 struct SceneObj
 {
 	uint32_t				  count = 0;
-	std::vector<Geometry*>	  geoms; // per instance
+	std::vector<Geometry*>	  geoms; // per instance (null when the instance is a scene)
+	std::vector<SceneObj*>	  scenes; // per instance: the nested scene of a hiprtInstanceTypeScene instance, else null
 	std::vector<Frame>		  frames;
 	std::vector<uint32_t>	  masks;
 	std::vector<Box>		  primBoxes, sortedBoxes;
@@ -999,9 +1001,10 @@ struct SceneObj
 	Box						  sceneBox;
 };
 
-Box instanceBox( const Geometry& g, const Frame& f )
+// (a geometry and a scene are bounded alike: through the child boxes of their root node, InstanceList.h:104-121)
+Box instanceBox( const Wide& wide, const Frame& f )
 {
-	const Box4Node& root = g.wide.boxes[0];
+	const Box4Node& root = wide.boxes[0];
 	Box				out	 = emptyBox();
 	for ( uint32_t c = 0; c < root.childCount; ++c )
 	{
@@ -1118,6 +1121,138 @@ hiprtHit traceSceneClosest( const SceneObj& s, const hiprtRay& worldRay, uint32_
 		node = pop();
 	}
 	return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// General traversal: custom primitives through a caller-supplied intersection function (the oracle's stand-in for a
+// hiprtFuncTable entry, hiprt_device_impl.h:767-776), scenes instanced in scenes (instance stack, hiprt_device_impl.h:1105-1193),
+// and the any-hit iterator drained to completion (every hit, in visiting order) next to the closest-hit query.
+// The function gets the ray in the primitive's object space and hit.primID set; it fills hit.t (and uv / normal) and returns
+// non-zero for a hit.
+typedef int ( *CustomIntersectFn )( const hiprtRay* ray, uint32_t geomType, void* user, hiprtHit* hit );
+
+struct Walk
+{
+	bool				   closest;	 // false: collect every hit
+	int					   tieMode;
+	uint32_t			   rayMask;
+	CustomIntersectFn	   fn;
+	void*				   user;
+	hiprtHit			   best;
+	std::vector<hiprtHit>* all;
+	uint32_t			   ids[hiprtMaxInstanceLevels];
+
+	void report( hiprtHit h, uint32_t level, hiprtRay& ray, bool custom )
+	{
+		for ( uint32_t l = 0; l < hiprtMaxInstanceLevels; ++l )
+			h.instanceIDs[l] = l < level ? ids[l] : InvalidValue;
+		if ( !closest )
+		{
+			all->push_back( h );
+			return;
+		}
+		bool better = custom || tieMode == 0 || !best.hasHit() || h.t < best.t; // (a custom hit always replaces: :767-776, 838-842)
+		if ( !better && h.t == best.t )
+		{
+			better = h.primID < best.primID;
+			for ( uint32_t l = 0; l < hiprtMaxInstanceLevels; ++l )
+				if ( h.instanceIDs[l] != best.instanceIDs[l] )
+				{
+					better = h.instanceIDs[l] < best.instanceIDs[l];
+					break;
+				}
+		}
+		if ( better ) best = h, ray.maxT = h.t;
+	}
+};
+
+void walkGeometry( const Geometry& g, hiprtRay& ray, uint32_t level, Walk& w )
+{
+	const V3			  invD = mk( 1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z );
+	std::vector<uint32_t> stack{ InvalidValue };
+	uint32_t			  node = RootIndex;
+	while ( node != InvalidValue )
+	{
+		if ( isBoxIndex( node ) )
+		{
+			uint32_t res[4];
+			orderChildren( g.wide.boxes[nodeAddr( node )], ray.origin, invD, ray.maxT, res );
+			for ( int k = 3; k >= 1; --k )
+				if ( res[k] != InvalidValue ) stack.push_back( res[k] );
+			if ( res[0] != InvalidValue )
+			{
+				node = res[0];
+				continue;
+			}
+		}
+		else if ( g.leafType == TriangleType )
+		{
+			const TrianglePairNode& leaf = g.leaves[nodeAddr( node )];
+			hiprtHit				cand[2];
+			bool					ok[2];
+			for ( uint32_t which = 0; which < 2; ++which )
+				ok[which] = hitPairTriangle( leaf, which, ray, cand[which] );
+			if ( w.closest && w.tieMode == 0 )
+			{
+				// the reference's pair rule: the second triangle replaces the first only when strictly nearer
+				int pick = ok[0] ? 0 : -1;
+				if ( ok[1] && ( !ok[0] || cand[0].t > cand[1].t ) ) pick = 1;
+				if ( pick >= 0 ) w.report( cand[pick], level, ray, false );
+			}
+			else
+				for ( uint32_t which = 0; which < 2; ++which )
+					if ( ok[which] ) w.report( cand[which], level, ray, false );
+		}
+		else
+		{
+			hiprtHit h;
+			h.primID = g.customLeaves[nodeAddr( node )].primIndex;
+			if ( w.fn && w.fn( &ray, g.geomType, w.user, &h ) ) w.report( h, level, ray, true );
+		}
+		node = stack.back();
+		stack.pop_back();
+	}
+}
+
+void walkScene( const SceneObj& s, hiprtRay& ray, uint32_t level, Walk& w )
+{
+	std::vector<uint32_t> stack{ InvalidValue };
+	uint32_t			  node = RootIndex;
+	while ( node != InvalidValue )
+	{
+		if ( isBoxIndex( node ) )
+		{
+			const V3 invD = mk( 1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z );
+			uint32_t res[4];
+			orderChildren( s.wide.boxes[nodeAddr( node )], ray.origin, invD, ray.maxT, res );
+			for ( int k = 3; k >= 1; --k )
+				if ( res[k] != InvalidValue ) stack.push_back( res[k] );
+			if ( res[0] != InvalidValue )
+			{
+				node = res[0];
+				continue;
+			}
+		}
+		else
+		{
+			const uint32_t		addr = nodeAddr( node );
+			const InstanceNode& in	 = s.leaves[addr];
+			if ( ( in.mask & w.rayMask ) && level < hiprtMaxInstanceLevels )
+			{
+				hiprtRay inner = in.identity ? ray : toObjectSpace( in, ray );
+				inner.maxT	   = ray.maxT;
+				w.ids[level]   = in.primIndex;
+				const uint32_t k = s.leafGeom[addr];
+				if ( s.scenes[k] )
+					walkScene( *s.scenes[k], inner, level + 1, w );
+				else
+					walkGeometry( *s.geoms[k], inner, level + 1, w );
+				ray.maxT = inner.maxT; // the distance found inside carries over (t is invariant under the instance transform)
+			}
+		}
+		node = stack.back();
+		stack.pop_back();
+	}
 }
 } // namespace
 
@@ -1299,11 +1434,22 @@ void orc_geometry_trace( void* h, const hiprtRay* rays, uint32_t n, hiprtHit* hi
 // Key-frame interpolation for the motion-blur tests. frames: hiprtFrameSRT rows (12 floats: axis-angle rotation, scale, translation,
 // time, pad). matrixOut: 3x4 object -> world matrix of the interpolated pose (hiprt_device_impl.h:1980-2005);
 // rayOut: the world ray carried into the instance (Transform::transformRay: origin and origin + direction through the inverse).
+void orc_motion_pose_typed(
+	const float* keyFrames, uint32_t count, int frameType, float time, float* matrixOut, const hiprtRay* rayIn, hiprtRay* rayOut );
+
 void orc_motion_pose( const float* srtFrames, uint32_t count, float time, float* matrixOut, const hiprtRay* rayIn, hiprtRay* rayOut )
+{
+	orc_motion_pose_typed( srtFrames, count, 0, time, matrixOut, rayIn, rayOut );
+}
+
+// frameType 0: hiprtFrameSRT rows (12 floats), 1: hiprtFrameMatrix rows (16 floats: the matrix is decomposed into scale / shear /
+// rotation first, Transform.h:61-127, and the key frames are interpolated in that form)
+void orc_motion_pose_typed(
+	const float* keyFrames, uint32_t count, int frameType, float time, float* matrixOut, const hiprtRay* rayIn, hiprtRay* rayOut )
 {
 	std::vector<Frame> frames( count );
 	for ( uint32_t i = 0; i < count; ++i )
-		frames[i] = frameFromSRT( srtFrames + 12 * size_t( i ) );
+		frames[i] = frameType == 1 ? frameFromMatrix( keyFrames + 16 * size_t( i ) ) : frameFromSRT( keyFrames + 12 * size_t( i ) );
 	const Frame f = frameAt( frames.data(), count, time );
 	if ( matrixOut )
 	{
@@ -1430,6 +1576,17 @@ uint32_t orc_canonicalize(
 // ---- scenes -------------------------------------------------------------------------------------
 // One frame per instance (frame k belongs to instance k). frameType 0: hiprtFrameSRT (12 floats),
 // 1: hiprtFrameMatrix (16 floats). geometryOfInstance[k] indexes `geometries`.
+// objectIsScene (optional, one flag per handle in `geometries`): the handle is an oracle scene, instanced as hiprtInstanceTypeScene
+void* orc_scene_create_multilevel(
+	void* const*	geometries,
+	uint32_t		geometryCount,
+	const uint32_t* geometryOfInstance,
+	const float*	frames,
+	int				frameType,
+	const uint32_t* masks,
+	uint32_t		instanceCount,
+	const uint32_t* objectIsScene );
+
 void* orc_scene_create(
 	void* const*	geometries,
 	uint32_t		geometryCount,
@@ -1439,19 +1596,35 @@ void* orc_scene_create(
 	const uint32_t* masks,
 	uint32_t		instanceCount )
 {
+	return orc_scene_create_multilevel( geometries, geometryCount, geometryOfInstance, frames, frameType, masks, instanceCount, nullptr );
+}
+
+void* orc_scene_create_multilevel(
+	void* const*	geometries,
+	uint32_t		geometryCount,
+	const uint32_t* geometryOfInstance,
+	const float*	frames,
+	int				frameType,
+	const uint32_t* masks,
+	uint32_t		instanceCount,
+	const uint32_t* objectIsScene )
+{
 	(void)geometryCount;
 	SceneObj* s = new SceneObj;
 	s->count	= instanceCount;
 	s->geoms.resize( instanceCount );
+	s->scenes.assign( instanceCount, nullptr );
 	s->frames.resize( instanceCount );
 	s->masks.resize( instanceCount );
 	s->primBoxes.resize( instanceCount );
 	for ( uint32_t k = 0; k < instanceCount; ++k )
 	{
-		s->geoms[k]	 = static_cast<Geometry*>( geometries[geometryOfInstance[k]] );
+		const bool nested = objectIsScene && objectIsScene[geometryOfInstance[k]];
+		s->geoms[k]		  = nested ? nullptr : static_cast<Geometry*>( geometries[geometryOfInstance[k]] );
+		s->scenes[k]	  = nested ? static_cast<SceneObj*>( geometries[geometryOfInstance[k]] ) : nullptr;
 		s->frames[k] = frames ? ( frameType == 1 ? frameFromMatrix( frames + 16 * size_t( k ) ) : frameFromSRT( frames + 12 * size_t( k ) ) ) : Frame();
 		s->masks[k]	 = masks ? masks[k] : FullRayMask;
-		s->primBoxes[k] = instanceBox( *s->geoms[k], s->frames[k] );
+		s->primBoxes[k] = instanceBox( s->geoms[k] ? s->geoms[k]->wide : s->scenes[k]->wide, s->frames[k] );
 	}
 	// same LBVH pipeline as geometries, leaves are instances
 	s->sceneBox = emptyBox();
@@ -1505,7 +1678,7 @@ void* orc_scene_create(
 		n.geometry	= nullptr;
 		n.mask		= s->masks[k];
 		n.primIndex = k;
-		n.type		= 0;
+		n.type		= s->scenes[k] ? 1 : 0;
 		n.isStatic	= 1;
 		n.identity	= ident ? 1 : 0;
 		s->leaves.push_back( n );
@@ -1554,6 +1727,64 @@ void orc_scene_trace( void* h, const hiprtRay* rays, uint32_t n, hiprtHit* hits,
 {
 	SceneObj& s = *static_cast<SceneObj*>( h );
 	forEachRay( n, [&]( uint32_t i ) { hits[i] = canonical( traceSceneClosest( s, rays[i], rayMask, tieMode ), true ); } );
+}
+
+// Custom primitives: an AABB list (hiprtAABBListPrimitive: min xyz at byte 0, max xyz at byte strideBytes / 2 of every record),
+// built by the same LBVH pipeline with custom leaves.
+void* orc_geometry_create_aabbs( const float* aabbs, uint32_t count, uint32_t strideBytes, uint32_t geomType )
+{
+	Geometry* g	 = new Geometry;
+	g->primCount = count;
+	g->leafType	 = CustomType;
+	g->geomType	 = geomType;
+	g->primBoxes.resize( count );
+	for ( uint32_t p = 0; p < count; ++p )
+	{
+		const float* lo = reinterpret_cast<const float*>( reinterpret_cast<const uint8_t*>( aabbs ) + size_t( p ) * strideBytes );
+		const float* hi = reinterpret_cast<const float*>( reinterpret_cast<const uint8_t*>( lo ) + strideBytes / 2 );
+		g->primBoxes[p] = Box{ mk( lo[0], lo[1], lo[2] ), mk( hi[0], hi[1], hi[2] ) };
+	}
+	finishBuild( *g );
+	sortAndBuild( *g );
+	if ( g->primCount > 1 )
+		g->root = buildTopology( g->sortedKeys.data(), g->primCount, g->sortedBoxes.data(), g->leafType, g->scratch );
+	wideAndPack( *g );
+	return g;
+}
+
+// General trace (single-threaded: `fn` may be a Python callback). isScene: `h` is a scene, else a geometry.
+// maxPerRay == 0: closest hit, one hiprtHit per ray in hitsOut. maxPerRay > 0: every hit along the ray in visiting order,
+// countOut[i] of them (all are counted, the first maxPerRay are stored at hitsOut[i * maxPerRay ...]).
+void orc_trace_general(
+	void* h, int isScene, const hiprtRay* rays, uint32_t n, uint32_t rayMask, int tieMode, CustomIntersectFn fn, void* user, uint32_t maxPerRay,
+	uint32_t* countOut, hiprtHit* hitsOut )
+{
+	std::vector<hiprtHit> all;
+	for ( uint32_t i = 0; i < n; ++i )
+	{
+		Walk w;
+		w.closest = maxPerRay == 0, w.tieMode = tieMode, w.rayMask = rayMask, w.fn = fn, w.user = user, w.all = &all;
+		for ( uint32_t& id : w.ids )
+			id = InvalidValue;
+		all.clear();
+		hiprtRay ray = rays[i];
+		if ( isScene )
+			walkScene( *static_cast<SceneObj*>( h ), ray, 0, w );
+		else
+			walkGeometry( *static_cast<Geometry*>( h ), ray, 0, w );
+		if ( maxPerRay == 0 )
+		{
+			hiprtHit b = w.best;
+			if ( !b.hasHit() ) b.uv = { 0.0f, 0.0f }, b.normal = { 0.0f, 0.0f, 0.0f };
+			for ( uint32_t l = 0; l < hiprtMaxInstanceLevels; ++l )
+				if ( !b.hasHit() || !isScene ) b.instanceIDs[l] = InvalidValue;
+			hitsOut[i] = b;
+			continue;
+		}
+		countOut[i] = uint32_t( all.size() );
+		for ( uint32_t k = 0; k < all.size() && k < maxPerRay; ++k )
+			hitsOut[size_t( i ) * maxPerRay + k] = all[k];
+	}
 }
 
 } // extern "C"

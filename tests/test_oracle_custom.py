@@ -1,0 +1,106 @@
+"""CPU-only: the oracle's general traversal -- custom primitives through an intersection function, scenes instanced in scenes,
+the any-hit iterator drained to completion -- against the reference's CustomIntersection.png, SceneIntersection.png and
+SceneIntersectionMlas.png (test/main.cpp:1296-1385, 1485-1670, 1672-1900; kernels HiprtTestKernel.h:62-79, 238-262, 286-326), and
+against the specialised two-level / geometry traversals it generalises."""
+import numpy as np
+
+from oracle import binding as orc
+from tests import helpers as H
+from tests import test_oracle_golden as G
+
+CIRCLE_BOXES = np.array([[0.15, 0.40, 0.35, 0.60], [0.40, 0.40, 0.60, 0.60], [0.65, 0.40, 0.85, 0.60]], np.float32)
+CENTRES = np.array([0.25, 0.5, 0.75], np.float32)
+TRIANGLES = np.array([[0.15, 0.40, 0], [0.35, 0.40, 0], [0.25, 0.60, 0], [0.40, 0.40, 0], [0.60, 0.40, 0], [0.50, 0.60, 0],
+                      [0.65, 0.40, 0], [0.85, 0.40, 0], [0.75, 0.60, 0]], np.float32)
+
+
+def circles(z):
+    lo = np.concatenate([CIRCLE_BOXES[:, :2], np.full((3, 1), z, np.float32)], 1)
+    hi = np.concatenate([CIRCLE_BOXES[:, 2:], np.full((3, 1), z, np.float32)], 1)
+    return orc.AabbGeometry(np.concatenate([lo, hi], 1), geom_type=0)
+
+
+def intersect_circle(ray, geom_type, prim):
+    """intersectCircle (HiprtTestKernel.h:62-79) in float32: a disc of radius 0.1 around (centre[prim], 0.5), seen along +z."""
+    cx = CENTRES[prim] - ray["origin"][0]
+    cy = np.float32(0.5) - ray["origin"][1]
+    if np.sqrt(cx * cx + cy * cy, dtype=np.float32) < np.float32(0.1):
+        return (np.float32(1.0) - ray["origin"][2]) / ray["direction"][2]
+    return None
+
+
+def unit_square_rays(w=512, h=512):
+    x = (np.arange(w, dtype=np.float32) / np.float32(w))[None, :].repeat(h, 0)
+    y = (np.arange(h, dtype=np.float32) / np.float32(h))[:, None].repeat(w, 1)
+    o = np.stack([x, y, np.full_like(x, -1.0)], -1).reshape(-1, 3)
+    return orc.make_rays(o, np.broadcast_to(np.array([0, 0, 1], np.float32), o.shape), max_t=1000.0)
+
+
+def scene_image(counts, hits):
+    """SceneIntersectionKernel: every hit adds the colour of (innermost instance, primitive) in the image's uint8 arithmetic."""
+    colours = np.array([[[1, 0, 0], [0, 1, 0], [0, 0, 1]], [[0, 1, 1], [1, 0, 1], [1, 1, 0]]], np.uint8) * np.uint8(255)
+    img = np.zeros((len(counts), 4), np.uint8)
+    img[:, 3] = 255
+    for k in range(hits.shape[1]):
+        valid = k < counts
+        ids = hits["instanceIDs"][:, k]
+        inner = np.where(ids[:, 1] != orc.INVALID, ids[:, 1], ids[:, 0])
+        c = colours[np.where(valid, inner, 0), np.where(valid, hits["primID"][:, k], 0)]
+        img[:, :3] += np.where(valid[:, None], c, 0).astype(np.uint8)
+    return img
+
+
+def test_custom_intersection_matches_reference_image():
+    hits = orc.trace_general(circles(0.0), unit_square_rays(), intersect_circle)
+    prim = hits["primID"]
+    colours = np.array([[255, 0], [0, 255], [255, 255], [0, 0]], np.uint8)
+    img = np.zeros((len(prim), 4), np.uint8)
+    img[:, :2] = colours[np.where(prim == orc.INVALID, 3, prim)]
+    img[:, 3] = 255
+    assert G._check(img, "CustomIntersection") == 0.0
+
+
+def test_scene_intersection_and_multi_level_match_reference_images():
+    srt = lambda dy: [0, 0, 1, 0, 1, 1, 1, 0, dy, 0, 0, 0]
+    tris = orc.Geometry(TRIANGLES, np.arange(9, dtype=np.uint32).reshape(3, 3))
+    mid = orc.Scene([circles(1.0), tris], [0, 1], np.array([srt(0.05), srt(-0.05)], np.float32), 0)
+    rays = unit_square_rays()
+    counts, hits = orc.trace_general(mid, rays, intersect_circle, max_per_ray=4)
+    assert counts.max() <= 2 and (hits["instanceIDs"][counts > 0, 0, 1] == orc.INVALID).all()
+    assert G._check(scene_image(counts, hits), "SceneIntersection") == 0.0
+
+    top = orc.Scene([mid], [0, 0], np.array([srt(0.12), srt(-0.12)], np.float32), 0)
+    counts, hits = orc.trace_general(top, rays, intersect_circle, max_per_ray=8)
+    hit = counts > 0
+    assert counts.max() <= 8 and (hits["instanceIDs"][hit, 0, 0] <= 1).all() and (hits["instanceIDs"][hit, 0, 1] <= 1).all()
+    assert G._check(scene_image(counts, hits), "SceneIntersectionMlas") == 0.0
+
+
+def same_records(a, b):
+    return all(np.array_equal(a[f], b[f]) for f in ("instanceIDs", "primID", "uv", "normal", "t"))  # (not the padding word)
+
+
+def test_general_traversal_agrees_with_the_specialised_ones():
+    """Triangles only: the general walker must return the records of orc_scene_trace / orc_geometry_trace, and a scene wrapped
+    in an identity top level the same hits one level deeper."""
+    scene, geoms = H.cornell_obj_scene([0, 1, 0, 0.5, 1, 1, 1, 0, 0, -3, 0, 0])
+    rays = H.obj_camera_rays(128, 128)
+    for tie_mode in (0, 1):
+        a = scene.trace(rays, tie_mode=tie_mode)
+        b = orc.trace_general(scene, rays, tie_mode=tie_mode)
+        assert same_records(a, b)
+        g = geoms[6]
+        assert same_records(g.trace(rays, tie_mode=tie_mode), orc.trace_general(g, rays, tie_mode=tie_mode))
+    top = orc.Scene([scene], [0], None, 0)
+    c = orc.trace_general(top, rays)
+    a = scene.trace(rays)
+    hit = a["primID"] != orc.INVALID
+    assert np.array_equal(a["primID"], c["primID"]) and np.array_equal(a["t"][hit], c["t"][hit])
+    assert (c["instanceIDs"][hit, 0] == 0).all() and np.array_equal(c["instanceIDs"][hit, 1], a["instanceIDs"][hit, 0])
+    # every hit along the ray: the same set the geometry-level any-hit iterator enumerates
+    verts, _, _ = H.cornell_box()
+    box = orc.Geometry(verts, np.arange(96, dtype=np.uint32).reshape(-1, 3))
+    box_rays = H.cornell_rays(128, 128)
+    counts, prims, _ = box.trace_all(box_rays, max_per_ray=16)
+    counts2, hits2 = orc.trace_general(box, box_rays, max_per_ray=16)
+    assert np.array_equal(counts, counts2) and np.array_equal(np.sort(prims, 1), np.sort(hits2["primID"], 1))
