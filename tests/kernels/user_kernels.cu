@@ -136,6 +136,15 @@ extern "C" __global__ void sceneKernel( hiprtScene scene, const hiprtRay* rays, 
 	hits[i] = tr.getNextHit();
 }
 
+// closest hit of a scene that holds custom primitives: the function table goes to the traversal object
+extern "C" __global__ void sceneTableKernel( hiprtScene scene, hiprtFuncTable table, const hiprtRay* rays, hiprtHit* hits, uint32_t numRays )
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i >= numRays ) return;
+	hiprtSceneTraversalClosest tr( scene, rays[i], hiprtFullRayMask, hiprtTraversalHintDefault, nullptr, table );
+	hits[i] = tr.getNextHit();
+}
+
 // motion blur: every ray is traced at the same `time` (an application would carry a time per ray in its own ray payload)
 extern "C" __global__ void motionSceneKernel( hiprtScene scene, const hiprtRay* rays, hiprtHit* hits, uint32_t numRays, float time )
 {

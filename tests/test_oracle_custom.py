@@ -104,3 +104,41 @@ def test_general_traversal_agrees_with_the_specialised_ones():
     counts, prims, _ = box.trace_all(box_rays, max_per_ray=16)
     counts2, hits2 = orc.trace_general(box, box_rays, max_per_ray=16)
     assert np.array_equal(counts, counts2) and np.array_equal(np.sort(prims, 1), np.sort(hits2["primID"], 1))
+
+
+def test_three_level_scene_equals_its_flattened_scene():
+    """Scenes instanced in scenes, three levels deep, against the single-level scene of the composed transforms: the same rays
+    hit, the same primitive, the instance ids compose, t agrees to float accuracy (the composed matrix rounds differently)."""
+    from hiprt_b200 import scenes
+
+    meshes = scenes.instanced_geometries(3)
+    leaf_frames = scenes.random_matrix_frames(6, seed=5, extent=2.0, scale_range=(0.6, 1.2))
+    mid_frames = scenes.random_matrix_frames(4, seed=6, extent=6.0, scale_range=(0.8, 1.1))
+    top_frames = scenes.random_matrix_frames(3, seed=7, extent=14.0, scale_range=(0.9, 1.0))
+    geoms = [orc.Geometry(v, i) for v, i in meshes]
+    leaf = orc.Scene(geoms, [k % 3 for k in range(6)], leaf_frames, 1)
+    mid = orc.Scene([leaf], [0] * 4, mid_frames, 1)
+    top = orc.Scene([mid], [0] * 3, top_frames, 1)
+
+    def matrix(f):
+        m = np.eye(4)
+        m[:3, :4] = f[:12].reshape(3, 4)
+        return m
+
+    flat_frames = np.zeros((72, 16), np.float32)
+    for a in range(3):
+        for b in range(4):
+            for c in range(6):
+                flat_frames[a * 24 + b * 6 + c, :12] = (matrix(top_frames[a]) @ matrix(mid_frames[b]) @ matrix(leaf_frames[c]))[:3].reshape(-1)
+    flat = orc.Scene(geoms, [k % 6 % 3 for k in range(72)], flat_frames, 1)
+
+    rays = scenes.pinhole_rays(160, 160, (0.0, 4.0, 45.0), (0, 0, 0))
+    deep = orc.trace_general(top, rays, tie_mode=1)
+    ref = flat.trace(rays, tie_mode=1)
+    hit = ref["primID"] != orc.INVALID
+    assert hit.mean() > 0.03 and np.array_equal(deep["primID"] != orc.INVALID, hit)
+    ids = deep["instanceIDs"][hit]
+    assert (ids[:, 3] == orc.INVALID).all()
+    same = (deep["primID"][hit] == ref["primID"][hit]) & (ids[:, 0] * 24 + ids[:, 1] * 6 + ids[:, 2] == ref["instanceIDs"][hit, 0])
+    assert same.mean() > 0.999
+    np.testing.assert_allclose(deep["t"][hit][same], ref["t"][hit][same], rtol=2e-5)
