@@ -54,6 +54,8 @@ FLT_MAX = np.float32(3.402823466e38)
 
 # int fn(const hiprtRay* ray, uint32_t geomType, void* user, hiprtHit* hit): the oracle's stand-in for a hiprtFuncTable entry
 CUSTOM_INTERSECT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p)
+# int fn(const hiprtRay* ray, uint32_t geomType, void* user, const hiprtHit* hit): non-zero rejects the hit
+HIT_FILTER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p)
 
 
 def build(force=False):
@@ -104,7 +106,8 @@ def lib():
         L.orc_scene_create_multilevel.restype = vp
         L.orc_geometry_create_aabbs.argtypes = [vp, u32, u32, u32]
         L.orc_geometry_create_aabbs.restype = vp
-        L.orc_trace_general.argtypes = [vp, i32, vp, u32, u32, i32, CUSTOM_INTERSECT_FN, vp, u32, vp, vp]
+        L.orc_trace_general.argtypes = [vp, i32, vp, u32, u32, i32, CUSTOM_INTERSECT_FN, HIT_FILTER_FN, vp, u32, vp, vp]
+        L.orc_geometry_set_geom_type.argtypes = [vp, u32]
         _lib = L
     return _lib
 
@@ -154,6 +157,10 @@ class Geometry:
                 self.h = None
         except Exception:  # interpreter shutdown: module globals may already be gone
             pass
+
+    def set_geom_type(self, geom_type):
+        """User geometry type (hiprtGeometryBuildInput::geomType): makes the hit filter of trace_general apply to this geometry."""
+        lib().orc_geometry_set_geom_type(self.h, geom_type)
 
     def _count(self, what):
         return int(lib().orc_geometry_count(self.h, what))
@@ -273,13 +280,21 @@ class AabbGeometry:
             pass
 
 
-def trace_general(obj, rays, intersect=None, ray_mask=0xFFFFFFFF, tie_mode=1, max_per_ray=0):
+def trace_general(obj, rays, intersect=None, ray_mask=0xFFFFFFFF, tie_mode=1, max_per_ray=0, hit_filter=None):
     """Closest hit (max_per_ray == 0: HIT_DTYPE [n]) or every hit along each ray in visiting order (max_per_ray > 0:
     (counts [n], HIT_DTYPE [n, max_per_ray])) through a Geometry, AabbGeometry or (multi-level) Scene. intersect(ray, geom_type,
     prim_id) -> None or t is the custom-primitive intersection function: `ray` is a RAY_DTYPE record in the primitive's object
-    space."""
+    space. hit_filter(ray, geom_type, hit) -> True rejects the candidate hit (a HIT_DTYPE record); it is consulted for the
+    geometries that have a user geometry type (Geometry.set_geom_type, AabbGeometry)."""
     rays = np.ascontiguousarray(rays, RAY_DTYPE)
     n = len(rays)
+
+    def filter_callback(ray_ptr, geom_type, _user, hit_ptr):
+        ray = np.ctypeslib.as_array(C.cast(ray_ptr, C.POINTER(C.c_uint8)), (32,)).view(RAY_DTYPE)[0]
+        hit = np.ctypeslib.as_array(C.cast(hit_ptr, C.POINTER(C.c_uint8)), (48,)).view(HIT_DTYPE)[0]
+        return int(bool(hit_filter(ray, geom_type, hit)))
+
+    flt = HIT_FILTER_FN(filter_callback) if hit_filter is not None else C.cast(None, HIT_FILTER_FN)
 
     def callback(ray_ptr, geom_type, _user, hit_ptr):
         ray = np.ctypeslib.as_array(C.cast(ray_ptr, C.POINTER(C.c_uint8)), (32,)).view(RAY_DTYPE)[0]
@@ -294,12 +309,12 @@ def trace_general(obj, rays, intersect=None, ray_mask=0xFFFFFFFF, tie_mode=1, ma
     is_scene = int(isinstance(obj, Scene))
     if max_per_ray == 0:
         hits = np.zeros(n, HIT_DTYPE)
-        lib().orc_trace_general(obj.h, is_scene, _p(rays), n, ray_mask, tie_mode, fn, None, 0, None, _p(hits))
+        lib().orc_trace_general(obj.h, is_scene, _p(rays), n, ray_mask, tie_mode, fn, flt, None, 0, None, _p(hits))
         return hits
     counts = np.zeros(n, np.uint32)
     hits = np.zeros((n, max_per_ray), HIT_DTYPE)
     hits["primID"] = INVALID
-    lib().orc_trace_general(obj.h, is_scene, _p(rays), n, ray_mask, tie_mode, fn, None, max_per_ray, _p(counts), _p(hits))
+    lib().orc_trace_general(obj.h, is_scene, _p(rays), n, ray_mask, tie_mode, fn, flt, None, max_per_ray, _p(counts), _p(hits))
     return counts, hits
 
 

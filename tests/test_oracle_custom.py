@@ -142,3 +142,41 @@ def test_three_level_scene_equals_its_flattened_scene():
     same = (deep["primID"][hit] == ref["primID"][hit]) & (ids[:, 0] * 24 + ids[:, 1] * 6 + ids[:, 2] == ref["instanceIDs"][hit, 0])
     assert same.mean() > 0.999
     np.testing.assert_allclose(deep["t"][hit][same], ref["t"][hit][same], rtol=2e-5)
+
+
+def test_cutout_through_the_hit_filter_matches_reference_image():
+    """The Cutout picture again (tests/test_oracle_golden.py evaluates the checkerboard after the fact), this time with the filter
+    where the reference has it: inside the traversal, as a hit-filter function of a geometry with a user geometry type
+    (cutoutFilter, HiprtTestKernel.h:88-100). A second quad behind the first shows through the holes only because a rejected hit
+    does not shorten the ray."""
+    v = np.array([[0, 0, 0], [0, 1, 0], [1, 1, 0], [1, 0, 0]], np.float32)
+    tri = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    calls = [0]
+
+    def cutout(ray, geom_type, hit):
+        calls[0] += 1
+        u, w_ = hit["uv"]
+        tx, ty = (w_, u + w_) if hit["primID"] == 0 else (u + w_, u)
+        return bool((int(np.float32(16.0) * np.float32(tx)) + int(np.float32(16.0) * np.float32(ty))) & 1)
+
+    g = orc.Geometry(v, tri)
+    g.set_geom_type(0)
+    rays = H.ortho_rays(256, 256)
+    hits = orc.trace_general(g, rays, hit_filter=cutout, tie_mode=0)
+    visible = hits["primID"] != orc.INVALID
+    assert calls[0] >= (256 * 256) * 0.9
+    img = np.zeros((256 * 256, 4), np.uint8)
+    img[:, :3] = np.where(visible, 255, 0)[:, None]
+    img[:, 3] = 255
+    golden = H.load_golden_image("Cutout")[::2, ::2].reshape(-1, 4)  # the checkerboard cells are 32 pixels wide
+    assert (np.abs(img.astype(int) - golden.astype(int)).max(1) > 10).mean() < 0.003
+
+    # two layers: the far quad is reported exactly where the near one is cut out
+    v2 = np.concatenate([v, v + np.array([0, 0, 0.5], np.float32)])
+    g2 = orc.Geometry(v2, np.concatenate([tri, tri + 4]), allow_pairing=False)
+    g2.set_geom_type(0)
+    near_only = lambda ray, geom_type, hit: hit["primID"] < 2 and cutout(ray, geom_type, hit)
+    both = orc.trace_general(g2, rays, hit_filter=near_only, tie_mode=1)
+    far = (both["primID"] >= 2) & (both["primID"] != orc.INVALID)
+    assert np.array_equal(far, ~visible & (both["primID"] != orc.INVALID))
+    assert (both["primID"][visible] < 2).all() and (both["primID"] != orc.INVALID).mean() > 0.95
