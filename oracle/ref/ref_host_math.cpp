@@ -12,8 +12,10 @@
 #include <hiprt/impl/MortonCode.h>
 #include <hiprt/impl/Transform.h>
 #include <hiprt/impl/Triangle.h>
+#include <hiprt/impl/TriangleMesh.h>
 
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 using namespace hiprt;
@@ -94,6 +96,29 @@ void ref_frames( uint32_t n, const float* frames, int frameType, float* srtOut, 
 		for ( int r = 0; r < 3; ++r )
 			for ( int c = 0; c < 4; ++c )
 				invOut[12 * i + 4 * r + c] = inv[r][c];
+	}
+}
+
+// TriangleMesh.h:32-50,89-157 and BvhNode.h:682-703: the 64-byte leaf of a triangle pair (the four vertices after the rotation that
+// puts the shared edge at [1,2], both primitive indices, the flags that undo the rotation in the reported uv and normal) and its box.
+// vertices: float3 stride 12; triangles: uint3 stride 12; pairs: uint2 per node (x == y: single triangle).
+void ref_pair_nodes( const float* vertices, uint32_t vertexCount, const uint32_t* triangles, uint32_t triangleCount, const uint32_t* pairs, uint32_t n, void* nodesOut, float* boxesOut )
+{
+	hiprtTriangleMeshPrimitive prim{};
+	prim.vertices		 = const_cast<float*>( vertices );
+	prim.vertexCount	 = vertexCount;
+	prim.vertexStride	 = 12;
+	prim.triangleIndices = const_cast<uint32_t*>( triangles );
+	prim.triangleCount	 = triangleCount;
+	prim.triangleStride	 = 12;
+	const TriangleMesh mesh( prim );
+	for ( uint32_t i = 0; i < n; ++i )
+	{
+		const TrianglePairNode node = mesh.fetchTrianglePairNode( uint2{ pairs[2 * i], pairs[2 * i + 1] } );
+		memcpy( static_cast<uint8_t*>( nodesOut ) + 64 * size_t( i ), &node, 64 );
+		const Aabb box = node.aabb();
+		boxesOut[6 * i + 0] = box.m_min.x, boxesOut[6 * i + 1] = box.m_min.y, boxesOut[6 * i + 2] = box.m_min.z;
+		boxesOut[6 * i + 3] = box.m_max.x, boxesOut[6 * i + 4] = box.m_max.y, boxesOut[6 * i + 5] = box.m_max.z;
 	}
 }
 

@@ -76,6 +76,24 @@ def ref_math_inputs(seed=2024):
     mats[2, :12] = np.array([[1, 1, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]], f).reshape(-1)
     mats[:, 12] = rng.uniform(0, 1, ns)
     d["frames_matrix"] = mats
+    # triangle pairs: every way two triangles can share an edge (3 edges x 3 rotations of the first x 6 vertex orders of the second),
+    # 12 random quads each, plus unpaired triangles (x == y)
+    import itertools
+    pv, pt, pl = [], [], []
+    for edge, rot0, perm1 in itertools.product(range(3), range(3), itertools.permutations(range(3))):
+        for _ in range(12):
+            a = rng.uniform(-1, 1, (4, 3)).astype(f)  # 0,1,2 = first triangle, 3 = the vertex across the shared edge
+            base = len(pv)
+            pv.extend(a)
+            first = np.roll(np.array([0, 1, 2]), rot0)
+            shared = [(0, 1), (1, 2), (2, 0)][edge]
+            second = np.array([shared[0], shared[1], 3])[list(perm1)]
+            pt.append(base + first)
+            pt.append(base + second)
+            pl.append([len(pt) - 2, len(pt) - 1])
+    for k in range(0, 60, 2):
+        pl.append([k, k])
+    d["pair_vertices"], d["pair_triangles"], d["pair_list"] = np.array(pv, f), np.array(pt, np.uint32), np.array(pl, np.uint32)
     # motion: key-frame sets (times ascending from 0), rays and times inside, on and beyond the key times
     sets = []
     for j in range(12):
@@ -123,6 +141,12 @@ def run(L, prefix, d):
     t01 = np.zeros((m, 2), np.float32)
     getattr(L, prefix + "slab")(m, p(d["slab_boxes"]), p(d["slab_o"]), p(d["slab_inv"]), p(d["slab_maxt"]), p(t01))
     out["slab_t01"] = t01
+    pn = len(d["pair_list"])
+    nodes, boxes = np.zeros((pn, 64), np.uint8), np.zeros((pn, 6), np.float32)
+    getattr(L, prefix + "pair_nodes")(p(d["pair_vertices"]), len(d["pair_vertices"]), p(d["pair_triangles"]), len(d["pair_triangles"]),
+                                      p(d["pair_list"]), pn, p(nodes), p(boxes))
+    nodes[:, 48:52] = 0  # the padding word between the vertices and the primitive indices is not written
+    out["pair_nodes"], out["pair_boxes"] = nodes, boxes
     for kind, name in ((0, "frames_srt"), (1, "frames_matrix")):
         fr = d[name]
         srt, inv = np.zeros((len(fr), 13), np.float32), np.zeros((len(fr), 12), np.float32)

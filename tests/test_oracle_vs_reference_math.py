@@ -45,6 +45,17 @@ def test_slab_test_is_the_references(oracle_out):
     assert ((b[:, 0] <= b[:, 1]).mean() > 0.02) and np.isinf(INPUTS["slab_inv"]).any()
 
 
+def test_triangle_pair_leaves_are_the_references(oracle_out):
+    """TriangleMesh::fetchTrianglePairNode: vertex rotation, primitive indices and the flags of all 54 ways to share an edge."""
+    from oracle.binding import TRIPAIR_DTYPE
+
+    got, want = oracle_out["pair_nodes"].view(TRIPAIR_DTYPE).reshape(-1), GOLDEN["pair_nodes"].view(TRIPAIR_DTYPE).reshape(-1)
+    assert len(np.unique(want["flags"])) >= 6
+    for field in ("v", "primIndex0", "primIndex1", "flags"):
+        assert np.array_equal(bits(got[field]), bits(want[field])), field
+    assert np.array_equal(bits(oracle_out["pair_boxes"]), bits(GOLDEN["pair_boxes"]))
+
+
 @pytest.mark.parametrize("name", ["frames_srt", "frames_matrix"])
 def test_frame_decomposition_and_inverse_are_the_references(oracle_out, name):
     assert np.array_equal(bits(oracle_out[name + "_decomposed"]), bits(GOLDEN[name + "_decomposed"]))
