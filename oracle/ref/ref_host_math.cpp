@@ -122,6 +122,23 @@ void ref_pair_nodes( const float* vertices, uint32_t vertexCount, const uint32_t
 	}
 }
 
+// Transform.h:460-517: world-space bounds of a box under the key frames of one instance (every key frame and three interpolated
+// poses between consecutive keys): what the scene builder bounds an instance with (InstanceList.h:104-121).
+void ref_motion_bounds( uint32_t frameCount, const float* frames, int frameType, uint32_t n, const float* boxesIn, float* boxesOut )
+{
+	const uint32_t		  stride = frameType == 1 ? 16 : 12;
+	std::vector<SRTFrame> keys( frameCount );
+	for ( uint32_t k = 0; k < frameCount; ++k )
+		keys[k] = frameOf( frames + stride * k, frameType );
+	const Transform transform( reinterpret_cast<const Frame*>( keys.data() ), 0, frameCount );
+	for ( uint32_t i = 0; i < n; ++i )
+	{
+		const Aabb out = transform.motionBounds( Aabb( f3( boxesIn + 6 * i ), f3( boxesIn + 6 * i + 3 ) ) );
+		boxesOut[6 * i + 0] = out.m_min.x, boxesOut[6 * i + 1] = out.m_min.y, boxesOut[6 * i + 2] = out.m_min.z;
+		boxesOut[6 * i + 3] = out.m_max.x, boxesOut[6 * i + 4] = out.m_max.y, boxesOut[6 * i + 5] = out.m_max.z;
+	}
+}
+
 // Transform.h:410-452: the key frames of one instance, the ray carried into the instance at `time` (motion blur).
 void ref_motion_ray( uint32_t frameCount, const float* frames, int frameType, uint32_t n, const float* times, const hiprtRay* raysIn, hiprtRay* raysOut )
 {

@@ -110,6 +110,8 @@ def ref_math_inputs(seed=2024):
     d["motion_count"] = np.array(len(sets))
     for j, (kind, keys) in enumerate(sets):
         d[f"motion_kind_{j}"], d[f"motion_keys_{j}"] = np.array(kind), keys
+    blo = rng.uniform(-2, 1, (200, 3)).astype(f)
+    d["motion_boxes"] = np.concatenate([blo, blo + rng.uniform(0, 2, (200, 3)).astype(f)], 1)
     nm = 300
     mr = np.zeros(nm, RAY)
     mr["origin"], mr["direction"] = rng.uniform(-4, 4, (nm, 3)), rng.normal(size=(nm, 3))
@@ -155,6 +157,17 @@ def run(L, prefix, d):
     return out
 
 
+def run_motion_bounds(L, prefix, d):
+    out = {}
+    boxes = d["motion_boxes"]
+    for j in range(int(d["motion_count"])):
+        keys = np.ascontiguousarray(d[f"motion_keys_{j}"])
+        res = np.zeros_like(boxes)
+        getattr(L, prefix + "motion_bounds")(len(keys), p(keys), int(d[f"motion_kind_{j}"]), len(boxes), p(boxes), p(res))
+        out[f"motion_bounds_{j}"] = res
+    return out
+
+
 def run_reference_motion(L, d):
     out = {}
     rays, times = d["motion_rays"], d["motion_times"]
@@ -171,6 +184,7 @@ def main():
     d = ref_math_inputs()
     out = run(L, "ref_", d)
     out.update(run_reference_motion(L, d))
+    out.update(run_motion_bounds(L, "ref_", d))
     np.savez_compressed(os.path.join(HERE, "ref_math.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

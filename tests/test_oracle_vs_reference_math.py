@@ -73,11 +73,19 @@ def test_motion_ray_transform_is_the_references():
                 assert np.array_equal(bits(np.atleast_1d(got[field])), bits(np.atleast_1d(want[i][field]))), (j, i, field)
 
 
+def test_motion_bounds_are_the_references():
+    """Transform::motionBounds: what the scene builder bounds an (animated) instance with."""
+    got = M.run_motion_bounds(orc.lib(), "orc_math_", INPUTS)
+    for k, v in got.items():
+        assert np.array_equal(bits(v), bits(GOLDEN[k])), k
+
+
 @pytest.mark.skipif(not os.path.exists(M.REF_LIB), reason="the compiled reference (oracle/_ref) is not on this machine")
 def test_committed_vectors_are_what_the_compiled_reference_returns():
     L = C.CDLL(M.REF_LIB)
     live = M.run(L, "ref_", INPUTS)
     live.update(M.run_reference_motion(L, INPUTS))
+    live.update(M.run_motion_bounds(L, "ref_", INPUTS))
     assert set(live) == set(GOLDEN.files)
     for k, v in live.items():
         assert np.array_equal(bits(v), bits(GOLDEN[k]), equal_nan=False) or np.array_equal(v, GOLDEN[k], equal_nan=True), k
