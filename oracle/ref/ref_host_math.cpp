@@ -139,6 +139,25 @@ void ref_motion_bounds( uint32_t frameCount, const float* frames, int frameType,
 	}
 }
 
+// Transform.h:188-230 under the pose at `time`: per input vector p: transform( p ), invTransform( p ), transformVector( p ),
+// invTransformVector( p ) (what hiprtPoint/VectorObjectToWorld/WorldToObject return)
+void ref_motion_points( uint32_t frameCount, const float* frames, int frameType, float time, uint32_t n, const float* in, float* out )
+{
+	const uint32_t		  stride = frameType == 1 ? 16 : 12;
+	std::vector<SRTFrame> keys( frameCount );
+	for ( uint32_t k = 0; k < frameCount; ++k )
+		keys[k] = frameOf( frames + stride * k, frameType );
+	const Transform transform( reinterpret_cast<const Frame*>( keys.data() ), 0, frameCount );
+	const SRTFrame	f = transform.interpolateFrames( time );
+	for ( uint32_t i = 0; i < n; ++i )
+	{
+		const float3 p	  = f3( in + 3 * i );
+		const float3 r[4] = { f.transform( p ), f.invTransform( p ), f.transformVector( p ), f.invTransformVector( p ) };
+		for ( int k = 0; k < 4; ++k )
+			out[12 * i + 3 * k] = r[k].x, out[12 * i + 3 * k + 1] = r[k].y, out[12 * i + 3 * k + 2] = r[k].z;
+	}
+}
+
 // Transform.h:410-452: the key frames of one instance, the ray carried into the instance at `time` (motion blur).
 void ref_motion_ray( uint32_t frameCount, const float* frames, int frameType, uint32_t n, const float* times, const hiprtRay* raysIn, hiprtRay* raysOut )
 {

@@ -168,6 +168,29 @@ def run_motion_bounds(L, prefix, d):
     return out
 
 
+POINT_TIMES = (0.0, 0.3, 0.5, 0.9, 1.0)
+
+
+def run_reference_points(L, d):
+    """Also stores, per key-frame set, the reference's decomposed key frames in the 64-byte layout of the scene storage
+    (rotation 4, scale 3, shear 3, translation 3, time, 2 pad): the input of the product's traversal-side code."""
+    out = {}
+    pts = np.ascontiguousarray(d["motion_rays"].view(RAY).reshape(-1)["direction"][:100])
+    for j in range(int(d["motion_count"])):
+        keys, kind = np.ascontiguousarray(d[f"motion_keys_{j}"]), int(d[f"motion_kind_{j}"])
+        srt, inv = np.zeros((len(keys), 13), np.float32), np.zeros((len(keys), 12), np.float32)
+        L.ref_frames(len(keys), p(keys), kind, p(srt), p(inv))
+        stored = np.zeros((len(keys), 16), np.float32)
+        stored[:, :13] = srt
+        stored[:, 13] = keys[:, 12 if kind == 1 else 10]
+        out[f"motion_stored_{j}"] = stored
+        res = np.zeros((len(POINT_TIMES), len(pts), 12), np.float32)
+        for k, time in enumerate(POINT_TIMES):
+            L.ref_motion_points(len(keys), p(keys), kind, C.c_float(time), len(pts), p(pts), p(res[k]))
+        out[f"motion_points_{j}"] = res
+    return out
+
+
 def run_reference_motion(L, d):
     out = {}
     rays, times = d["motion_rays"], d["motion_times"]
@@ -185,6 +208,7 @@ def main():
     out = run(L, "ref_", d)
     out.update(run_reference_motion(L, d))
     out.update(run_motion_bounds(L, "ref_", d))
+    out.update(run_reference_points(L, d))
     np.savez_compressed(os.path.join(HERE, "ref_math.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

@@ -86,6 +86,7 @@ def test_committed_vectors_are_what_the_compiled_reference_returns():
     live = M.run(L, "ref_", INPUTS)
     live.update(M.run_reference_motion(L, INPUTS))
     live.update(M.run_motion_bounds(L, "ref_", INPUTS))
+    live.update(M.run_reference_points(L, INPUTS))
     assert set(live) == set(GOLDEN.files)
     for k, v in live.items():
         assert np.array_equal(bits(v), bits(GOLDEN[k]), equal_nan=False) or np.array_equal(v, GOLDEN[k], equal_nan=True), k
