@@ -1,0 +1,129 @@
+"""CPU-only: the PRODUCT's device-side traversal -- include/hiprt/hiprt_device.h, the traversal objects user kernels and the
+library's generic trace kernels instantiate -- built for the host (tests/host/product_device_host.cpp: device qualifiers defined
+away, intrinsics given their plain meaning, nothing of the header changed) and run on the CPU over the oracle's node arrays (the
+layouts are the product's, include/hiprt/hiprt_b200_layout.h). Held to the oracle hit for hit -- primID / instanceID exact, t, uv and
+normal BIT-identical (the triangle and slab arithmetic of both are bit-identical to the reference's, see
+tests/test_oracle_vs_reference_math.py) -- and to the reference's golden images. A check of product source without a GPU; what the
+GPU adds is the compiler's contraction and the kernels around the objects, which the -m gpu tests cover."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from hiprt_b200 import scenes
+from oracle import binding as orc
+from tests import helpers as H
+from tests import test_oracle_golden as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDA_INCLUDE = "/usr/local/cuda/include"
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None or not os.path.exists(os.path.join(CUDA_INCLUDE, "vector_types.h")),
+                                reason="needs g++ and the CUDA toolkit's vector type headers")
+CLOSEST, ANY = 2, 1
+
+
+@pytest.fixture(scope="module")
+def product(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("host") / "libproduct_device_host.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-I", CUDA_INCLUDE,
+                           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "host", "product_device_host.cpp"), "-o", so])
+    L = C.CDLL(so)
+    L.prod_trace_geometry_all.restype = C.c_uint64
+    return L
+
+
+def p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def trace_geometry(L, og, rays, kind=CLOSEST):
+    boxes, leaves = np.ascontiguousarray(og.box_nodes), np.ascontiguousarray(og.leaves)
+    rays = np.ascontiguousarray(rays, orc.RAY_DTYPE)
+    hits = np.zeros(len(rays), orc.HIT_DTYPE)
+    L.prod_trace_geometry(p(boxes), p(leaves), len(boxes), len(leaves), p(rays), len(rays), p(hits), kind)
+    return hits
+
+
+def trace_scene(L, oscene, rays, kind=CLOSEST, ray_mask=0xFFFFFFFF):
+    geoms = oscene.geometries
+    gb = [np.ascontiguousarray(g.box_nodes) for g in geoms]
+    gl = [np.ascontiguousarray(g.leaves) for g in geoms]
+    boxes, leaves = np.ascontiguousarray(oscene.box_nodes), np.ascontiguousarray(oscene.leaves)
+    geometry_of_leaf = np.ascontiguousarray(oscene.geometry_of_instance[leaves["bits"] & 0xFFFFFF], np.uint32)
+    gb_ptrs = (C.c_void_p * len(geoms))(*[a.ctypes.data for a in gb])
+    gl_ptrs = (C.c_void_p * len(geoms))(*[a.ctypes.data for a in gl])
+    rays = np.ascontiguousarray(rays, orc.RAY_DTYPE)
+    hits = np.zeros(len(rays), orc.HIT_DTYPE)
+    L.prod_trace_scene(p(boxes), p(leaves), len(leaves), p(geometry_of_leaf), gb_ptrs, gl_ptrs, len(geoms), p(rays), len(rays), p(hits), kind, ray_mask)
+    return hits
+
+
+def assert_same_hits(got, ref, scene=False):
+    hit = ref["primID"] != orc.INVALID
+    assert np.array_equal(got["primID"], ref["primID"])
+    if scene:
+        assert np.array_equal(got["instanceIDs"][hit, 0], ref["instanceIDs"][hit, 0])
+    for field in ("t", "uv", "normal"):
+        assert np.array_equal(got[field][hit].view(np.uint32), ref[field][hit].view(np.uint32)), field
+
+
+@pytest.mark.parametrize("mesh", ["cornell", "sphere", "soup"])
+def test_geometry_traversal_objects_return_the_oracles_hits(product, mesh):
+    if mesh == "cornell":
+        verts, _, _ = H.cornell_box()
+        og, rays = orc.Geometry(verts, np.arange(96, dtype=np.uint32).reshape(-1, 3)), H.cornell_rays(192, 192)
+    elif mesh == "sphere":
+        v, i = scenes.sphere_mesh(96, 48)
+        og, rays = orc.Geometry(v, i), scenes.pinhole_rays(160, 160, (0, 0, 3), (0, 0, 0))
+    else:
+        v = scenes.random_soup(3000, seed=3)  # non-indexed: three vertices per triangle
+        og, rays = orc.Geometry(v), scenes.random_rays(20000, [-1, -1, -1], [1, 1, 1], seed=5)
+    ref = og.trace(rays, tie_mode=1)  # the order-independent closest-hit rule the product implements
+    assert 0.05 < (ref["primID"] != orc.INVALID).mean()
+    assert_same_hits(trace_geometry(product, og, rays), ref)
+    occluded = trace_geometry(product, og, rays, ANY)["primID"] != orc.INVALID
+    assert np.array_equal(occluded, ref["primID"] != orc.INVALID)
+
+
+def test_any_hit_iterator_enumerates_the_oracles_hits(product):
+    verts, _, _ = H.cornell_box()
+    og = orc.Geometry(verts, np.arange(96, dtype=np.uint32).reshape(-1, 3))
+    rays = H.cornell_rays()
+    boxes, leaves = np.ascontiguousarray(og.box_nodes), np.ascontiguousarray(og.leaves)
+    counts, prims = np.zeros(len(rays), np.uint32), np.full((len(rays), 16), orc.INVALID, np.uint32)
+    product.prod_trace_geometry_all(p(boxes), p(leaves), len(boxes), len(leaves), p(rays), len(rays), 16, p(counts), p(prims))
+    ocounts, oprims, _ = og.trace_all(rays, max_per_ray=16)
+    assert np.array_equal(counts, ocounts) and np.array_equal(np.sort(prims, 1), np.sort(oprims, 1))
+    # ... which is the reference's MinimumCornellBox picture
+    ok, bad, mx = H.image_matches(G.minimum_cornell_image(prims).reshape(512, 512, 4), H.load_golden_image("MinimumCornellBox"))
+    assert ok and bad == 0.0
+
+
+@pytest.mark.parametrize("name, frame", [
+    ("PrimaryRayCornellBox", None),
+    ("RotateCornellBox", [0, 1, 0, 0.5, 1, 1, 1, 0, 0, -3, 0, 0]),
+    ("ScaleCornellBox", [0, 0, 1, 0, 2, 2, 2, 0, 0, 0, 0, 0]),
+])
+def test_scene_traversal_objects_return_the_oracles_hits_and_the_reference_images(product, name, frame):
+    oscene, _ = H.cornell_obj_scene(frame)
+    rays = H.obj_camera_rays()
+    got = trace_scene(product, oscene, rays)
+    assert_same_hits(got, oscene.trace(rays, tie_mode=1), scene=True)
+    G._check(G._colour_image(got), name)
+    occluded = trace_scene(product, oscene, rays, ANY)["primID"] != orc.INVALID
+    assert np.array_equal(occluded, got["primID"] != orc.INVALID)
+
+
+def test_scene_traversal_respects_instance_masks(product):
+    d = np.load(os.path.join(H.GOLDEN, "cornell_obj.npz"))
+    n = int(d["shape_count"])
+    geoms = [orc.Geometry(d["vertices"], d[f"tris_{k}"]) for k in range(n)]
+    masks = np.array([0 if k % 2 == 0 else 0xFFFFFFFF for k in range(n)], np.uint32)
+    oscene = orc.Scene(geoms, np.arange(n), None, 0, masks=masks)
+    got = trace_scene(product, oscene, H.obj_camera_rays())
+    G._check(G._colour_image(got), "RayMaskCornellBox")
+    none = trace_scene(product, oscene, H.obj_camera_rays(64, 64), ray_mask=0)
+    assert (none["primID"] == orc.INVALID).all()
