@@ -269,7 +269,16 @@ class AabbGeometry:
 
     def __init__(self, aabbs, geom_type=0):
         self.aabbs = np.ascontiguousarray(aabbs, np.float32).reshape(-1, 6)
+        self.geom_type = geom_type
         self.h = lib().orc_geometry_create_aabbs(_p(self.aabbs), len(self.aabbs), 24, geom_type)
+
+    def _read(self, what, dtype, n):
+        out = np.zeros(n, dtype)
+        lib().orc_geometry_read(self.h, what, _p(out))
+        return out
+
+    box_nodes = property(lambda s: s._read(6, BOX4_DTYPE, int(lib().orc_geometry_count(s.h, 1))))
+    leaves = property(lambda s: s._read(10, np.uint32, len(s.aabbs)))  # CustomNode: the primitive index, in leaf order
 
     def __del__(self):
         try:

@@ -64,10 +64,53 @@ struct HostDim3
 	unsigned x = 1, y = 1, z = 1;
 };
 static HostDim3 threadIdx{ 0, 0, 0 }, blockIdx{ 0, 0, 0 }, blockDim, gridDim;
-#define HIPRT_B200_DEFAULT_FUNC_TABLE
 #include <hiprt/hiprt_device.h>
 
 using namespace hiprt;
+
+// The two dispatchers every translation unit that includes the device header provides (hiprtBuildTraceKernels generates them from the
+// function-name table): here they route to the host copies of the test kernels' custom intersection functions.
+typedef bool ( *HostIntersector )( const hiprtRay& ray, const void* data, void* payload, hiprtHit& hit );
+
+// tests/kernels/user_kernels.cu intersectCircle: a disc of radius 0.1 around (centres[primID], 0.5) in the plane z = 1
+static bool hostIntersectCircle( const hiprtRay& ray, const void* data, void*, hiprtHit& hit )
+{
+	const float dx = static_cast<const float*>( data )[hit.primID] - ray.origin.x;
+	const float dy = 0.5f - ray.origin.y;
+	if ( sqrtf( dx * dx + dy * dy ) >= 0.1f ) return false;
+	hit.t = ( 1.0f - ray.origin.z ) / ray.direction.z;
+	return true;
+}
+
+// tests/kernels/user_kernels.cu intersectSphere: data = float4 (centre, radius) per primitive
+static bool hostIntersectSphere( const hiprtRay& ray, const void* data, void*, hiprtHit& hit )
+{
+	const float4 s	= static_cast<const float4*>( data )[hit.primID];
+	const float3 oc = make_float3( ray.origin.x - s.x, ray.origin.y - s.y, ray.origin.z - s.z );
+	const float3 d	= ray.direction;
+	const float	 a	= d.x * d.x + d.y * d.y + d.z * d.z;
+	const float	 b	= 2.0f * ( oc.x * d.x + oc.y * d.y + oc.z * d.z );
+	const float	 c	= oc.x * oc.x + oc.y * oc.y + oc.z * oc.z - s.w * s.w;
+	const float	 disc = b * b - 4.0f * a * c;
+	if ( disc < 0.0f ) return false;
+	const float t = ( -b - sqrtf( disc ) ) / ( 2.0f * a );
+	if ( t < ray.minT || t > ray.maxT ) return false;
+	hit.t	   = t;
+	hit.normal = make_float3( oc.x + t * d.x, oc.y + t * d.y, oc.z + t * d.z );
+	hit.uv	   = make_float2( 0.0f, 0.0f );
+	return true;
+}
+
+static HostIntersector g_intersectors[8] = {};
+
+bool intersectFunc( uint32_t geomType, uint32_t rayType, const hiprtFuncTableHeader& tableHeader, const hiprtRay& ray, void* payload, hiprtHit& hit )
+{
+	const uint32_t index = tableHeader.numGeomTypes * rayType + geomType;
+	if ( index >= 8 || !g_intersectors[index] ) return false;
+	return g_intersectors[index]( ray, tableHeader.funcDataSets ? tableHeader.funcDataSets[index].intersectFuncData : nullptr, payload, hit );
+}
+
+bool filterFunc( uint32_t, uint32_t, const hiprtFuncTableHeader&, const hiprtRay&, void*, const hiprtHit& ) { return false; }
 
 static GeomHeader geometryHeader( const void* boxNodes, const void* leaves, uint32_t boxCount, uint32_t leafCount )
 {
@@ -154,6 +197,95 @@ void prod_trace_scene(
 			hiprtSceneTraversalAnyHit tr( reinterpret_cast<hiprtScene>( &s ), rays[i], rayMask );
 			hits[i] = tr.getNextHit();
 		}
+	}
+}
+
+// ---- general form: custom primitives through the function table, scenes instanced in scenes, animated instances ----------------
+// objects: children before parents. kind 0: triangle geometry, 1: custom-primitive geometry (leaves = CustomNode), 2: scene (leaves =
+// 64-byte instance nodes; childOfLeaf[l] = index of the object leaf l instances; frames = the scene's 64-byte key frames or null).
+struct HostObject
+{
+	uint32_t	kind, geomType;
+	const void* boxNodes;
+	const void* leaves;
+	uint32_t	leafCount, pad;
+	const uint32_t* childOfLeaf;
+	const void* frames;
+};
+
+// intersectorOfType[g]: 0 none, 1 circle, 2 sphere; dataOfType[g]: its data. maxPerRay == 0: closest hit (one record per ray);
+// otherwise every hit through the any-hit scene iterator (counts[i] hits, the first maxPerRay stored).
+void prod_trace_general(
+	const HostObject* objects, uint32_t objectCount, uint32_t root, uint32_t numGeomTypes, const uint32_t* intersectorOfType, const void* const* dataOfType,
+	const hiprtRay* rays, uint32_t n, float time, uint32_t maxPerRay, uint32_t* counts, hiprtHit* hits )
+{
+	std::vector<GeomHeader>				   geoms( objectCount );
+	std::vector<SceneHeader>			   scenes( objectCount );
+	std::vector<std::vector<InstanceNode>> nodes( objectCount );
+	for ( uint32_t k = 0; k < objectCount; ++k )
+	{
+		const HostObject& o = objects[k];
+		if ( o.kind != 2 )
+		{
+			geoms[k]		  = geometryHeader( o.boxNodes, o.leaves, 0, o.leafCount );
+			geoms[k].geomType = ( o.geomType << 1 ) | ( o.kind == 0 ? 1u : 0u );
+			continue;
+		}
+		nodes[k].resize( o.leafCount );
+		memcpy( nodes[k].data(), o.leaves, sizeof( InstanceNode ) * o.leafCount );
+		for ( uint32_t l = 0; l < o.leafCount; ++l )
+		{
+			const uint32_t child = o.childOfLeaf[l];
+			if ( objects[child].kind == 2 )
+				nodes[k][l].scene = &scenes[child];
+			else
+				nodes[k][l].geometry = &geoms[child];
+		}
+		scenes[k]				= SceneHeader{};
+		scenes[k].boxNodes		= static_cast<Box4Node*>( const_cast<void*>( o.boxNodes ) );
+		scenes[k].primNodes		= nodes[k].data();
+		scenes[k].frames		= static_cast<SRTFrame*>( const_cast<void*>( o.frames ) );
+		scenes[k].primCount		= o.leafCount;
+		scenes[k].primNodeCount = o.leafCount;
+	}
+	std::vector<hiprtFuncDataSet> sets( numGeomTypes );
+	for ( uint32_t g = 0; g < numGeomTypes; ++g )
+	{
+		sets[g].intersectFuncData = dataOfType[g];
+		g_intersectors[g]		  = intersectorOfType[g] == 1 ? hostIntersectCircle : intersectorOfType[g] == 2 ? hostIntersectSphere : nullptr;
+	}
+	hiprtFuncTableHeader table{ numGeomTypes, 1, sets.data() };
+	const hiprtFuncTable tablePtr = reinterpret_cast<hiprtFuncTable>( &table );
+	const bool			 isScene  = objects[root].kind == 2;
+	for ( uint32_t i = 0; i < n; ++i )
+	{
+		if ( maxPerRay == 0 )
+		{
+			if ( isScene )
+			{
+				hiprtSceneTraversalClosest tr( reinterpret_cast<hiprtScene>( &scenes[root] ), rays[i], hiprtFullRayMask, hiprtTraversalHintDefault, nullptr, tablePtr, 0, time );
+				hits[i] = tr.getNextHit();
+			}
+			else
+			{
+				hiprtGeomCustomTraversalClosest tr( reinterpret_cast<hiprtGeometry>( &geoms[root] ), rays[i], hiprtTraversalHintDefault, nullptr, tablePtr );
+				hits[i] = tr.getNextHit();
+			}
+			continue;
+		}
+		hiprtSceneTraversalAnyHit tr( reinterpret_cast<hiprtScene>( &scenes[root] ), rays[i], hiprtFullRayMask, hiprtTraversalHintDefault, nullptr, tablePtr, 0, time );
+		uint32_t				  c = 0;
+		while ( true )
+		{
+			const hiprtHit hit = tr.getNextHit();
+			if ( hit.hasHit() )
+			{
+				if ( c < maxPerRay ) hits[size_t( i ) * maxPerRay + c] = hit;
+				++c;
+			}
+			if ( tr.getCurrentState() != hiprtTraversalStateHit ) break;
+		}
+		counts[i] = c;
 	}
 }
 }

@@ -127,3 +127,90 @@ def test_scene_traversal_respects_instance_masks(product):
     G._check(G._colour_image(got), "RayMaskCornellBox")
     none = trace_scene(product, oscene, H.obj_camera_rays(64, 64), ray_mask=0)
     assert (none["primID"] == orc.INVALID).all()
+
+
+# ---- custom primitives through the function table, scenes instanced in scenes -----------------------------------------------------
+class HostObject(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("geomType", C.c_uint32), ("boxNodes", C.c_void_p), ("leaves", C.c_void_p), ("leafCount", C.c_uint32),
+                ("pad", C.c_uint32), ("childOfLeaf", C.c_void_p), ("frames", C.c_void_p)]
+
+
+def flatten(obj, table, keep):
+    """Depth-first object table for prod_trace_general (children before parents); returns the index of `obj`."""
+    if id(obj) in table["index"]:
+        return table["index"][id(obj)]
+    boxes, leaves = np.ascontiguousarray(obj.box_nodes), np.ascontiguousarray(obj.leaves)
+    keep += [boxes, leaves]
+    if isinstance(obj, orc.Scene):
+        children = [flatten(g, table, keep) for g in obj.geometries]
+        child_of_leaf = np.ascontiguousarray(np.asarray(children, np.uint32)[obj.geometry_of_instance[leaves["bits"] & 0xFFFFFF]])
+        keep.append(child_of_leaf)
+        rec = HostObject(2, 0, boxes.ctypes.data, leaves.ctypes.data, len(leaves), 0, child_of_leaf.ctypes.data, None)
+    elif isinstance(obj, orc.AabbGeometry):
+        rec = HostObject(1, obj.geom_type, boxes.ctypes.data, leaves.ctypes.data, len(leaves), 0, None, None)
+    else:
+        rec = HostObject(0, 0x7FFFFFFF, boxes.ctypes.data, leaves.ctypes.data, len(leaves), 0, None, None)
+    table["objects"].append(rec)
+    table["index"][id(obj)] = len(table["objects"]) - 1
+    return table["index"][id(obj)]
+
+
+def trace_general(L, obj, rays, intersectors=(), data=(), max_per_ray=0):
+    table, keep = {"objects": [], "index": {}}, []
+    root = flatten(obj, table, keep)
+    objects = (HostObject * len(table["objects"]))(*table["objects"])
+    kinds = np.asarray(list(intersectors) or [0], np.uint32)
+    arrays = [np.ascontiguousarray(a) for a in data] or [np.zeros(1, np.float32)]
+    ptrs = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+    rays = np.ascontiguousarray(rays, orc.RAY_DTYPE)
+    n = len(rays)
+    counts = np.zeros(n, np.uint32)
+    hits = np.zeros((n, max(max_per_ray, 1)), orc.HIT_DTYPE)
+    hits["primID"] = orc.INVALID
+    L.prod_trace_general(objects, len(objects), root, len(kinds), p(kinds), ptrs, p(rays), n, C.c_float(0.0), max_per_ray, p(counts), p(hits))
+    return hits[:, 0] if max_per_ray == 0 else (counts, hits)
+
+
+def test_custom_primitives_and_multi_level_scenes_reproduce_the_reference_images(product):
+    """CustomIntersection, SceneIntersection and SceneIntersectionMlas through the product's traversal objects on the CPU: the
+    function table, custom leaves next to triangles, the re-entrant any-hit scene iterator and the instance stack."""
+    from tests import test_oracle_custom as T
+
+    rays = T.unit_square_rays()
+    prim = trace_general(product, T.circles(0.0), rays, intersectors=[1], data=[T.CENTRES])["primID"]
+    colours = np.array([[255, 0], [0, 255], [255, 255], [0, 0]], np.uint8)
+    img = np.zeros((len(prim), 4), np.uint8)
+    img[:, :2] = colours[np.where(prim == orc.INVALID, 3, prim)]
+    img[:, 3] = 255
+    assert G._check(img, "CustomIntersection") == 0.0
+
+    srt = lambda dy: [0, 0, 1, 0, 1, 1, 1, 0, dy, 0, 0, 0]
+    tris = orc.Geometry(T.TRIANGLES, np.arange(9, dtype=np.uint32).reshape(3, 3))
+    mid = orc.Scene([T.circles(1.0), tris], [0, 1], np.array([srt(0.05), srt(-0.05)], np.float32), 0)
+    counts, hits = trace_general(product, mid, rays, intersectors=[1], data=[T.CENTRES], max_per_ray=4)
+    assert counts.max() <= 2
+    assert G._check(T.scene_image(counts, hits), "SceneIntersection") == 0.0
+
+    top = orc.Scene([mid], [0, 0], np.array([srt(0.12), srt(-0.12)], np.float32), 0)
+    counts, hits = trace_general(product, top, rays, intersectors=[1], data=[T.CENTRES], max_per_ray=8)
+    assert G._check(T.scene_image(counts, hits), "SceneIntersectionMlas") == 0.0
+    # the same hits as the oracle's walker, level by level
+    ocounts, ohits = orc.trace_general(top, rays, T.intersect_circle, max_per_ray=8)
+    assert np.array_equal(counts, ocounts)
+    key = lambda h: np.sort(h["instanceIDs"][:, :, 0].astype(np.int64) * 100 + h["instanceIDs"][:, :, 1].astype(np.int64) * 10 + h["primID"], 1)
+    assert np.array_equal(key(hits), key(ohits))
+
+
+def test_three_level_scene_closest_hits_equal_the_oracles(product):
+    meshes = scenes.instanced_geometries(3)
+    geoms = [orc.Geometry(v, i) for v, i in meshes]
+    leaf = orc.Scene(geoms, [k % 3 for k in range(6)], scenes.random_matrix_frames(6, seed=5, extent=2.0, scale_range=(0.6, 1.2)), 1)
+    mid = orc.Scene([leaf], [0] * 4, scenes.random_matrix_frames(4, seed=6, extent=6.0, scale_range=(0.8, 1.1)), 1)
+    top = orc.Scene([mid], [0] * 3, scenes.random_matrix_frames(3, seed=7, extent=14.0, scale_range=(0.9, 1.0)), 1)
+    rays = scenes.pinhole_rays(160, 160, (0.0, 4.0, 45.0), (0, 0, 0))
+    got = trace_general(product, top, rays)
+    ref = orc.trace_general(top, rays, tie_mode=1)
+    hit = ref["primID"] != orc.INVALID
+    assert hit.mean() > 0.03 and np.array_equal(got["primID"], ref["primID"])
+    assert np.array_equal(got["instanceIDs"][hit], ref["instanceIDs"][hit])
+    assert np.array_equal(got["t"][hit].view(np.uint32), ref["t"][hit].view(np.uint32))
