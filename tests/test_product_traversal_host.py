@@ -214,3 +214,59 @@ def test_three_level_scene_closest_hits_equal_the_oracles(product):
     assert hit.mean() > 0.03 and np.array_equal(got["primID"], ref["primID"])
     assert np.array_equal(got["instanceIDs"][hit], ref["instanceIDs"][hit])
     assert np.array_equal(got["t"][hit].view(np.uint32), ref["t"][hit].view(np.uint32))
+
+
+def test_animated_instance_reproduces_the_motion_blur_slerp_image(product):
+    """MotionBlurSlerp through the product's traversal objects on the CPU: a custom sphere (geometry type 1 of 2) under an ANIMATED
+    instance node -- the node carries the key-frame range, the scene header the 64-byte key frames (here the reference's own
+    decomposition of the identity and diag(-1, -1, 1), tests/golden/ref_math.npz), the instance box is the motion bound -- traced at
+    128 evenly spaced times per pixel of every fourth row and column (the reference draws 512 random times: its own sampling noise
+    is what remains)."""
+    from tests.golden import make_ref_math as M
+    from tests.test_oracle_ao import randf
+
+    f32 = np.float32
+    stored = np.ascontiguousarray(np.load(os.path.join(M.HERE, "ref_math.npz"))["motion_stored_12"])
+    assert stored.shape == (2, 16) and stored[1, 13] == 1.0 and np.array_equal(stored[1, :4], np.array([0, 0, 1, 0], f32))
+    sphere = orc.AabbGeometry(np.array([[-1.5, -0.5, -0.5, -0.5, 0.5, 0.5]], f32), geom_type=1)
+    scene = orc.Scene([sphere], [0], None, 0)
+    boxes, leaves = np.ascontiguousarray(scene.box_nodes), np.ascontiguousarray(scene.leaves)
+    # animated instance node: {frameIndex, frameCount} in place of the matrix, neither static nor identity (bits 25, 26)
+    leaves["invMatrix"][0, 0, :2] = np.array([0, 2], np.uint32).view(f32)
+    leaves["bits"][0] &= ~np.uint32((1 << 25) | (1 << 26))
+    bound = np.zeros((1, 6), f32)
+    keys = np.zeros((2, 16), f32)
+    keys[0, [0, 5, 10]] = 1.0
+    keys[1, [0, 5]], keys[1, 10], keys[1, 12] = -1.0, 1.0, 1.0
+    orc.lib().orc_math_motion_bounds(2, p(keys), 1, 1, p(sphere.aabbs), p(bound))
+    boxes["box"][0, 0] = bound.reshape(2, 3)
+    gboxes, gleaves = np.ascontiguousarray(sphere.box_nodes), np.ascontiguousarray(sphere.leaves)
+    child = np.zeros(1, np.uint32)
+    objects = (HostObject * 2)(HostObject(1, 1, gboxes.ctypes.data, gleaves.ctypes.data, 1, 0, None, None),
+                               HostObject(2, 0, boxes.ctypes.data, leaves.ctypes.data, 1, 0, child.ctypes.data, stored.ctypes.data))
+    kinds = np.array([0, 2], np.uint32)
+    spheres = np.array([[-1.0, 0.0, 0.0, 0.5]], f32)
+    ptrs = (C.c_void_p * 2)(None, spheres.ctypes.data)
+
+    res, stride, samples = 512, 4, 128
+    ys, xs = np.meshgrid(np.arange(0, res, stride, dtype=np.uint32), np.arange(0, res, stride, dtype=np.uint32), indexing="ij")
+    xs, ys = xs.reshape(-1), ys.reshape(-1)
+    seed = H.tea16(xs, ys)[0].astype(np.uint32)  # MotionBlurSlerpKernel's jitter (HiprtTestKernel.h:373-383)
+    dx = f32(2.0) * ((xs.astype(f32) + randf(seed)) / f32(res)) - f32(1.0)
+    dy = f32(2.0) * ((ys.astype(f32) + randf(seed)) / f32(res)) - f32(1.0)
+    d = np.stack([dx * f32(1.576494), dy * f32(1.576494), np.full_like(dx, -5.0)], -1).astype(f32)
+    d = (d / np.sqrt((d * d).sum(1, dtype=f32), dtype=f32)[:, None]).astype(f32)
+    rays = orc.make_rays(np.broadcast_to(np.array([0, 0, 5], f32), d.shape), d)
+    n = len(rays)
+    count = np.zeros(n, np.int64)
+    counts, hits = np.zeros(n, np.uint32), np.zeros(n, orc.HIT_DTYPE)
+    for k in range(samples):
+        product.prod_trace_general(objects, 2, 1, 2, p(kinds), ptrs, p(rays), n, C.c_float((k + 0.5) / samples), 0, p(counts), p(hits))
+        count += hits["primID"] != orc.INVALID
+    frac = (count / samples).astype(f32)[:, None]
+    colour = frac * np.array([0.9, 0.1, 0.1], f32) + (f32(1.0) - frac) * f32(0.1)
+    img = (np.power(colour, f32(1.0 / 2.2)) * f32(255)).astype(np.uint8)
+    golden = H.load_golden_image("MotionBlurSlerp")[::stride, ::stride, :3].reshape(-1, 3)
+    diff = np.abs(img.astype(np.int64) - golden.astype(np.int64)).max(1)
+    assert 0.3 < (count > 0).mean() < 0.5
+    assert (diff > 10).mean() < 0.005, ((diff > 10).mean(), diff.max())
