@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #define __CUDACC__ 1
@@ -141,6 +142,39 @@ void prod_trace_geometry( const void* boxNodes, const void* leaves, uint32_t box
 			hits[i] = tr.getNextHit();
 		}
 	}
+}
+
+// the same closest-hit query with the traversal stack in "shared" + "global" memory (hiprtGlobalStack / hiprtDynamicStack): a ring of
+// sharedSize entries that spills its oldest entry to the global region. One host thread is lane 0 of warp 0 of block 0.
+void prod_trace_geometry_global_stack(
+	const void* boxNodes, const void* leaves, uint32_t boxCount, uint32_t leafCount, const hiprtRay* rays, uint32_t n, hiprtHit* hits, uint32_t sharedSize,
+	uint32_t globalSize, int dynamic, uint32_t* maxStateOut )
+{
+	GeomHeader			  h = geometryHeader( boxNodes, leaves, boxCount, leafCount );
+	std::vector<uint32_t> shared( 32u * ( sharedSize + 1 ) ), global( 64u + 32u * 32u * ( globalSize + 1 ) );
+	hiprtSharedStackBuffer sharedBuffer{ sharedSize, shared.data() };
+	hiprtGlobalStackBuffer globalBuffer{ globalSize, 32u * 32u, global.data() }; // 32 warp slots: the dynamic variant locks one of them
+	uint32_t			   worst = 0;
+	for ( uint32_t i = 0; i < n; ++i )
+	{
+		if ( dynamic )
+		{
+			hiprtDynamicStack									  stack( globalBuffer, sharedBuffer );
+			hiprtGeomTraversalClosestCustomStack<hiprtDynamicStack> tr( reinterpret_cast<hiprtGeometry>( &h ), rays[i], stack );
+			hits[i] = tr.getNextHit();
+			worst	= std::max<uint32_t>( worst, tr.getCurrentState() );
+		}
+		else
+		{
+			hiprtGlobalStack									 stack( globalBuffer, sharedBuffer );
+			hiprtGeomTraversalClosestCustomStack<hiprtGlobalStack> tr( reinterpret_cast<hiprtGeometry>( &h ), rays[i], stack );
+			hits[i] = tr.getNextHit();
+			worst	= std::max<uint32_t>( worst, tr.getCurrentState() );
+		}
+	}
+	if ( maxStateOut ) *maxStateOut = worst;
+	for ( uint32_t k = 0; k < 32; ++k ) // every lock of the dynamic variant must have been released
+		if ( dynamic && global[k] != 0 && maxStateOut ) *maxStateOut = 0xFFFFFFFFu;
 }
 
 // every hit along the ray through the re-entrant any-hit iterator; returns the total number of hits

@@ -270,3 +270,23 @@ def test_animated_instance_reproduces_the_motion_blur_slerp_image(product):
     diff = np.abs(img.astype(np.int64) - golden.astype(np.int64)).max(1)
     assert 0.3 < (count > 0).mean() < 0.5
     assert (diff > 10).mean() < 0.005, ((diff > 10).mean(), diff.max())
+
+
+@pytest.mark.parametrize("dynamic", [0, 1])
+@pytest.mark.parametrize("shared_size", [0, 1, 2, 16])
+def test_global_and_dynamic_stacks_spill_and_refill_correctly(product, dynamic, shared_size):
+    """hiprtGlobalStack / hiprtDynamicStack (hiprt_device.h; reference hiprt_device_impl.h:86-247): with a "shared" ring of 0, 1, 2
+    or 16 entries in front of the global region, every push beyond the ring spills the oldest entry and every pop past it refills
+    from the global region; the hits must be those of the private stack, bit for bit, and the dynamic variant must release its
+    warp slot."""
+    v, i = scenes.sphere_mesh(128, 64)
+    og = orc.Geometry(v, i)
+    rays = scenes.random_rays(6000, [-1.2, -1.2, -1.2], [1.2, 1.2, 1.2], seed=9)
+    ref = trace_geometry(product, og, rays)
+    boxes, leaves = np.ascontiguousarray(og.box_nodes), np.ascontiguousarray(og.leaves)
+    hits = np.zeros(len(rays), orc.HIT_DTYPE)
+    state = C.c_uint32(0)
+    product.prod_trace_geometry_global_stack(p(boxes), p(leaves), len(boxes), len(leaves), p(rays), len(rays), p(hits), shared_size, 64, dynamic, C.byref(state))
+    assert state.value == 1, state.value  # hiprtTraversalStateFinished (1) for every ray: no overflow (3), locks released
+    assert (ref["primID"] != orc.INVALID).mean() > 0.3
+    assert_same_hits(hits, ref)
