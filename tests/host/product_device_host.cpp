@@ -111,7 +111,25 @@ bool intersectFunc( uint32_t geomType, uint32_t rayType, const hiprtFuncTableHea
 	return g_intersectors[index]( ray, tableHeader.funcDataSets ? tableHeader.funcDataSets[index].intersectFuncData : nullptr, payload, hit );
 }
 
-bool filterFunc( uint32_t, uint32_t, const hiprtFuncTableHeader&, const hiprtRay&, void*, const hiprtHit& ) { return false; }
+// the reference's Cutout test filter (cutoutFilter, HiprtTestKernel.h:88-100) for the unit quad of two triangles: texture
+// coordinates interpolated from hit.uv per primitive, a 16 x 16 checkerboard of holes; true REJECTS the hit
+static bool hostCutoutFilter( const hiprtRay&, const void*, void*, const hiprtHit& hit )
+{
+	const float u = hit.uv.x, v = hit.uv.y;
+	const float tx = hit.primID == 0 ? v : u + v;
+	const float ty = hit.primID == 0 ? u + v : u;
+	return ( ( uint32_t( 16.0f * tx ) + uint32_t( 16.0f * ty ) ) & 1u ) != 0u;
+}
+
+typedef bool ( *HostFilter )( const hiprtRay& ray, const void* data, void* payload, const hiprtHit& hit );
+static HostFilter g_filters[8] = {};
+
+bool filterFunc( uint32_t geomType, uint32_t rayType, const hiprtFuncTableHeader& tableHeader, const hiprtRay& ray, void* payload, const hiprtHit& hit )
+{
+	const uint32_t index = tableHeader.numGeomTypes * rayType + geomType;
+	if ( index >= 8 || !g_filters[index] ) return false;
+	return g_filters[index]( ray, tableHeader.funcDataSets ? tableHeader.funcDataSets[index].filterFuncData : nullptr, payload, hit );
+}
 
 static GeomHeader geometryHeader( const void* boxNodes, const void* leaves, uint32_t boxCount, uint32_t leafCount )
 {
@@ -125,6 +143,12 @@ static GeomHeader geometryHeader( const void* boxNodes, const void* leaves, uint
 }
 
 extern "C" {
+// hit filter of a function-table slot: 0 none, 1 the Cutout checkerboard
+void prod_set_filter( uint32_t index, uint32_t kind )
+{
+	if ( index < 8 ) g_filters[index] = kind == 1 ? hostCutoutFilter : nullptr;
+}
+
 // kind 2: closest hit, 1: any hit (hiprtTraversalType)
 void prod_trace_geometry( const void* boxNodes, const void* leaves, uint32_t boxCount, uint32_t leafCount, const hiprtRay* rays, uint32_t n, hiprtHit* hits, int kind )
 {
@@ -300,9 +324,14 @@ void prod_trace_general(
 				hiprtSceneTraversalClosest tr( reinterpret_cast<hiprtScene>( &scenes[root] ), rays[i], hiprtFullRayMask, hiprtTraversalHintDefault, nullptr, tablePtr, 0, time );
 				hits[i] = tr.getNextHit();
 			}
-			else
+			else if ( objects[root].kind == 1 )
 			{
 				hiprtGeomCustomTraversalClosest tr( reinterpret_cast<hiprtGeometry>( &geoms[root] ), rays[i], hiprtTraversalHintDefault, nullptr, tablePtr );
+				hits[i] = tr.getNextHit();
+			}
+			else
+			{
+				hiprtGeomTraversalClosest tr( reinterpret_cast<hiprtGeometry>( &geoms[root] ), rays[i], hiprtTraversalHintDefault, nullptr, tablePtr );
 				hits[i] = tr.getNextHit();
 			}
 			continue;

@@ -149,7 +149,8 @@ def flatten(obj, table, keep):
     elif isinstance(obj, orc.AabbGeometry):
         rec = HostObject(1, obj.geom_type, boxes.ctypes.data, leaves.ctypes.data, len(leaves), 0, None, None)
     else:
-        rec = HostObject(0, 0x7FFFFFFF, boxes.ctypes.data, leaves.ctypes.data, len(leaves), 0, None, None)
+        # (no user geometry type unless the test gives one: 0x7FFFFFFF << 1 | 1 is the "invalid" type of a plain triangle mesh)
+        rec = HostObject(0, getattr(obj, "host_geom_type", 0x7FFFFFFF), boxes.ctypes.data, leaves.ctypes.data, len(leaves), 0, None, None)
     table["objects"].append(rec)
     table["index"][id(obj)] = len(table["objects"]) - 1
     return table["index"][id(obj)]
@@ -290,3 +291,24 @@ def test_global_and_dynamic_stacks_spill_and_refill_correctly(product, dynamic, 
     assert state.value == 1, state.value  # hiprtTraversalStateFinished (1) for every ray: no overflow (3), locks released
     assert (ref["primID"] != orc.INVALID).mean() > 0.3
     assert_same_hits(hits, ref)
+
+
+def test_hit_filter_on_triangles_reproduces_the_cutout_image(product):
+    """Cutout (test/main.cpp:1219-1290): the unit quad with a user geometry type, closest hit with the checkerboard hit filter in
+    function-table slot 0 -- the filter runs inside the product's traversal, a rejected hit is not reported."""
+    v = np.array([[0, 0, 0], [0, 1, 0], [1, 1, 0], [1, 0, 0]], np.float32)
+    quad = orc.Geometry(v, np.array([[0, 1, 2], [0, 2, 3]], np.uint32))
+    quad.host_geom_type = 0
+    rays = H.ortho_rays()
+    product.prod_set_filter(0, 1)
+    try:
+        filtered = trace_general(product, quad, rays, intersectors=[0], data=[np.zeros(1, np.float32)])
+    finally:
+        product.prod_set_filter(0, 0)
+    plain = trace_general(product, quad, rays, intersectors=[0], data=[np.zeros(1, np.float32)])
+    visible = filtered["primID"] != orc.INVALID
+    assert (plain["primID"] != orc.INVALID).mean() > 0.99 and 0.4 < visible.mean() < 0.6
+    img = np.zeros((len(rays), 4), np.uint8)
+    img[:, :3] = np.where(visible, 255, 0)[:, None]
+    img[:, 3] = 255
+    G._check(img, "Cutout")
