@@ -351,4 +351,53 @@ void prod_trace_general(
 		counts[i] = c;
 	}
 }
+
+// The transform query functions of the device API (hiprtPoint/VectorObjectToWorld/WorldToObject) for instance 0 of a scene whose only
+// instance has the given 64-byte key frames: per input vector the four results, in the order object->world point, world->object point,
+// object->world vector, world->object vector. twoLevels != 0: the instance sits, under an identity frame, inside an outer scene and the
+// multi-level overloads are used.
+void prod_transform_queries( const void* keyFrames, uint32_t frameCount, float time, uint32_t n, const float* in, float* out, int twoLevels )
+{
+	InstanceRecord record{};
+	record.frameIndex = 0;
+	record.frameCount = frameCount;
+	record.type		  = hiprtInstanceTypeGeometry;
+	SceneHeader inner{};
+	inner.instances	 = &record;
+	inner.frames	 = static_cast<SRTFrame*>( const_cast<void*>( keyFrames ) );
+	inner.frameCount = frameCount;
+	inner.primCount	 = 1;
+	SRTFrame identity{};
+	identity.rotation = { 0.0f, 0.0f, 0.0f, 1.0f };
+	identity.scale	  = { 1.0f, 1.0f, 1.0f };
+	InstanceRecord outerRecord{};
+	outerRecord.frameIndex = 0;
+	outerRecord.frameCount = 1;
+	outerRecord.type	   = hiprtInstanceTypeScene;
+	outerRecord.scene	   = &inner;
+	SceneHeader outer{};
+	outer.instances	 = &outerRecord;
+	outer.frames	 = &identity;
+	outer.frameCount = 1;
+	outer.primCount	 = 1;
+	const uint32_t ids[hiprtMaxInstanceLevels] = { 0, 0, hiprtInvalidValue, hiprtInvalidValue };
+	for ( uint32_t i = 0; i < n; ++i )
+	{
+		const float3 p = make_float3( in[3 * i], in[3 * i + 1], in[3 * i + 2] );
+		float3		 r[4];
+		if ( twoLevels )
+		{
+			const hiprtScene s = reinterpret_cast<hiprtScene>( &outer );
+			r[0] = hiprtPointObjectToWorld( p, s, ids, time ), r[1] = hiprtPointWorldToObject( p, s, ids, time );
+			r[2] = hiprtVectorObjectToWorld( p, s, ids, time ), r[3] = hiprtVectorWorldToObject( p, s, ids, time );
+		}
+		else
+		{
+			const hiprtScene s = reinterpret_cast<hiprtScene>( &inner );
+			r[0] = hiprtPointObjectToWorld( p, s, 0u, time ), r[1] = hiprtPointWorldToObject( p, s, 0u, time );
+			r[2] = hiprtVectorObjectToWorld( p, s, 0u, time ), r[3] = hiprtVectorWorldToObject( p, s, 0u, time );
+		}
+		memcpy( out + 12 * i, r, sizeof( r ) );
+	}
+}
 }

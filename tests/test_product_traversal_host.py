@@ -312,3 +312,21 @@ def test_hit_filter_on_triangles_reproduces_the_cutout_image(product):
     img[:, :3] = np.where(visible, 255, 0)[:, None]
     img[:, 3] = 255
     G._check(img, "Cutout")
+
+
+@pytest.mark.parametrize("two_levels", [0, 1])
+def test_transform_queries_are_the_references(product, two_levels):
+    """hiprtPoint/VectorObjectToWorld/WorldToObject of the device API (reference: hiprt_device.h:508-583) against the reference's
+    SRTFrame::transform / invTransform / transformVector / invTransformVector under Transform::interpolateFrames, bit for bit
+    (tests/golden/ref_math.npz), through the single-level signature and through the multi-level one with an identity outer level."""
+    from tests.golden import make_ref_math as M
+
+    golden = np.load(os.path.join(M.HERE, "ref_math.npz"))
+    inputs = M.ref_math_inputs()
+    pts = np.ascontiguousarray(inputs["motion_rays"].view(M.RAY).reshape(-1)["direction"][:100])
+    for j in range(int(inputs["motion_count"])):
+        stored = np.ascontiguousarray(golden[f"motion_stored_{j}"])
+        for k, time in enumerate(M.POINT_TIMES):
+            out = np.zeros((len(pts), 12), np.float32)
+            product.prod_transform_queries(p(stored), len(stored), C.c_float(time), len(pts), p(pts), p(out), two_levels)
+            assert np.array_equal(out.view(np.uint32), golden[f"motion_points_{j}"][k].view(np.uint32)), (j, time)
