@@ -330,3 +330,26 @@ def test_transform_queries_are_the_references(product, two_levels):
             out = np.zeros((len(pts), 12), np.float32)
             product.prod_transform_queries(p(stored), len(stored), C.c_float(time), len(pts), p(pts), p(out), two_levels)
             assert np.array_equal(out.view(np.uint32), golden[f"motion_points_{j}"][k].view(np.uint32)), (j, time)
+
+
+def test_exact_ties_are_broken_towards_the_smaller_ids(product):
+    """"Ties broken deterministically": every triangle of the Cornell box exists twice (primitives p and p + 32 at the same place)
+    and the doubled geometry is instanced twice under the same frame, so EVERY hit is a four-way exact tie in t. The product's
+    traversal objects and the oracle's order-independent rule (min over t, instanceID, primID) must both report instance 0 and
+    the lower primitive, whatever order the BVH visits them in."""
+    verts, _, _ = H.cornell_box()
+    doubled = np.concatenate([verts, verts])
+    og = orc.Geometry(doubled, np.arange(192, dtype=np.uint32).reshape(-1, 3), allow_pairing=False)
+    rays = H.cornell_rays(160, 160)
+    single = orc.Geometry(verts, np.arange(96, dtype=np.uint32).reshape(-1, 3)).trace(rays, tie_mode=1)
+    hit = single["primID"] != orc.INVALID
+    for hits in (trace_geometry(product, og, rays), og.trace(rays, tie_mode=1)):
+        assert np.array_equal(hits["primID"], single["primID"]) and (hits["primID"][hit] < 32).all()
+        assert np.array_equal(hits["t"][hit].view(np.uint32), single["t"][hit].view(np.uint32))
+    frame = np.tile(np.asarray([0, 1, 0, 0.3, 1, 1, 1, 5, 0, 0, 0, 0], np.float32), (2, 1))
+    oscene = orc.Scene([og], [0, 0], frame, 0)
+    one = orc.Scene([og], [0], frame[:1], 0).trace(rays, tie_mode=1)
+    for hits in (trace_scene(product, oscene, rays), oscene.trace(rays, tie_mode=1)):
+        h = hits["primID"] != orc.INVALID
+        assert h.mean() > 0.3 and np.array_equal(hits["primID"], one["primID"])
+        assert (hits["instanceIDs"][h, 0] == 0).all() and (hits["primID"][h] < 32).all()
