@@ -127,3 +127,27 @@ def test_custom_spheres_in_a_scene_against_the_oracle(ctx):
     scene.destroy()
     g_mesh.destroy()
     ctx.destroy_geometry(g_spheres)
+
+
+def test_library_kernels_break_exact_ties_towards_the_smaller_ids(ctx):
+    """The four-way exact ties of tests/test_product_traversal_host.py::test_exact_ties_are_broken_towards_the_smaller_ids through
+    the library's own trace kernels (csrc/trace_kernels.cu): doubled Cornell box, instanced twice under the same frame."""
+    from tests import helpers as H
+
+    verts, _, _ = H.cornell_box()
+    doubled = np.concatenate([verts, verts])
+    idx = np.arange(192, dtype=np.uint32).reshape(-1, 3)
+    rays = H.cornell_rays(160, 160)
+    d_rays = ctx.rays_to_device(rays)
+    geom = ctx.build(to_dev(ctx, doubled), to_dev(ctx, idx), flags=api.FAST_BUILD | api.DISABLE_PAIRING)
+    single = orc.Geometry(verts, np.arange(96, dtype=np.uint32).reshape(-1, 3)).trace(rays, tie_mode=1)
+    hit = single["primID"] != orc.INVALID
+    got = ctx.hits_to_host(ctx.trace(geom, d_rays))
+    assert np.array_equal(got["primID"], single["primID"]) and (got["primID"][hit] < 32).all()
+    frame = np.tile(np.asarray([0, 1, 0, 0.3, 1, 1, 1, 5, 0, 0, 0, 0], np.float32), (2, 1))
+    scene = ctx.build_scene([geom, geom], frame, frame_type=api.FRAME_SRT)
+    got = ctx.hits_to_host(ctx.trace(scene, d_rays))
+    h = got["primID"] != api.INVALID
+    assert h.mean() > 0.3 and (got["instanceIDs"][h, 0] == 0).all() and (got["primID"][h] < 32).all()
+    scene.destroy()
+    geom.destroy()
