@@ -158,6 +158,14 @@ class Context
 
 	~Context()
 	{
+		// `modules` unloads its CUmodules when the members are destroyed: make this context's device current for that
+		try
+		{
+			bind();
+		}
+		catch ( ... )
+		{
+		}
 		if ( m_profileEventsCreated )
 			for ( auto& e : m_profile.events )
 				cudaEventDestroy( e );
@@ -251,8 +259,9 @@ class Context
 		}
 	}
 
-	std::string		  cacheDir;
-	HostTracePipeline hostPipeline;
+	std::string			  cacheDir;
+	HostTracePipeline	  hostPipeline;
+	compiler::ModuleCache modules; // user trace kernels loaded into THIS context's CUDA context
 
 	// ---- primitive kind of built geometries (chooses the library trace kernel without a device read) ----
 	void noteGeometryKind( void* geometry, bool triangles )
@@ -915,7 +924,7 @@ hiprtError hiprtBuildTraceKernels(
 	return guarded( context, [&] {
 		Context* c = ctx( context );
 		compiler::buildTraceKernels(
-			c->ccMajor(), c->ccMinor(), numFunctions, funcNames, src, moduleName ? moduleName : "hiprt_user_module", numHeaders, headers,
+			c->modules, c->ccMajor(), c->ccMinor(), numFunctions, funcNames, src, moduleName ? moduleName : "hiprt_user_module", numHeaders, headers,
 			includeNames, numOptions, options, numGeomTypes, numRayTypes, funcNameSets, functionsOut, moduleOut );
 	} );
 }
@@ -939,7 +948,7 @@ hiprtError hiprtBuildTraceKernelsFromBitcode(
 	return guarded( context, [&] {
 		Context* c = ctx( context );
 		compiler::buildTraceKernelsFromBitcode(
-			c->ccMajor(), c->ccMinor(), numFunctions, funcNames, moduleName ? moduleName : "hiprt_user_module", bitcodeBinary, bitcodeBinarySize,
+			c->modules, c->ccMajor(), c->ccMinor(), numFunctions, funcNames, moduleName ? moduleName : "hiprt_user_module", bitcodeBinary, bitcodeBinarySize,
 			numGeomTypes, numRayTypes, funcNameSets, functionsOut );
 	} );
 }

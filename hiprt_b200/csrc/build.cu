@@ -367,18 +367,16 @@ void buildScene(
 	primBoxesKernel<InstanceSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
 	runLbvh( dev, src, balanced, n, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
 }
-// Refit in place (hiprtBuildOperationUpdate): same primitive count and order as the build, moved positions.
+// Refit in place (hiprtBuildOperationUpdate): same primitive count and order as the build, moved positions. The kernels take
+// the node arrays from the device header, so a compacted, loaded or imported structure is updated where it actually lies.
 void updateGeometry(
 	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions, void*, cudaStream_t stream, void* storage )
 {
 	(void)dev;
-	const uint32_t nMax = uint32_t( geometryPrimCount( input ) );
+	const uint32_t nMax = uint32_t( std::max( geometryPrimCount( input ), importLeafCount( input ) ) );
 	if ( nMax == 0 ) throw std::runtime_error( "empty geometry" );
-	uint8_t*	out		  = static_cast<uint8_t*>( storage );
-	GeomHeader* header	  = reinterpret_cast<GeomHeader*>( out );
-	Box4Node*	boxNodes  = reinterpret_cast<Box4Node*>( out + alignUp( sizeof( GeomHeader ) ) );
-	void*		leafNodes = out + alignUp( sizeof( GeomHeader ) ) + alignUp( maxBoxNodeCount( nMax ) * sizeof( Box4Node ) );
-	const uint32_t grid	  = DivideRoundUp( uint32_t( maxBoxNodeCount( nMax ) ), 128u );
+	const GeomHeader* header = static_cast<const GeomHeader*>( storage );
+	const uint32_t	  grid	 = DivideRoundUp( uint32_t( maxBoxNodeCount( nMax ) ), 128u ); // upper bound; trimmed by header->boxNodeCount
 	if ( input.type == hiprtPrimitiveTypeTriangleMesh )
 	{
 		const auto&		   m = input.primitive.triangleMesh;
@@ -388,13 +386,13 @@ void updateGeometry(
 		src.triangles	   = ( m.triangleCount == 0 ) ? nullptr : static_cast<const uint8_t*>( m.triangleIndices );
 		src.triangleStride = m.triangleStride;
 		src.pairs		   = nullptr; // the pairing is read back from the leaves
-		refitKernel<TriangleMeshSource><<<grid, 128, 0, stream>>>( src, &header->boxNodeCount, boxNodes, leafNodes );
+		refitKernel<TriangleMeshSource><<<grid, 128, 0, stream>>>( src, header, &header->boxNodeCount );
 	}
 	else
 	{
 		const auto&	   a = input.primitive.aabbList;
 		AabbListSource src{ static_cast<const uint8_t*>( a.aabbs ), a.aabbStride };
-		refitKernel<AabbListSource><<<grid, 128, 0, stream>>>( src, &header->boxNodeCount, boxNodes, leafNodes );
+		refitKernel<AabbListSource><<<grid, 128, 0, stream>>>( src, header, &header->boxNodeCount );
 	}
 	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
@@ -405,23 +403,18 @@ void updateScene(
 	(void)dev;
 	const uint32_t n = input.instanceCount;
 	if ( n == 0 ) throw std::runtime_error( "empty scene" );
-	const SceneLayout S			= sceneLayout( input );
-	uint8_t*		  out		= static_cast<uint8_t*>( storage );
-	SceneHeader*	  header	= reinterpret_cast<SceneHeader*>( out );
-	Box4Node*		  boxNodes	= reinterpret_cast<Box4Node*>( out + S.boxNodes );
-	InstanceNode*	  instNodes = reinterpret_cast<InstanceNode*>( out + S.primNodes );
-	InstanceRecord*	  records	= reinterpret_cast<InstanceRecord*>( out + S.instances );
-	SRTFrame*		  frames	= reinterpret_cast<SRTFrame*>( out + S.frames );
-	InstanceSource	  src{};
+	const SceneHeader* header = static_cast<const SceneHeader*>( storage );
+	InstanceSource	   src{};
 	src.instances  = static_cast<const hiprtInstance*>( input.instances );
 	src.headers	   = static_cast<const hiprtTransformHeader*>( input.instanceTransformHeaders );
-	src.frames	   = ( input.frameCount > 0 && input.instanceFrames != nullptr ) ? frames : nullptr;
+	// non-null = "this scene has converted frames"; the kernels replace it by header->frames
+	src.frames	   = ( input.frameCount > 0 && input.instanceFrames != nullptr ) ? reinterpret_cast<const SRTFrame*>( storage ) : nullptr;
 	src.masks	   = static_cast<const uint32_t*>( input.instanceMasks );
 	src.frameCount = input.frameCount;
 	const uint32_t work = std::max( n, input.frameCount );
 	updateSceneInputsKernel<<<DivideRoundUp( work, 256u ), 256, 0, stream>>>(
-		records, frames, src, n, input.instanceFrames, input.frameType == hiprtFrameTypeMatrix );
-	refitKernel<InstanceSource><<<DivideRoundUp( uint32_t( maxBoxNodeCount( n ) ), 128u ), 128, 0, stream>>>( src, &header->boxNodeCount, boxNodes, instNodes );
+		header, src, n, input.instanceFrames, input.frameType == hiprtFrameTypeMatrix );
+	refitKernel<InstanceSource><<<DivideRoundUp( uint32_t( maxBoxNodeCount( n ) ), 128u ), 128, 0, stream>>>( src, header, &header->boxNodeCount );
 	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
 

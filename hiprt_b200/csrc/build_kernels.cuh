@@ -855,11 +855,25 @@ __device__ __forceinline__ DBox refreshLeaf<InstanceSource>( const InstanceSourc
 	return src.box( p );
 }
 
+// The node arrays are taken from the structure's own header (both header kinds start with {boxNodes, primNodes}; a scene's
+// converted frames follow at `framesPtr`): after hiprtCompactGeometry / hiprtCompactScene, hiprtLoadGeometry or a custom-BVH
+// import they do not sit where a fresh build of the same input would put them (reference: LbvhBuilder.h:445-452 reads the header back).
 template <typename Source>
-__global__ void __launch_bounds__( 128 ) refitKernel( Source src, const uint32_t* boxNodeCount, Box4Node* boxNodes, void* leafNodes )
+__device__ __forceinline__ void rebaseSource( Source&, const void* ) {}
+template <>
+__device__ __forceinline__ void rebaseSource<InstanceSource>( InstanceSource& src, const void* header )
+{
+	if ( src.frames != nullptr ) src.frames = static_cast<const SceneHeader*>( header )->frames;
+}
+
+template <typename Source>
+__global__ void __launch_bounds__( 128 ) refitKernel( Source src, const void* header, const uint32_t* boxNodeCount )
 {
 	uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
 	if ( node >= *boxNodeCount ) return;
+	Box4Node* const boxNodes  = static_cast<Box4Node* const*>( header )[0];
+	void* const		leafNodes = static_cast<void* const*>( header )[1];
+	rebaseSource<Source>( src, header );
 	uint32_t* words = reinterpret_cast<uint32_t*>( boxNodes + node );
 	const uint4 children = *reinterpret_cast<const uint4*>( words );
 	const uint32_t c[4]	 = { children.x, children.y, children.z, children.w };
@@ -915,9 +929,11 @@ __global__ void __launch_bounds__( 128 ) refitKernel( Source src, const uint32_t
 // Scene update: refresh the per-instance records and the converted frames (the part of initSceneKernel that
 // depends on the inputs), leaving header counters and topology alone.
 __global__ void __launch_bounds__( 256 ) updateSceneInputsKernel(
-	InstanceRecord* records, SRTFrame* frames, InstanceSource src, uint32_t instanceCount, const void* apiFrames, bool matrixFrames )
+	const SceneHeader* header, InstanceSource src, uint32_t instanceCount, const void* apiFrames, bool matrixFrames )
 {
-	const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t	index	= blockIdx.x * blockDim.x + threadIdx.x;
+	InstanceRecord* records = header->instances;
+	SRTFrame*		frames	= header->frames;
 	if ( index < instanceCount )
 	{
 		const hiprtInstance		   inst = src.instances[index];

@@ -6,7 +6,10 @@
 #pragma once
 #include <hiprt/hiprt_types.h>
 
+#include <map>
+#include <mutex>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace hiprt
@@ -20,7 +23,27 @@ struct NotAvailable : std::runtime_error
 
 void setCurrentContext( void* cuContext );
 
+// Loaded modules of ONE hiprtContext, keyed by source + options (+ function table). CUmodule / CUfunction handles belong to the
+// CUDA context they were loaded in, so the cache lives in the hiprtContext (as the reference's does: Compiler is a member of
+// Context) and is unloaded with it.
+class ModuleCache
+{
+  public:
+	ModuleCache() = default;
+	ModuleCache( const ModuleCache& ) = delete;
+	ModuleCache& operator=( const ModuleCache& ) = delete;
+	~ModuleCache();
+	void*  find( const std::string& key );
+	void*  insert( const std::string& key, void* module ); // returns the module kept (an earlier one if another thread won)
+	size_t size();
+
+  private:
+	std::map<std::string, void*> m_modules;
+	std::mutex					 m_mutex;
+};
+
 void buildTraceKernels(
+	ModuleCache&	  cache,
 	int				  ccMajor,
 	int				  ccMinor,
 	uint32_t		  numFunctions,
@@ -46,6 +69,7 @@ std::vector<char> linkTraceKernels(
 	int ccMajor, int ccMinor, const char* bitcode, size_t bitcodeSize, const char* moduleName, uint32_t numGeomTypes, uint32_t numRayTypes, hiprtFuncNameSet* funcNameSets );
 
 void buildTraceKernelsFromBitcode(
+	ModuleCache&	  cache,
 	int				  ccMajor,
 	int				  ccMinor,
 	uint32_t		  numFunctions,

@@ -1,9 +1,6 @@
 """GPU: hiprtBuildTraceKernelsFromBitcode end to end -- the test kernels compiled offline by nvcc as relocatable device code,
 linked with the generated dispatchers, loaded and launched -- must return exactly the hits of the same kernel built from source
-through hiprtBuildTraceKernels (NVRTC). The link step itself is covered without a GPU by tests/test_bitcode_link.py.
-
-This file was written after the round's GPU budget was spent: it has not run on a GPU yet, hence the non-strict xfail marker
-(remove it once it has passed on a B200)."""
+through hiprtBuildTraceKernels (NVRTC). The link step itself is covered without a GPU by tests/test_bitcode_link.py."""
 import ctypes as C
 import os
 import shutil
@@ -16,7 +13,7 @@ from hiprt_b200 import api, scenes
 from tests.test_gpu_parity import to_dev
 from tests.test_gpu_user_kernels import Launcher, build_kernels, dev_ptr
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first run on a GPU pending (no GPU minutes were left when it was written)", strict=False)]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 

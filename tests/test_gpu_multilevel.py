@@ -1,10 +1,7 @@
 """GPU parity of the two paths that so far were held to pictures only -- custom primitives through the function table and scenes
 instanced in scenes -- against the oracle's general traversal (oracle/hiprt_oracle.cpp walkScene / walkGeometry, itself pinned
 by the reference's CustomIntersection / SceneIntersection / SceneIntersectionMlas images in tests/test_oracle_custom.py):
-primID and every level of instanceIDs exact, t within 1e-5 relative.
-
-Written after the round's GPU budget was spent: these tests have not run on a GPU yet, hence the non-strict xfail marker (remove it
-once they have passed on a B200)."""
+primID and every level of instanceIDs exact, t within 1e-5 relative."""
 import ctypes as C
 
 import numpy as np
@@ -15,7 +12,7 @@ from oracle import binding as orc
 from tests.test_gpu_parity import to_dev
 from tests.test_gpu_user_kernels import Launcher, build_kernels, dev_ptr
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="first run on a GPU pending (no GPU minutes were left when it was written)", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
