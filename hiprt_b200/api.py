@@ -26,6 +26,9 @@ PRIM_TRIANGLE_MESH, PRIM_AABB_LIST = 0, 1
 INSTANCE_GEOMETRY, INSTANCE_SCENE = 0, 1
 FRAME_SRT, FRAME_MATRIX = 0, 1
 ANY_HIT, CLOSEST_HIT = 1, 2
+FORMAT_FULL, FORMAT_COMPACT, FORMAT_PRIM_ID = 0, 1, 2  # hiprtB200HitFormat
+COMPACT_DTYPE = np.dtype([("primID", "<u4"), ("t", "<f4"), ("uv", "<f4", 2)])
+FORMAT_WORDS = {0: 12, 1: 4, 2: 1}
 DEVICE_AMD, DEVICE_NVIDIA = 0, 1
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("minT", "<f4"), ("direction", "<f4", 3), ("maxT", "<f4")])
@@ -169,6 +172,19 @@ SIGNATURES = {
     "hiprtB200TraceSceneAtTime": [_vp, _vp, _vp, _vp, C.c_float, _u32, _vp, C.c_int, _u32, _vp],
     "hiprtB200TraceGeometryHost": [_vp, _vp, _vp, _u32, _vp, C.c_int, _vp],
     "hiprtB200TraceSceneHost": [_vp, _vp, _vp, _u32, _vp, C.c_int, _u32, _vp],
+    "hiprtB200TraceGeometryFormat": [_vp, _vp, _vp, _u32, _vp, C.c_int, C.c_int, _vp],
+    "hiprtB200TraceGeometryFormatHost": [_vp, _vp, _vp, _u32, _vp, C.c_int, C.c_int, _vp],
+    "hiprtB200HitFormatSize": [C.c_int],
+    "hiprtB200TraceGeometryStats": [_vp, _vp, _vp, _u32, _vp, C.c_int, _vp, _vp],
+    "hiprtB200GetGeometrySize": [_vp, _vp, _P(_sz)],
+    "hiprtB200AllocateGeometryBlob": [_vp, _sz, _P(_vp)],
+    "hiprtB200RelocateGeometry": [_vp, _vp, _vp],
+    "hiprtB200SharedAlloc": [_vp, _sz, _P(_vp), _vp],
+    "hiprtB200SharedFree": [_vp, _vp],
+    "hiprtB200SharedOpen": [_vp, _vp, _P(_vp)],
+    "hiprtB200SharedClose": [_vp, _vp],
+    "hiprtB200ResolveAoFrame": [_vp, _vp, C.c_int, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp],
+    "hiprtB200WaitFlags": [_vp, _vp, _u32, _u32, _u32, _vp, _vp],
     "hiprtB200GetTempLayout": [_sz, _sz, _P(_sz), _u32],
     "hiprtB200GetDeviceHeaders": [_P(_P(C.c_char_p)), _P(_P(C.c_char_p))],
     "hiprtB200LinkTraceKernels": [C.c_int, C.c_int, C.c_char_p, C.c_char_p, _sz, _u32, _u32, _P(FuncNameSet), _vp, _P(_sz), C.c_char_p, _sz],
@@ -194,6 +210,7 @@ def lib():
             fn.argtypes = argtypes
             fn.restype = C.c_int
         L.hiprtB200GetDeviceHeaders.restype = C.c_uint32
+        L.hiprtB200HitFormatSize.restype = C.c_size_t
         L.hiprtB200GetLastErrorString.restype = C.c_char_p
         _lib = L
     return _lib
@@ -451,6 +468,89 @@ class Context:
             self._check(lib().hiprtB200TraceGeometry(self.h, handle, _ptr(rays), n, _ptr(hits), kind, _stream_handle(stream)),
                         "hiprtB200TraceGeometry")
         return hits
+
+    def trace_format(self, geom, rays, fmt, out=None, kind=CLOSEST_HIT, stream=None):
+        """hiprtB200TraceGeometryFormat: device tensor of records [n, 12 | 4 | 1] int32 in hiprtB200HitFormat `fmt`."""
+        t = self.torch
+        n = rays.numel() * rays.element_size() // 32
+        if out is None:
+            out = t.empty((n, FORMAT_WORDS[fmt]), dtype=t.int32, device=self.device)
+        self._check(lib().hiprtB200TraceGeometryFormat(self.h, geom.h if hasattr(geom, "h") else geom, _ptr(rays), n, _ptr(out), fmt, kind,
+                                                       _stream_handle(stream)), "hiprtB200TraceGeometryFormat")
+        return out
+
+    def trace_format_host(self, geom, rays_np, fmt, out_np=None, kind=CLOSEST_HIT, stream=None):
+        """hiprtB200TraceGeometryFormatHost with HOST buffers: records as HIT_DTYPE / COMPACT_DTYPE / uint32."""
+        n = len(rays_np)
+        if out_np is None:
+            out_np = np.empty(n, {0: HIT_DTYPE, 1: COMPACT_DTYPE, 2: np.dtype("<u4")}[fmt])
+        self._check(lib().hiprtB200TraceGeometryFormatHost(self.h, geom.h if hasattr(geom, "h") else geom, rays_np.ctypes.data_as(C.c_void_p), n,
+                                                           out_np.ctypes.data_as(C.c_void_p), fmt, kind, _stream_handle(stream)),
+                    "hiprtB200TraceGeometryFormatHost")
+        return out_np
+
+    def trace_stats(self, geom, rays, kind=CLOSEST_HIT, stream=None):
+        """(box-node visits, leaf visits) of tracing `rays` (instrumented kernel; hits are discarded)."""
+        t = self.torch
+        n = rays.numel() * rays.element_size() // 32
+        hits = t.empty((n, 12), dtype=t.int32, device=self.device)
+        counts = t.zeros(2, dtype=t.int64, device=self.device)
+        self._check(lib().hiprtB200TraceGeometryStats(self.h, geom.h if hasattr(geom, "h") else geom, _ptr(rays), n, _ptr(hits), kind, _ptr(counts),
+                                                      _stream_handle(stream)), "hiprtB200TraceGeometryStats")
+        c = counts.cpu().numpy()
+        return int(c[0]), int(c[1])
+
+    # ---- multi-GPU plumbing ---------------------------------------------------------------------
+    def geometry_size(self, geom):
+        sz = C.c_size_t()
+        self._check(lib().hiprtB200GetGeometrySize(self.h, geom.h if hasattr(geom, "h") else geom, C.byref(sz)), "hiprtB200GetGeometrySize")
+        return sz.value
+
+    def allocate_geometry_blob(self, size):
+        g = C.c_void_p()
+        self._check(lib().hiprtB200AllocateGeometryBlob(self.h, size, C.byref(g)), "hiprtB200AllocateGeometryBlob")
+        return g
+
+    def relocate_geometry(self, handle, stream=None):
+        self._check(lib().hiprtB200RelocateGeometry(self.h, handle, _stream_handle(stream)), "hiprtB200RelocateGeometry")
+
+    def blob_tensor(self, handle, size):
+        """uint8 device tensor aliasing a geometry blob (for torch.distributed.broadcast); keeps no ownership."""
+        t = self.torch
+        iface = {"shape": (int(size),), "typestr": "|u1", "data": (int(handle.value if hasattr(handle, "value") else handle), False), "version": 2}
+        holder = type("DeviceBlob", (), {"__cuda_array_interface__": iface})()
+        return t.as_tensor(holder, device=self.device)
+
+    def shared_alloc(self, nbytes):
+        """(device pointer, 64-byte IPC handle) of memory other ranks of the box can map."""
+        p = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        self._check(lib().hiprtB200SharedAlloc(self.h, int(nbytes), C.byref(p), handle), "hiprtB200SharedAlloc")
+        return p.value, bytes(handle)
+
+    def shared_open(self, handle_bytes):
+        p = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle_bytes)
+        self._check(lib().hiprtB200SharedOpen(self.h, buf, C.byref(p)), "hiprtB200SharedOpen")
+        return p.value
+
+    def shared_close(self, ptr):
+        self._check(lib().hiprtB200SharedClose(self.h, C.c_void_p(ptr)), "hiprtB200SharedClose")
+
+    def shared_free(self, ptr):
+        self._check(lib().hiprtB200SharedFree(self.h, C.c_void_p(ptr)), "hiprtB200SharedFree")
+
+    def resolve_ao_frame(self, primary, primary_fmt, ao_prim_ids, first_ao_ray, pixel_index, spp, framebuffer_ptr, done_flag_ptr, done_value,
+                         block_counter, stream=None):
+        """hiprtB200ResolveAoFrame; framebuffer_ptr / done_flag_ptr are raw device addresses (local or peer-mapped)."""
+        self._check(lib().hiprtB200ResolveAoFrame(self.h, _ptr(primary), primary_fmt, _ptr(ao_prim_ids), _ptr(first_ao_ray), _ptr(pixel_index),
+                                                  int(pixel_index.numel()), spp, C.c_void_p(framebuffer_ptr),
+                                                  C.c_void_p(done_flag_ptr) if done_flag_ptr else None, done_value, _ptr(block_counter),
+                                                  _stream_handle(stream)), "hiprtB200ResolveAoFrame")
+
+    def wait_flags(self, flags_ptr, count, stride_words, value, timeout=None, stream=None):
+        self._check(lib().hiprtB200WaitFlags(self.h, C.c_void_p(flags_ptr), count, stride_words, value, _ptr(timeout), _stream_handle(stream)),
+                    "hiprtB200WaitFlags")
 
     def trace_scene_at_time(self, scene, rays, times=None, time=0.0, hits=None, kind=CLOSEST_HIT, mask=0xFFFFFFFF, stream=None):
         """Scene trace with motion blur: `times` = float32 device tensor (one time per ray) or None (every ray at `time`)."""

@@ -9,6 +9,7 @@
 
 #include "builders.h"
 #include "compiler.h"
+#include "frame.h"
 #include "trace.h"
 
 #include <algorithm>
@@ -73,9 +74,11 @@ class HostTracePipeline
 	}
 
 	void run(
-		hiprtGeometry geometry, bool triangles, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, hiprtHit* hostHits, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t user,
-		uint32_t smCount )
+		hiprtGeometry geometry, bool triangles, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, void* hostRecords, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t user,
+		uint32_t smCount, uint32_t format = hiprtB200HitFormatFull )
 	{
+		const size_t recordSize = hiprtB200HitFormatSize( hiprtB200HitFormat( format ) );
+		uint8_t*	 hostHits	= static_cast<uint8_t*>( hostRecords );
 		std::lock_guard<std::mutex> lock( m_mutex );
 		init();
 		// order after whatever the caller has queued on its stream (e.g. the build)
@@ -94,14 +97,14 @@ class HostTracePipeline
 			checkCuda( cudaStreamWaitEvent( m_compute, m_up[slot], 0 ), "cudaStreamWaitEvent" );
 			if ( c >= uint32_t( Slots ) ) checkCuda( cudaStreamWaitEvent( m_compute, m_down[slot], 0 ), "cudaStreamWaitEvent" );
 			if ( geometry )
-				traceGeometry( geometry, triangles, m_rays[slot], count, m_hits[slot], type, m_counters + slot * 16, smCount, m_compute );
+				traceGeometry( geometry, triangles, m_rays[slot], count, m_hits[slot], type, m_counters + slot * 16, smCount, m_compute, format );
 			else
 				traceScene( scene, m_rays[slot], count, m_hits[slot], type, mask, m_counters + slot * 16, smCount, m_compute );
 			checkCuda( cudaGetLastError(), "trace launch" );
 			checkCuda( cudaEventRecord( m_traced[slot], m_compute ), "cudaEventRecord" );
 
 			checkCuda( cudaStreamWaitEvent( m_d2h, m_traced[slot], 0 ), "cudaStreamWaitEvent" );
-			checkCuda( cudaMemcpyAsync( hostHits + first, m_hits[slot], size_t( count ) * sizeof( hiprtHit ), cudaMemcpyDeviceToHost, m_d2h ), "D2H hits" );
+			checkCuda( cudaMemcpyAsync( hostHits + size_t( first ) * recordSize, m_hits[slot], size_t( count ) * recordSize, cudaMemcpyDeviceToHost, m_d2h ), "D2H hits" );
 			checkCuda( cudaEventRecord( m_down[slot], m_d2h ), "cudaEventRecord" );
 		}
 		checkCuda( cudaStreamSynchronize( m_d2h ), "cudaStreamSynchronize" );
@@ -302,6 +305,9 @@ class Context
 			cudaMemcpyAsync( &geomType, static_cast<uint8_t*>( geometry ) + offsetof( GeomHeader, geomType ), sizeof( uint32_t ), cudaMemcpyDeviceToHost, stream ),
 			"cudaMemcpyAsync" );
 		checkCuda( cudaStreamSynchronize( stream ), "cudaStreamSynchronize" );
+		// remembered: a handle this context did not build itself (loaded / replicated blob) must not cost a synchronisation per
+		// launch; hiprtDestroyGeometry forgets it again
+		noteGeometryKind( geometry, geomType & 1u );
 		return geomType & 1u;
 	}
 
@@ -1040,6 +1046,153 @@ hiprtError hiprtB200TraceSceneHost(
 {
 	if ( !context || !scene || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] { ctx( context )->hostPipeline.run( nullptr, false, scene, hostRays, numRays, hostHits, type, mask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount ); } );
+}
+
+// ---- compact output records, multi-GPU plumbing (include/hiprt/hiprt_b200.h) ------------------------------------------------
+size_t hiprtB200HitFormatSize( hiprtB200HitFormat format )
+{
+	return format == hiprtB200HitFormatFull ? sizeof( hiprtHit ) : ( format == hiprtB200HitFormatCompact ? 16 : 4 );
+}
+
+hiprtError hiprtB200TraceGeometryFormat(
+	hiprtContext context, hiprtGeometry geometry, const hiprtRay* rays, uint32_t numRays, void* records, hiprtB200HitFormat format, hiprtTraversalType type,
+	hiprtApiStream stream )
+{
+	if ( !context || !geometry || ( numRays && ( !rays || !records ) ) || uint32_t( format ) > hiprtB200HitFormatPrimID ) return hiprtErrorInvalidParameter;
+	const bool triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) );
+	if ( !triangles && format != hiprtB200HitFormatFull ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		traceGeometry(
+			geometry, triangles, rays, numRays, records, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
+			uint32_t( format ) );
+		checkCuda( cudaGetLastError(), "trace launch" );
+	} );
+}
+
+hiprtError hiprtB200TraceGeometryFormatHost(
+	hiprtContext context, hiprtGeometry geometry, const hiprtRay* hostRays, uint32_t numRays, void* hostRecords, hiprtB200HitFormat format, hiprtTraversalType type,
+	hiprtApiStream stream )
+{
+	if ( !context || !geometry || numRays == 0 || !hostRays || !hostRecords || uint32_t( format ) > hiprtB200HitFormatPrimID ) return hiprtErrorInvalidParameter;
+	const bool triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) );
+	if ( !triangles && format != hiprtB200HitFormatFull ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		ctx( context )->hostPipeline.run(
+			geometry, triangles, nullptr, hostRays, numRays, hostRecords, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount,
+			uint32_t( format ) );
+	} );
+}
+
+hiprtError hiprtB200TraceGeometryStats(
+	hiprtContext context, hiprtGeometry geometry, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint64_t* visitCounts,
+	hiprtApiStream stream )
+{
+	if ( !context || !geometry || !visitCounts || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
+	if ( !ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) ) ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		traceGeometryStats(
+			geometry, rays, numRays, hits, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
+			reinterpret_cast<unsigned long long*>( visitCounts ) );
+		checkCuda( cudaGetLastError(), "trace launch" );
+	} );
+}
+
+hiprtError hiprtB200GetGeometrySize( hiprtContext context, hiprtGeometry geometry, size_t* sizeOut )
+{
+	if ( !context || !geometry || !sizeOut ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		GeomHeader h;
+		checkCuda( cudaMemcpy( &h, geometry, sizeof( h ), cudaMemcpyDeviceToHost ), "cudaMemcpy" );
+		*sizeOut = h.size;
+	} );
+}
+
+hiprtError hiprtB200AllocateGeometryBlob( hiprtContext context, size_t size, hiprtGeometry* geometryOut )
+{
+	if ( !context || size < 64 || !geometryOut ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] { *geometryOut = reinterpret_cast<hiprtGeometry>( ctx( context )->allocatePool( { size } )[0] ); } );
+}
+
+hiprtError hiprtB200RelocateGeometry( hiprtContext context, hiprtGeometry geometry, hiprtApiStream stream )
+{
+	if ( !context || !geometry ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		relocateGeometry( geometry, static_cast<cudaStream_t>( stream ) );
+		checkCuda( cudaGetLastError(), "relocate launch" );
+	} );
+}
+
+hiprtError hiprtB200SharedAlloc( hiprtContext context, size_t bytes, void** devicePtrOut, void* handleOut )
+{
+	if ( !context || bytes == 0 || !devicePtrOut || !handleOut ) return hiprtErrorInvalidParameter;
+	static_assert( sizeof( cudaIpcMemHandle_t ) == 64, "the IPC handle is documented as 64 opaque bytes" );
+	return guarded( context, [&] {
+		void*		p = nullptr;
+		cudaError_t e = cudaMalloc( &p, bytes );
+		if ( e == cudaErrorMemoryAllocation ) throw OutOfDeviceMemory( "cudaMalloc: out of device memory" );
+		checkCuda( e, "cudaMalloc" );
+		checkCuda( cudaMemset( p, 0, bytes ), "cudaMemset" );
+		cudaIpcMemHandle_t h;
+		e = cudaIpcGetMemHandle( &h, p );
+		if ( e != cudaSuccess )
+		{
+			cudaFree( p );
+			checkCuda( e, "cudaIpcGetMemHandle" );
+		}
+		memcpy( handleOut, &h, sizeof( h ) );
+		*devicePtrOut = p;
+	} );
+}
+
+hiprtError hiprtB200SharedFree( hiprtContext context, void* devicePtr )
+{
+	if ( !context || !devicePtr ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] { checkCuda( cudaFree( devicePtr ), "cudaFree" ); } );
+}
+
+hiprtError hiprtB200SharedOpen( hiprtContext context, const void* handle, void** devicePtrOut )
+{
+	if ( !context || !handle || !devicePtrOut ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		cudaIpcMemHandle_t h;
+		memcpy( &h, handle, sizeof( h ) );
+		void* p = nullptr;
+		checkCuda( cudaIpcOpenMemHandle( &p, h, cudaIpcMemLazyEnablePeerAccess ), "cudaIpcOpenMemHandle" );
+		*devicePtrOut = p;
+	} );
+}
+
+hiprtError hiprtB200SharedClose( hiprtContext context, void* devicePtr )
+{
+	if ( !context || !devicePtr ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] { checkCuda( cudaIpcCloseMemHandle( devicePtr ), "cudaIpcCloseMemHandle" ); } );
+}
+
+hiprtError hiprtB200ResolveAoFrame(
+	hiprtContext context, const void* primaryRecords, hiprtB200HitFormat primaryFormat, const uint32_t* aoPrimIDs, const uint32_t* firstAoRay,
+	const uint32_t* pixelIndex, uint32_t numPixels, uint32_t spp, float* framebuffer, uint32_t* doneFlag, uint32_t doneValue, uint32_t* blockCounter,
+	hiprtApiStream stream )
+{
+	if ( !context || uint32_t( primaryFormat ) > hiprtB200HitFormatPrimID || spp == 0 || !framebuffer || ( doneFlag && !blockCounter ) ) return hiprtErrorInvalidParameter;
+	if ( numPixels && ( !primaryRecords || !aoPrimIDs || !firstAoRay || !pixelIndex ) ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		const uint32_t stride = uint32_t( hiprtB200HitFormatSize( primaryFormat ) );
+		const uint32_t offset = primaryFormat == hiprtB200HitFormatFull ? 16u /* offsetof( hiprtHit, primID ) */ : 0u;
+		resolveAoFrame(
+			primaryRecords, stride, offset, aoPrimIDs, firstAoRay, pixelIndex, numPixels, spp, framebuffer, doneFlag, doneValue, blockCounter,
+			ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ) );
+		checkCuda( cudaGetLastError(), "resolve launch" );
+	} );
+}
+
+hiprtError hiprtB200WaitFlags(
+	hiprtContext context, const uint32_t* flags, uint32_t count, uint32_t strideWords, uint32_t value, uint32_t* timeoutOut, hiprtApiStream stream )
+{
+	if ( !context || !flags || count == 0 || count > 1024 || strideWords == 0 ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		waitFlags( flags, count, strideWords, value, timeoutOut, static_cast<cudaStream_t>( stream ) );
+		checkCuda( cudaGetLastError(), "wait launch" );
+	} );
 }
 
 hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount, size_t* offsetsOut, uint32_t numOffsets )

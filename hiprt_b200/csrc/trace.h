@@ -1,14 +1,22 @@
 // Launchers of the library's trace kernels (trace_kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <hiprt/hiprt_b200.h>
 #include <hiprt/hiprt_types.h>
 
 namespace hiprt
 {
 // workCounter: one device uint32 the persistent variant uses as its ray-batch counter (reset on `stream` before the launch)
 // triangles: the geometry holds triangle pairs (fast kernel) rather than custom primitives (generic kernel)
+// format: hiprtB200HitFormat of the output records (`hits` then points to 48-, 16- or 4-byte records); formats other than the
+// full hiprtHit exist for triangle geometries only
 void traceGeometry(
-	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream );
+	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, void* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount,
+	cudaStream_t stream, uint32_t format = 0 );
+// instrumented variant of the triangle kernel: adds {box-node visits, leaf visits} of the launch to stats[0..1]
+void traceGeometryStats(
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream,
+	unsigned long long* stats );
 // times: optional device array of one time per ray (motion blur); nullptr = every ray at `time`
 void traceScene(
 	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, uint32_t* workCounter, uint32_t smCount,

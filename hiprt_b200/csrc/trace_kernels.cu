@@ -68,6 +68,19 @@ __device__ __forceinline__ void storeHit( hiprtHit* hits, uint32_t index, const 
 	hp[1] = make_float4( __uint_as_float( hit.primID ), 0.0f, hit.uv.x, hit.uv.y );
 	hp[2] = make_float4( hit.normal.x, hit.normal.y, hit.normal.z, hit.t );
 }
+// Output record formats of the library kernels (hiprtB200HitFormat, include/hiprt/hiprt_b200.h): the full 48-byte hiprtHit, a
+// 16-byte {primID, t, u, v} record, or the primitive id alone (occlusion queries: hiprtInvalidValue = not occluded). The
+// traversal is the same; the smaller records cut the write traffic of a launch (48 -> 16 / 4 bytes per ray).
+template <uint32_t Format>
+__device__ __forceinline__ void storeHitAs( void* out, uint32_t index, const hiprtHit& hit )
+{
+	if constexpr ( Format == hiprtB200HitFormatFull )
+		storeHit( static_cast<hiprtHit*>( out ), index, hit );
+	else if constexpr ( Format == hiprtB200HitFormatCompact )
+		static_cast<float4*>( out )[index] = make_float4( __uint_as_float( hit.primID ), hit.t, hit.uv.x, hit.uv.y );
+	else
+		static_cast<uint32_t*>( out )[index] = hit.primID;
+}
 
 // One thread per ray. Persistent = the grid only fills the machine and every warp keeps fetching batches of 32
 // consecutive rays from a global counter until the buffer is exhausted (no block-granular tail: a block slot is
@@ -160,13 +173,59 @@ struct F8
 {
 	float v[8];
 };
+// Node loads carry an L2 evict-last hint, ray loads and hit stores an evict-first one (and bypass L1): a launch streams
+// 32 B of ray in and up to 48 B of hit out per ray through the same L2 that has to keep the node working set (C3: 0.36 GB of
+// rays + 0.54 GB of hits per frame against 126 MB of L2), and the top stall of the kernel is the scoreboard wait on node loads.
+template <bool Hints>
 __device__ __forceinline__ F8 ldg8( const void* p, uint32_t i )
 {
 	F8 r;
-	asm( "ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-		 : "=f"( r.v[0] ), "=f"( r.v[1] ), "=f"( r.v[2] ), "=f"( r.v[3] ), "=f"( r.v[4] ), "=f"( r.v[5] ), "=f"( r.v[6] ), "=f"( r.v[7] )
-		 : "l"( reinterpret_cast<const char*>( p ) + 32u * i ) );
+	if constexpr ( Hints )
+		asm( "ld.global.nc.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+			 : "=f"( r.v[0] ), "=f"( r.v[1] ), "=f"( r.v[2] ), "=f"( r.v[3] ), "=f"( r.v[4] ), "=f"( r.v[5] ), "=f"( r.v[6] ), "=f"( r.v[7] )
+			 : "l"( reinterpret_cast<const char*>( p ) + 32u * i ) );
+	else
+		asm( "ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+			 : "=f"( r.v[0] ), "=f"( r.v[1] ), "=f"( r.v[2] ), "=f"( r.v[3] ), "=f"( r.v[4] ), "=f"( r.v[5] ), "=f"( r.v[6] ), "=f"( r.v[7] )
+			 : "l"( reinterpret_cast<const char*>( p ) + 32u * i ) );
 	return r;
+}
+// A hiprtRay is 32 bytes and 32-byte aligned inside the ray buffer: ONE streaming 256-bit load.
+template <bool Hints>
+__device__ __forceinline__ hiprtRay loadRayT( const hiprtRay* rays, uint32_t index )
+{
+	if constexpr ( !Hints ) return loadRay( rays, index );
+	F8 r;
+	asm( "ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		 : "=f"( r.v[0] ), "=f"( r.v[1] ), "=f"( r.v[2] ), "=f"( r.v[3] ), "=f"( r.v[4] ), "=f"( r.v[5] ), "=f"( r.v[6] ), "=f"( r.v[7] )
+		 : "l"( rays + index ) );
+	hiprtRay ray;
+	ray.origin = make_float3( r.v[0], r.v[1], r.v[2] ), ray.minT = r.v[3];
+	ray.direction = make_float3( r.v[4], r.v[5], r.v[6] ), ray.maxT = r.v[7];
+	return ray;
+}
+__device__ __forceinline__ void stStream16( void* p, float4 v )
+{
+	uint64_t policy;
+	asm( "createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"( policy ) );
+	asm volatile( "st.global.L1::no_allocate.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"( p ), "f"( v.x ), "f"( v.y ), "f"( v.z ), "f"( v.w ), "l"( policy ) : "memory" );
+}
+template <uint32_t Format, bool Hints>
+__device__ __forceinline__ void storeHitT( void* out, uint32_t index, const hiprtHit& hit )
+{
+	if constexpr ( !Hints )
+		storeHitAs<Format>( out, index, hit );
+	else if constexpr ( Format == hiprtB200HitFormatFull )
+	{
+		float4* hp = reinterpret_cast<float4*>( static_cast<hiprtHit*>( out ) + index );
+		stStream16( hp, make_float4( __uint_as_float( hit.instanceIDs[0] ), __uint_as_float( hit.instanceIDs[1] ), __uint_as_float( hit.instanceIDs[2] ), __uint_as_float( hit.instanceIDs[3] ) ) );
+		stStream16( hp + 1, make_float4( __uint_as_float( hit.primID ), 0.0f, hit.uv.x, hit.uv.y ) );
+		stStream16( hp + 2, make_float4( hit.normal.x, hit.normal.y, hit.normal.z, hit.t ) );
+	}
+	else if constexpr ( Format == hiprtB200HitFormatCompact )
+		stStream16( static_cast<float4*>( out ) + index, make_float4( __uint_as_float( hit.primID ), hit.t, hit.uv.x, hit.uv.y ) );
+	else
+		__stcs( static_cast<uint32_t*>( out ) + index, hit.primID );
 }
 
 // Slab test of child `s` of a box node. Octant bit k set = direction component k negative (near plane is hi).
@@ -198,11 +257,11 @@ __device__ __forceinline__ bool slabTest( const float* b, const float3 o, const 
 }
 
 // One box-node visit: tests the four children, leaves the hit ones sorted (nearest last) in c[4-n..3].
-template <uint32_t Octant>
+template <uint32_t Octant, bool Hints = false>
 __device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxNodes, uint32_t node, const float3 o, const float3 invD, float maxT, uint32_t c[4] )
 {
 	const void* p  = boxNodes + ( node >> 4 );
-	const F8	w0 = ldg8( p, 0 ), w1 = ldg8( p, 1 ), w2 = ldg8( p, 2 ), w3 = ldg8( p, 3 );
+	const F8	w0 = ldg8<Hints>( p, 0 ), w1 = ldg8<Hints>( p, 1 ), w2 = ldg8<Hints>( p, 2 ), w3 = ldg8<Hints>( p, 3 );
 	const float b[24] = { w0.v[4], w0.v[5], w0.v[6], w0.v[7], w1.v[0], w1.v[1], w1.v[2], w1.v[3], w1.v[4], w1.v[5], w1.v[6], w1.v[7],
 						  w2.v[0], w2.v[1], w2.v[2], w2.v[3], w2.v[4], w2.v[5], w2.v[6], w2.v[7], w3.v[0], w3.v[1], w3.v[2], w3.v[3] };
 	c[0] = __float_as_uint( w0.v[0] ), c[1] = __float_as_uint( w0.v[1] ), c[2] = __float_as_uint( w0.v[2] ), c[3] = __float_as_uint( w0.v[3] );
@@ -238,23 +297,25 @@ __device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxN
 // Refill  > 0: lane-granular persistent threads -- whenever at least `Refill` lanes are idle (their ray is finished) those
 // lanes write their hits and fetch the next rays from `workCounter`, the others keep their state; returns when the ray
 // buffer is exhausted and every lane is done. Pays off for incoherent rays only (see the kernel below).
-template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum, uint32_t Refill = 0>
+template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum, uint32_t Refill = 0, uint32_t Format = hiprtB200HitFormatFull, bool Hints = false, bool Stats = false>
 __device__ __forceinline__ void traceTrianglesWarp(
 	const Box4Node* __restrict__ boxNodes,
 	const TrianglePairNode* __restrict__ leaves,
 	const hiprtRay* __restrict__ rays,
-	hiprtHit* __restrict__ hits,
+	void* __restrict__ hits,
 	uint32_t		index,
 	bool			live,
 	uint32_t* const stackBase,
 	uint32_t*		workCounter = nullptr,
-	uint32_t		numRays		= 0 )
+	uint32_t		numRays		= 0,
+	unsigned long long* stats	= nullptr ) // Stats: {box-node visits, leaf visits} of the launch are added here
 {
 	constexpr uint32_t TotalDepth = 64; // the reference's private stack size
 	uint32_t		   localStack[TotalDepth - SharedDepth];
 	uint32_t		   top = 0;
+	uint32_t		   boxVisits = 0, leafVisits = 0;
 
-	hiprtRay ray	  = loadRay( rays, live ? index : 0u );
+	hiprtRay ray	  = loadRayT<Hints>( rays, live ? index : 0u );
 	float3	 invD	  = rcp3( ray.direction );
 	float	 maxT0	  = ray.maxT;
 	uint32_t bestRef  = InvalidValue; // (leaf address << 1) | triangle of the pair
@@ -280,10 +341,15 @@ __device__ __forceinline__ void traceTrianglesWarp(
 		hiprtHit hit;
 		if ( bestRef != InvalidValue && !overflow )
 		{
-			ray.maxT = maxT0;
-			intersectPairTriangle( leaves, bestRef >> 1, bestRef & 1u, ray, hit );
+			if constexpr ( Format == hiprtB200HitFormatPrimID )
+				hit.primID = bestPrim;
+			else
+			{
+				ray.maxT = maxT0;
+				intersectPairTriangle( leaves, bestRef >> 1, bestRef & 1u, ray, hit );
+			}
 		}
-		storeHit( hits, index, hit );
+		storeHitT<Format, Hints>( hits, index, hit );
 	};
 
 	auto pop = [&]() -> uint32_t {
@@ -317,7 +383,7 @@ __device__ __forceinline__ void traceTrianglesWarp(
 					if ( idle && mine < numRays )
 					{
 						index	 = mine;
-						ray		 = loadRay( rays, index );
+						ray		 = loadRayT<Hints>( rays, index );
 						invD	 = rcp3( ray.direction );
 						maxT0	 = ray.maxT;
 						bestRef	 = InvalidValue;
@@ -347,17 +413,18 @@ __device__ __forceinline__ void traceTrianglesWarp(
 			{
 				uint32_t c[4];
 				uint32_t n;
+				if constexpr ( Stats ) ++boxVisits;
 				switch ( octant ) // warp-uniform
 				{
-				case 0: n = visitBox4<0>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 1: n = visitBox4<1>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 2: n = visitBox4<2>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 3: n = visitBox4<3>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 4: n = visitBox4<4>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 5: n = visitBox4<5>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 6: n = visitBox4<6>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 7: n = visitBox4<7>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				default: n = visitBox4<GeneralOctant>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 0: n = visitBox4<0, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 1: n = visitBox4<1, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 2: n = visitBox4<2, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 3: n = visitBox4<3, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 4: n = visitBox4<4, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 5: n = visitBox4<5, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 6: n = visitBox4<6, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 7: n = visitBox4<7, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				default: n = visitBox4<GeneralOctant, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
 				}
 				// hit children: c[4-n..3], nearest first. Far-to-near onto the stack, then the nearest is popped.
 				if ( top + 4 <= SharedDepth )
@@ -400,7 +467,8 @@ __device__ __forceinline__ void traceTrianglesWarp(
 		{
 			const uint32_t addr = node >> 3;
 			const void*	   p	= leaves + addr;
-			const F8	   l0 = ldg8( p, 0 ), l1 = ldg8( p, 1 );
+			if constexpr ( Stats ) ++leafVisits;
+			const F8	   l0 = ldg8<Hints>( p, 0 ), l1 = ldg8<Hints>( p, 1 );
 			const uint32_t prim0 = __float_as_uint( l1.v[5] ), prim1 = __float_as_uint( l1.v[6] );
 			const float3   pv0 = make_float3( l0.v[0], l0.v[1], l0.v[2] ), pv1 = make_float3( l0.v[3], l0.v[4], l0.v[5] );
 			const float3   pv2 = make_float3( l0.v[6], l0.v[7], l1.v[0] ), pv3 = make_float3( l1.v[1], l1.v[2], l1.v[3] );
@@ -430,6 +498,16 @@ __device__ __forceinline__ void traceTrianglesWarp(
 	}
 
 	if ( Refill == 0 && live ) finish();
+	if constexpr ( Stats )
+	{
+		boxVisits  = __reduce_add_sync( FullMask, boxVisits );
+		leafVisits = __reduce_add_sync( FullMask, leafVisits );
+		if ( ( threadIdx.x & 31u ) == 0 )
+		{
+			atomicAdd( stats, static_cast<unsigned long long>( boxVisits ) );
+			atomicAdd( stats + 1, static_cast<unsigned long long>( leafVisits ) );
+		}
+	}
 }
 
 // Persistent = the grid only fills the machine and every warp keeps fetching batches of 32 consecutive rays from a
@@ -438,9 +516,9 @@ __device__ __forceinline__ void traceTrianglesWarp(
 // Refill > 0 (persistent only): a warp whose fetched batch is INCOHERENT (mixed direction octants: AO / diffuse bounces)
 // keeps that batch and from then on refills idle lanes one by one; ncu shows 15 of 32 lanes active on 8-spp AO rays without
 // it. Coherent batches (primary, shadow rays) stay warp-granular: refilling them lane by lane was measured 12-18 % slower.
-template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill = 0>
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill = 0, uint32_t Format = hiprtB200HitFormatFull, bool Hints = false, bool Stats = false>
 __global__ void __launch_bounds__( Block, Refill != 0 ? 1024u / Block : 1u ) traceTrianglesKernel(
-	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, uint32_t* workCounter )
+	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, void* __restrict__ hits, uint32_t* workCounter, unsigned long long* stats )
 {
 	__shared__ uint32_t sStack[Block * SharedDepth];
 	const GeomHeader*	header					 = reinterpret_cast<const GeomHeader*>( geom );
@@ -467,17 +545,17 @@ __global__ void __launch_bounds__( Block, Refill != 0 ? 1024u / Block : 1u ) tra
 				const bool	   coherent = __all_sync( FullMask, mine == first );
 				if ( !coherent )
 				{
-					traceTrianglesWarp<Type, SharedDepth, BoxQuorum, Refill>( boxNodes, leaves, rays, hits, index, live, stackBase, workCounter, numRays );
+					traceTrianglesWarp<Type, SharedDepth, BoxQuorum, Refill, Format, Hints, Stats>( boxNodes, leaves, rays, hits, index, live, stackBase, workCounter, numRays, stats );
 					return; // the refilling traversal drains the ray buffer
 				}
 			}
-			traceTrianglesWarp<Type, SharedDepth, BoxQuorum>( boxNodes, leaves, rays, hits, index, live, stackBase );
+			traceTrianglesWarp<Type, SharedDepth, BoxQuorum, 0, Format, Hints, Stats>( boxNodes, leaves, rays, hits, index, live, stackBase, nullptr, 0, stats );
 		}
 	}
 	else
 	{
 		const uint32_t index = blockIdx.x * Block + threadIdx.x;
-		traceTrianglesWarp<Type, SharedDepth, BoxQuorum>( boxNodes, leaves, rays, hits, index, index < numRays, stackBase );
+		traceTrianglesWarp<Type, SharedDepth, BoxQuorum, 0, Format, Hints, Stats>( boxNodes, leaves, rays, hits, index, index < numRays, stackBase, nullptr, 0, stats );
 	}
 }
 
@@ -530,75 +608,84 @@ static void launchGeometry( hiprtGeometry geom, const hiprtRay* rays, uint32_t n
 		kernel<<<DivideRoundUp( numRays, Block ), Block, 0, stream>>>( geom, rays, numRays, hits, workCounter );
 }
 
-// Tuning variants (HIPRT_B200_TRACE_VARIANT): block size / shared stack depth / box-phase quorum / persistent warps.
-template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill>
-static void launchTrianglesT( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
+// The configuration the round-1 sweeps settled on: blocks of 128 threads, 32 stack entries per lane in
+// shared memory, box-phase quorum 16, persistent warps, lane refill (threshold 8) for incoherent batches.
+// HIPRT_B200_TRACE_VARIANT: 1 = generic traversal objects (what a user kernel compiles), 2 = fast kernel without cache hints.
+template <hiprtTraversalType Type, uint32_t Format, bool Hints, bool Stats = false>
+static void launchTrianglesT(
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream, unsigned long long* stats = nullptr )
 {
-	auto kernel = traceTrianglesKernel<Type, Block, SharedDepth, BoxQuorum, Persistent, Refill>;
-	if constexpr ( Persistent )
-	{
-		static int blocksPerSm = 0; // same value for every caller: a benign race
-		if ( blocksPerSm == 0 ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSm, kernel, int( Block ), 0 );
-		cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), stream );
-		const uint32_t blocks = std::min( DivideRoundUp( numRays, Block ), smCount * uint32_t( std::max( blocksPerSm, 1 ) ) );
-		kernel<<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits, workCounter );
-	}
-	else
-		kernel<<<DivideRoundUp( numRays, Block ), Block, 0, stream>>>( geom, rays, numRays, hits, workCounter );
+	constexpr uint32_t Block = 128;
+	auto			   kernel = traceTrianglesKernel<Type, Block, 32, 16, true, 8, Format, Hints, Stats>;
+	static int		   blocksPerSm = 0; // same value for every caller: a benign race
+	if ( blocksPerSm == 0 ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSm, kernel, int( Block ), 0 );
+	cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), stream );
+	const uint32_t blocks = std::min( DivideRoundUp( numRays, Block ), smCount * uint32_t( std::max( blocksPerSm, 1 ) ) );
+	kernel<<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits, workCounter, stats );
 }
 
-template <uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill = 0>
-static void launchTriangles(
-	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, bool any, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
+template <uint32_t Format, bool Hints>
+static void launchTriangles( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, bool any, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
 {
 	if ( any )
-		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, Block, SharedDepth, BoxQuorum, Persistent, Refill>( geom, rays, numRays, hits, workCounter, smCount, stream );
+		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, Format, Hints>( geom, rays, numRays, hits, workCounter, smCount, stream );
 	else
-		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, Block, SharedDepth, BoxQuorum, Persistent, Refill>( geom, rays, numRays, hits, workCounter, smCount, stream );
+		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, Format, Hints>( geom, rays, numRays, hits, workCounter, smCount, stream );
 }
 
+// Instrumented launch (SURVEY.md 8d "counted by an instrumented build"): the same kernel with per-lane visit counters, summed
+// into stats[0] (box-node visits) and stats[1] (leaf visits). Used by bench.py outside the timed region for the cache-level
+// traffic of a ray batch (128 B per box visit + 64 B per leaf visit).
+void traceGeometryStats(
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream,
+	unsigned long long* stats )
+{
+	if ( numRays == 0 ) return;
+	if ( type == hiprtTraversalTerminateAtAnyHit )
+		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, hiprtB200HitFormatFull, true, true>( geom, rays, numRays, hits, workCounter, smCount, stream, stats );
+	else
+		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, hiprtB200HitFormatFull, true, true>( geom, rays, numRays, hits, workCounter, smCount, stream, stats );
+}
+
+// Generic kernel output in another record format: traced into full hits is not possible without a staging buffer, so the
+// generic (custom-primitive) path supports the full format only; api.cpp rejects the others for such geometries.
 void traceGeometry(
-	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount,
-	cudaStream_t stream )
+	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, void* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount,
+	cudaStream_t stream, uint32_t format )
 {
 	if ( numRays == 0 ) return;
 	const bool any = type == hiprtTraversalTerminateAtAnyHit;
-	if ( triangles )
+	const int  variant = traceVariant();
+	if ( triangles && ( variant != 1 || format != hiprtB200HitFormatFull ) )
 	{
-#define HIPRT_B200_TRI( B, D, Q, P ) launchTriangles<B, D, Q, P>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
-		switch ( traceVariant() )
+		const bool hints = variant != 2;
+		switch ( format )
 		{
-		case 1: break; // generic traversal objects (as a user kernel would use them)
-		case 10: HIPRT_B200_TRI( 128, 32, 1, false )
-		case 11: HIPRT_B200_TRI( 128, 32, 8, false )
-		case 12: HIPRT_B200_TRI( 128, 32, 16, false )
-		case 13: HIPRT_B200_TRI( 64, 32, 16, false )
-		case 21: HIPRT_B200_TRI( 64, 32, 16, true )
-		case 25: HIPRT_B200_TRI( 128, 16, 16, true )
-		case 40: launchTriangles<128, 32, 16, true, 4>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
-		case 41: launchTriangles<128, 32, 16, true, 8>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
-		case 42: launchTriangles<128, 32, 16, true, 16>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
-		case 43: launchTriangles<128, 32, 16, true, 1>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
-		default: launchTriangles<128, 32, 16, true, 8>( geom, rays, numRays, hits, any, workCounter, smCount, stream ); return;
+		case hiprtB200HitFormatCompact:
+			if ( hints )
+				launchTriangles<hiprtB200HitFormatCompact, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+			else
+				launchTriangles<hiprtB200HitFormatCompact, false>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+			return;
+		case hiprtB200HitFormatPrimID:
+			if ( hints )
+				launchTriangles<hiprtB200HitFormatPrimID, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+			else
+				launchTriangles<hiprtB200HitFormatPrimID, false>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+			return;
+		default:
+			if ( hints )
+				launchTriangles<hiprtB200HitFormatFull, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+			else
+				launchTriangles<hiprtB200HitFormatFull, false>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+			return;
 		}
-#undef HIPRT_B200_TRI
 	}
-#define HIPRT_B200_LAUNCH( B, D, P )                                                                                                       \
-	if ( any )                                                                                                                             \
-		launchGeometry<hiprtTraversalTerminateAtAnyHit, B, D, P>( geom, rays, numRays, hits, workCounter, smCount, stream );               \
-	else                                                                                                                                   \
-		launchGeometry<hiprtTraversalTerminateAtClosestHit, B, D, P>( geom, rays, numRays, hits, workCounter, smCount, stream );
-	switch ( traceVariant() )
-	{
-	case 0: HIPRT_B200_LAUNCH( 128, 12, false ) break;
-	case 2: HIPRT_B200_LAUNCH( 64, 12, false ) break;
-	case 3: HIPRT_B200_LAUNCH( 64, 32, false ) break;
-	case 4: HIPRT_B200_LAUNCH( 128, 32, true ) break;
-	case 5: HIPRT_B200_LAUNCH( 64, 32, true ) break;
-	case 6: HIPRT_B200_LAUNCH( 128, 24, false ) break;
-	default: HIPRT_B200_LAUNCH( 128, 32, false ) break;
-	}
-#undef HIPRT_B200_LAUNCH
+	hiprtHit* fullHits = static_cast<hiprtHit*>( hits );
+	if ( any )
+		launchGeometry<hiprtTraversalTerminateAtAnyHit, 128, 32, false>( geom, rays, numRays, fullHits, workCounter, smCount, stream );
+	else
+		launchGeometry<hiprtTraversalTerminateAtClosestHit, 128, 32, false>( geom, rays, numRays, fullHits, workCounter, smCount, stream );
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -756,7 +843,7 @@ __device__ __forceinline__ void traceSceneWarp(
 			{
 				const uint32_t addr = node >> 3;
 				const void*	   p	= leaves + addr;
-				const F8	   l0 = ldg8( p, 0 ), l1 = ldg8( p, 1 );
+				const F8	   l0 = ldg8<false>( p, 0 ), l1 = ldg8<false>( p, 1 );
 				const uint32_t prim0 = __float_as_uint( l1.v[5] ), prim1 = __float_as_uint( l1.v[6] );
 				const float3   pv0 = make_float3( l0.v[0], l0.v[1], l0.v[2] ), pv1 = make_float3( l0.v[3], l0.v[4], l0.v[5] );
 				const float3   pv2 = make_float3( l0.v[6], l0.v[7], l1.v[0] ), pv3 = make_float3( l1.v[1], l1.v[2], l1.v[3] );

@@ -209,15 +209,17 @@ def shadow_rays(rays, hits, light=(2.0, 4.0, 3.0)):
     return make_rays(p, (d / dist[:, None]).astype(f32), 0.0, (dist * f32(0.99)).astype(f32)), ok
 
 
-def ao_rays(rays, hits, spp=16, radius=0.05):
-    """`spp` cosine-hemisphere any-hit rays per hit pixel (sampleHemisphereCosine, test/shared.h:133-144)."""
+def ao_rays(rays, hits, spp=16, radius=0.05, pixel_ids=None):
+    """`spp` cosine-hemisphere any-hit rays per hit pixel (sampleHemisphereCosine, test/shared.h:133-144). The sampler is seeded
+    with tea<16>(pixel, sample): `pixel` is the ray's position in `rays`, or pixel_ids[position] when given (sharded frames seed
+    by the global pixel index, so the rays do not depend on which rank owns the pixel)."""
     ok = np.nonzero(hits["primID"] != 0xFFFFFFFF)[0]
     p = hit_points(rays[ok], hits[ok])
     n = normalize(hits["normal"][ok].astype(np.float64))
     # face the normal against the incoming ray
     flip = (n * rays["direction"][ok]).sum(1) > 0
     n[flip] = -n[flip]
-    pix = np.repeat(ok.astype(np.uint32), spp)
+    pix = np.repeat((ok if pixel_ids is None else np.asarray(pixel_ids)[ok]).astype(np.uint32), spp)
     smp = np.tile(np.arange(spp, dtype=np.uint32), len(ok))
     seed, _ = tea16(pix, smp)
     seed, u0 = randf(seed)

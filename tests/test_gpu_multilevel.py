@@ -119,7 +119,32 @@ def test_custom_spheres_in_a_scene_against_the_oracle(ctx):
     # fused multiply-adds in the device's sphere test move t by a few ulp and flip the odd grazing ray
     agree = (got["primID"] == ref["primID"]) & (got["instanceIDs"][:, 0] == ref["instanceIDs"][:, 0])
     assert agree.mean() > 0.995, agree.mean()
-    assert (dt[agree & hit] <= 1e-4).all()
+    both = agree & hit
+    on_mesh = np.isin(got["instanceIDs"][:, 0], (1, 3))
+    assert (dt[both & on_mesh] <= 5e-5).all(), dt[both & on_mesh].max()  # triangles: the scene bar (fma-built matrices, tests/test_gpu_scene.py)
+    # spheres: t = (-b - sqrt(b^2 - 4ac)) / 2a in float32 cancels near the silhouette, so the bar is the forward error of that
+    # formula, evaluated in float64 on the object-space ray (the device contracts it to fmas, the callback above does not)
+    sel = np.nonzero(both & ~on_mesh)[0]
+    assert len(sel) > 100
+    inst = got["instanceIDs"][sel, 0].astype(np.int64)
+    m = np.zeros((4, 4, 4))
+    m[:, :3, :] = np.asarray(frames, np.float64).reshape(4, 4, 4)[:, :3, :]
+    m[:, 3, 3] = 1.0
+    inv = np.linalg.inv(m)[inst]
+    o = np.einsum("nij,nj->ni", inv[:, :3, :3], rays["origin"][sel].astype(np.float64)) + inv[:, :3, 3]
+    d = np.einsum("nij,nj->ni", inv[:, :3, :3], rays["direction"][sel].astype(np.float64))
+    sp = spheres[got["primID"][sel]].astype(np.float64)
+    oc = o - sp[:, :3]
+    a, b, c = (d * d).sum(1), 2 * (oc * d).sum(1), (oc * oc).sum(1) - sp[:, 3] ** 2
+    disc = np.maximum(b * b - 4 * a * c, 1e-300)
+    t64 = (-b - np.sqrt(disc)) / (2 * a)
+    eps = np.finfo(np.float32).eps
+    # inputs (matrix entries, object-space ray) carry a few eps each; the discriminant amplifies them by (b^2 + 4a|c|) / disc
+    bound = 1e-5 + 64 * eps * (b * b + 4 * a * np.abs(c)) / (2 * a * np.sqrt(disc) * np.abs(t64))
+    for name, tt in (("device", got["t"][sel]), ("oracle", ref["t"][sel])):
+        err = np.abs(tt - t64) / np.abs(t64)
+        assert (err <= bound).all(), (name, float((err / bound).max()))
+    assert np.median(bound) < 1e-4  # the bar is tight for the typical hit, loose only at grazing incidence
     api.lib().hiprtDestroyFuncTable(ctx.h, table)
     scene.destroy()
     g_mesh.destroy()
