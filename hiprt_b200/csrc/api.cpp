@@ -10,6 +10,7 @@
 #include "builders.h"
 #include "compiler.h"
 #include "frame.h"
+#include "qnode.h"
 #include "trace.h"
 
 #include <algorithm>
@@ -75,7 +76,7 @@ class HostTracePipeline
 
 	void run(
 		hiprtGeometry geometry, bool triangles, hiprtScene scene, const hiprtRay* hostRays, uint32_t numRays, void* hostRecords, hiprtTraversalType type, hiprtRayMask mask, cudaStream_t user,
-		uint32_t smCount, uint32_t format = hiprtB200HitFormatFull )
+		uint32_t smCount, uint32_t format = hiprtB200HitFormatFull, const void* qRegion = nullptr )
 	{
 		const size_t recordSize = hiprtB200HitFormatSize( hiprtB200HitFormat( format ) );
 		uint8_t*	 hostHits	= static_cast<uint8_t*>( hostRecords );
@@ -97,7 +98,7 @@ class HostTracePipeline
 			checkCuda( cudaStreamWaitEvent( m_compute, m_up[slot], 0 ), "cudaStreamWaitEvent" );
 			if ( c >= uint32_t( Slots ) ) checkCuda( cudaStreamWaitEvent( m_compute, m_down[slot], 0 ), "cudaStreamWaitEvent" );
 			if ( geometry )
-				traceGeometry( geometry, triangles, m_rays[slot], count, m_hits[slot], type, m_counters + slot * 16, smCount, m_compute, format );
+				traceGeometry( geometry, triangles, m_rays[slot], count, m_hits[slot], type, m_counters + slot * 16, smCount, m_compute, format, qRegion );
 			else
 				traceScene( scene, m_rays[slot], count, m_hits[slot], type, mask, m_counters + slot * 16, smCount, m_compute );
 			checkCuda( cudaGetLastError(), "trace launch" );
@@ -266,19 +267,26 @@ class Context
 	HostTracePipeline	  hostPipeline;
 	compiler::ModuleCache modules; // user trace kernels loaded into THIS context's CUDA context
 
-	// ---- primitive kind of built geometries (chooses the library trace kernel without a device read) ----
-	void noteGeometryKind( void* geometry, bool triangles )
+	// ---- what the library knows about a geometry handle without a device read: its primitive kind (chooses the trace kernel)
+	// and its traversal-only Q region (qnode.h), nullptr when it has none ----
+	struct GeomInfo
+	{
+		bool   triangles = false;
+		void*  qRegion	 = nullptr;
+		size_t blobSize	 = 0; // hiprtB200AllocateGeometryBlob: bytes reserved for the public structure (the Q region follows)
+	};
+	void noteGeometryKind( void* geometry, bool triangles, void* qRegion = nullptr, size_t blobSize = 0 )
 	{
 		std::lock_guard<std::mutex> lock( m_mutex );
-		m_geomKind[geometry] = triangles;
+		m_geomKind[geometry] = GeomInfo{ triangles, qRegion, blobSize };
 	}
 	// (batch builds register 100 000 geometries per call: one lock, one rehash)
-	void noteGeometryKinds( hiprtGeometry* geometries, const hiprtGeometryBuildInput* inputs, uint32_t count )
+	void noteGeometryKinds( hiprtGeometry* geometries, const hiprtGeometryBuildInput* inputs, uint32_t count, const std::vector<void*>& qRegions )
 	{
 		std::lock_guard<std::mutex> lock( m_mutex );
 		m_geomKind.reserve( m_geomKind.size() + count );
 		for ( uint32_t i = 0; i < count; ++i )
-			m_geomKind[geometries[i]] = inputs[i].type == hiprtPrimitiveTypeTriangleMesh;
+			m_geomKind[geometries[i]] = GeomInfo{ inputs[i].type == hiprtPrimitiveTypeTriangleMesh, qRegions.empty() ? nullptr : qRegions[i], 0 };
 	}
 	void forgetGeometry( void* geometry )
 	{
@@ -291,22 +299,33 @@ class Context
 		for ( uint32_t i = 0; i < count; ++i )
 			m_geomKind.erase( geometries[i] );
 	}
+	GeomInfo geometryInfo( void* geometry )
+	{
+		std::lock_guard<std::mutex> lock( m_mutex );
+		auto						it = m_geomKind.find( geometry );
+		return it != m_geomKind.end() ? it->second : GeomInfo{};
+	}
 	// Geometries this context did not build (e.g. written by another library with the same format): the header
 	// word is read back once per call, after the work queued on `stream`.
-	bool geometryHasTriangles( void* geometry, cudaStream_t stream )
+	bool geometryHasTriangles( void* geometry, cudaStream_t stream, const void** qRegionOut = nullptr )
 	{
 		{
 			std::lock_guard<std::mutex> lock( m_mutex );
 			auto						it = m_geomKind.find( geometry );
-			if ( it != m_geomKind.end() ) return it->second;
+			if ( it != m_geomKind.end() )
+			{
+				if ( qRegionOut ) *qRegionOut = it->second.qRegion;
+				return it->second.triangles;
+			}
 		}
+		if ( qRegionOut ) *qRegionOut = nullptr;
 		uint32_t geomType = 0;
 		checkCuda(
 			cudaMemcpyAsync( &geomType, static_cast<uint8_t*>( geometry ) + offsetof( GeomHeader, geomType ), sizeof( uint32_t ), cudaMemcpyDeviceToHost, stream ),
 			"cudaMemcpyAsync" );
 		checkCuda( cudaStreamSynchronize( stream ), "cudaStreamSynchronize" );
-		// remembered: a handle this context did not build itself (loaded / replicated blob) must not cost a synchronisation per
-		// launch; hiprtDestroyGeometry forgets it again
+		// remembered: a handle this context did not build itself must not cost a synchronisation per launch;
+		// hiprtDestroyGeometry forgets it again
 		noteGeometryKind( geometry, geomType & 1u );
 		return geomType & 1u;
 	}
@@ -336,7 +355,7 @@ class Context
 	hiprtLogLevel		  m_logMask = hiprtLogLevelNone;
 	std::string			  m_lastError;
 	std::map<void*, Pool> m_pools;
-	std::unordered_map<void*, bool> m_geomKind;
+	std::unordered_map<void*, GeomInfo> m_geomKind;
 	std::mutex			  m_mutex;
 	uint32_t*			  m_workCounters	= nullptr;
 	uint32_t			  m_workCounterNext = 0;
@@ -436,7 +455,7 @@ hiprtError hiprtCreateGeometries(
 		checkBuildFlags( ctx( context ), buildOptions );
 		std::vector<size_t> sizes( numGeometries );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
-			sizes[i] = geometryStorageSize( buildInputs[i] );
+			sizes[i] = geometryAllocationSize( buildInputs[i] );
 		const std::vector<void*> ptrs = ctx( context )->allocatePool( sizes );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
 			*geometriesOut[i] = reinterpret_cast<hiprtGeometry>( ptrs[i] );
@@ -487,13 +506,28 @@ hiprtError hiprtBuildGeometries(
 		Context* c = ctx( context );
 		checkBuildFlags( c, buildOptions );
 		cudaStream_t s = static_cast<cudaStream_t>( stream );
-		c->noteGeometryKinds( geometriesOut, buildInputs, numGeometries );
 		if ( buildOperation == hiprtBuildOperationUpdate )
 		{
+			// the structure is refitted where it lies (it may have been compacted, loaded or relocated since the build): its Q
+			// region, if it has one, is the one on record for the handle
 			for ( uint32_t i = 0; i < numGeometries; ++i )
-				updateGeometry( c->info(), buildInputs[i], buildOptions, temporaryBuffer, s, geometriesOut[i] );
+				updateGeometry( c->info(), buildInputs[i], buildOptions, temporaryBuffer, s, geometriesOut[i], c->geometryInfo( geometriesOut[i] ).qRegion );
 			return;
 		}
+		// Q regions: single (non-batch) builds of triangle meshes only
+		std::vector<void*> qRegions;
+		{
+			bool any = false;
+			for ( uint32_t i = 0; i < numGeometries && !any; ++i )
+				any = !usesBatch( geometryPrimCount( buildInputs[i] ), buildOptions ) && geometryQRegion( buildInputs[i], buildOptions, geometriesOut[i] );
+			if ( any )
+			{
+				qRegions.resize( numGeometries, nullptr );
+				for ( uint32_t i = 0; i < numGeometries; ++i )
+					if ( !usesBatch( geometryPrimCount( buildInputs[i] ), buildOptions ) ) qRegions[i] = geometryQRegion( buildInputs[i], buildOptions, geometriesOut[i] );
+			}
+		}
+		c->noteGeometryKinds( geometriesOut, buildInputs, numGeometries, qRegions );
 		// inputs small enough for the batch builder are built together first (Context.cpp:153-168)
 		uint32_t batched = 0;
 		for ( uint32_t i = 0; i < numGeometries; ++i )
@@ -517,7 +551,7 @@ hiprtError hiprtBuildGeometries(
 			buildGeometriesBatch( c->info(), batchInputs.data(), uint32_t( batchInputs.size() ), buildOptions, temporaryBuffer, s, batchOut.data() );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
 			if ( !usesBatch( geometryPrimCount( buildInputs[i] ), buildOptions ) )
-				buildGeometry( c->info(), buildInputs[i], buildOptions, temporaryBuffer, s, geometriesOut[i] );
+				buildGeometry( c->info(), buildInputs[i], buildOptions, temporaryBuffer, s, geometriesOut[i], qRegions.empty() ? nullptr : qRegions[i] );
 	} );
 }
 
@@ -579,6 +613,8 @@ hiprtError hiprtCompactGeometries(
 			boxBytes[i]			  = RoundUp( size_t( headers[i].boxNodeCount ) * sizeof( Box4Node ), size_t( 64 ) );
 			leafBytes[i]		  = RoundUp( size_t( headers[i].primNodeCount ) * leafSize, size_t( 64 ) );
 			sizes[i]			  = 64 + boxBytes[i] + leafBytes[i];
+			// a geometry that has a Q region keeps one: regenerated behind the compacted structure
+			if ( c->geometryInfo( geometriesIn[i] ).qRegion ) sizes[i] += qRegionSize( headers[i].boxNodeCount );
 		}
 		const std::vector<void*> out = c->allocatePool( sizes );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
@@ -589,10 +625,12 @@ hiprtError hiprtCompactGeometries(
 			checkCuda( cudaMemcpyAsync( dst + 64 + boxBytes[i], headers[i].primNodes, leafBytes[i], cudaMemcpyDeviceToDevice, s ), "copy leaves" );
 			h.boxNodes	= reinterpret_cast<Box4Node*>( dst + 64 );
 			h.primNodes = dst + 64 + boxBytes[i];
-			h.size		= sizes[i];
+			h.size		= 64 + boxBytes[i] + leafBytes[i];
 			checkCuda( cudaMemcpyAsync( dst, &h, sizeof( GeomHeader ), cudaMemcpyHostToDevice, s ), "write header" );
 			*geometriesOut[i] = reinterpret_cast<hiprtGeometry>( dst );
-			c->noteGeometryKind( dst, headers[i].geomType & 1u );
+			void* q = sizes[i] > h.size ? dst + h.size : nullptr;
+			compressBoxNodes( reinterpret_cast<const GeomHeader*>( dst ), q, headers[i].boxNodeCount, s );
+			c->noteGeometryKind( dst, headers[i].geomType & 1u, q );
 		}
 		checkCuda( cudaStreamSynchronize( s ), "cudaStreamSynchronize" );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
@@ -857,6 +895,7 @@ hiprtError hiprtLoadGeometry( hiprtContext context, hiprtGeometry& geometryOut, 
 		f.seekg( 0 );
 		f.read( reinterpret_cast<char*>( buf.data() ), std::streamsize( buf.size() ) );
 		if ( !f ) throw std::runtime_error( "truncated geometry file" );
+		// (no Q region: a file may hold an imported hierarchy whose leaf boxes are not the boxes of the vertices -- qnode.h)
 		const std::vector<void*> out = ctx( context )->allocatePool( { size_t( h.size ) } );
 		const uintptr_t			 base = reinterpret_cast<uintptr_t>( out[0] );
 		h.boxNodes					  = reinterpret_cast<Box4Node*>( reinterpret_cast<uintptr_t>( h.boxNodes ) + base );
@@ -980,8 +1019,11 @@ hiprtError hiprtB200TraceGeometry(
 {
 	if ( !context || !geometry || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
-		const bool triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) );
-		traceGeometry( geometry, triangles, rays, numRays, hits, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ) );
+		const void* q		 = nullptr;
+		const bool	triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ), &q );
+		traceGeometry(
+			geometry, triangles, rays, numRays, hits, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
+			hiprtB200HitFormatFull, q );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
 }
@@ -1029,8 +1071,11 @@ hiprtError hiprtB200TraceGeometryHost(
 {
 	if ( !context || !geometry || numRays == 0 || !hostRays || !hostHits ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
-		const bool triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) );
-		ctx( context )->hostPipeline.run( geometry, triangles, nullptr, hostRays, numRays, hostHits, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount );
+		const void* q		 = nullptr;
+		const bool	triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ), &q );
+		ctx( context )->hostPipeline.run(
+			geometry, triangles, nullptr, hostRays, numRays, hostHits, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount,
+			hiprtB200HitFormatFull, q );
 	} );
 }
 
@@ -1059,12 +1104,13 @@ hiprtError hiprtB200TraceGeometryFormat(
 	hiprtApiStream stream )
 {
 	if ( !context || !geometry || ( numRays && ( !rays || !records ) ) || uint32_t( format ) > hiprtB200HitFormatPrimID ) return hiprtErrorInvalidParameter;
-	const bool triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) );
+	const void* q		 = nullptr;
+	const bool	triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ), &q );
 	if ( !triangles && format != hiprtB200HitFormatFull ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
 		traceGeometry(
 			geometry, triangles, rays, numRays, records, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
-			uint32_t( format ) );
+			uint32_t( format ), q );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
 }
@@ -1074,12 +1120,13 @@ hiprtError hiprtB200TraceGeometryFormatHost(
 	hiprtApiStream stream )
 {
 	if ( !context || !geometry || numRays == 0 || !hostRays || !hostRecords || uint32_t( format ) > hiprtB200HitFormatPrimID ) return hiprtErrorInvalidParameter;
-	const bool triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) );
+	const void* q		 = nullptr;
+	const bool	triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ), &q );
 	if ( !triangles && format != hiprtB200HitFormatFull ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
 		ctx( context )->hostPipeline.run(
 			geometry, triangles, nullptr, hostRays, numRays, hostRecords, type, hiprtFullRayMask, static_cast<cudaStream_t>( stream ), ctx( context )->info().smCount,
-			uint32_t( format ) );
+			uint32_t( format ), q );
 	} );
 }
 
@@ -1088,11 +1135,12 @@ hiprtError hiprtB200TraceGeometryStats(
 	hiprtApiStream stream )
 {
 	if ( !context || !geometry || !visitCounts || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
-	if ( !ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ) ) ) return hiprtErrorInvalidParameter;
+	const void* q = nullptr;
+	if ( !ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ), &q ) ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
 		traceGeometryStats(
 			geometry, rays, numRays, hits, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
-			reinterpret_cast<unsigned long long*>( visitCounts ) );
+			reinterpret_cast<unsigned long long*>( visitCounts ), q );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
 }
@@ -1110,7 +1158,13 @@ hiprtError hiprtB200GetGeometrySize( hiprtContext context, hiprtGeometry geometr
 hiprtError hiprtB200AllocateGeometryBlob( hiprtContext context, size_t size, hiprtGeometry* geometryOut )
 {
 	if ( !context || size < 64 || !geometryOut ) return hiprtErrorInvalidParameter;
-	return guarded( context, [&] { *geometryOut = reinterpret_cast<hiprtGeometry>( ctx( context )->allocatePool( { size } )[0] ); } );
+	// room for the Q region of the structure that will arrive (box nodes are at most the whole blob: 64 B per 128 B of them)
+	return guarded( context, [&] {
+		const size_t publicSize = ( size + 63 ) & ~size_t( 63 );
+		void*		 p			= ctx( context )->allocatePool( { publicSize + qRegionSize( size / sizeof( Box4Node ) ) } )[0];
+		ctx( context )->noteGeometryKind( p, false, nullptr, publicSize );
+		*geometryOut = reinterpret_cast<hiprtGeometry>( p );
+	} );
 }
 
 hiprtError hiprtB200RelocateGeometry( hiprtContext context, hiprtGeometry geometry, hiprtApiStream stream )
@@ -1119,6 +1173,20 @@ hiprtError hiprtB200RelocateGeometry( hiprtContext context, hiprtGeometry geomet
 	return guarded( context, [&] {
 		relocateGeometry( geometry, static_cast<cudaStream_t>( stream ) );
 		checkCuda( cudaGetLastError(), "relocate launch" );
+		// a blob from hiprtB200AllocateGeometryBlob has room for a Q region behind it: the sender's was not part of the copy,
+		// regenerate it here (a structure that is not a triangle mesh marks the region invalid on the device)
+		const auto info = ctx( context )->geometryInfo( geometry );
+		if ( info.blobSize )
+		{
+			uint32_t head[12];
+			checkCuda( cudaMemcpyAsync( head, geometry, sizeof( head ), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>( stream ) ), "cudaMemcpyAsync" );
+			checkCuda( cudaStreamSynchronize( static_cast<cudaStream_t>( stream ) ), "cudaStreamSynchronize" );
+			const GeomHeader* h = reinterpret_cast<const GeomHeader*>( head );
+			const bool		  triangles = h->geomType & 1u;
+			void*			  q = ( triangles && h->boxNodeCount <= info.blobSize / sizeof( Box4Node ) ) ? reinterpret_cast<uint8_t*>( geometry ) + info.blobSize : nullptr;
+			compressBoxNodes( reinterpret_cast<const GeomHeader*>( geometry ), q, h->boxNodeCount, static_cast<cudaStream_t>( stream ) );
+			ctx( context )->noteGeometryKind( geometry, triangles, q, info.blobSize );
+		}
 	} );
 }
 

@@ -2,6 +2,7 @@
 // (kernels: build_kernels.cuh; reference host side: hiprt/impl/LbvhBuilder.{h,cpp},
 // PlocBuilder.{h,cpp}, BatchBuilder.{h,cpp}, Context.cpp:144-290.)
 #include "batch_kernels.cuh"
+#include "qnode.h"
 
 namespace hiprt
 {
@@ -76,6 +77,22 @@ size_t geometryStorageSize( const hiprtGeometryBuildInput& input )
 	const size_t n		  = std::max( geometryPrimCount( input ), importLeafCount( input ) );
 	const size_t leafSize = input.type == hiprtPrimitiveTypeTriangleMesh ? sizeof( TrianglePairNode ) : sizeof( CustomNode );
 	return alignUp( sizeof( GeomHeader ) ) + alignUp( maxBoxNodeCount( n ) * sizeof( Box4Node ) ) + alignUp( n * leafSize );
+}
+
+// What hiprtCreateGeometry allocates: the public structure (`size` of the header, what hiprtSaveGeometry writes) followed, for
+// triangle meshes, by the traversal-only Q region of the library's own trace kernels (qnode.h).
+size_t geometryAllocationSize( const hiprtGeometryBuildInput& input )
+{
+	const size_t n = std::max( geometryPrimCount( input ), importLeafCount( input ) );
+	return geometryStorageSize( input ) + ( input.type == hiprtPrimitiveTypeTriangleMesh ? qRegionSize( maxBoxNodeCount( n ) ) : 0 );
+}
+
+// Where the Q region of a geometry built from `input` lies inside its allocation, or nullptr when such a build has none
+// (custom primitives, imported hierarchies whose leaf boxes are the caller's, a single primitive).
+void* geometryQRegion( const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* storage )
+{
+	if ( input.type != hiprtPrimitiveTypeTriangleMesh || isImport( options ) || geometryPrimCount( input ) < 2 ) return nullptr;
+	return static_cast<uint8_t*>( storage ) + geometryStorageSize( input );
 }
 
 size_t geometryTempSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
@@ -217,7 +234,7 @@ static void runImport(
 }
 
 void buildGeometry(
-	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* tempBuffer, cudaStream_t stream, void* storage )
+	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* tempBuffer, cudaStream_t stream, void* storage, void* qRegion )
 {
 	const bool import = isImport( options );
 	if ( import && ( input.nodeList.nodeCount == 0 || input.nodeList.leafNodes == nullptr || ( input.nodeList.nodeCount > 1 && input.nodeList.internalNodes == nullptr ) ) )
@@ -274,6 +291,12 @@ void buildGeometry(
 		primBoxesKernel<TriangleMeshSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
 		dev.mark( "boxes", stream );
 		runLbvh( dev, src, balanced, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
+		if ( qRegion )
+		{
+			compressBoxNodes( header, qRegion, uint32_t( maxBoxNodeCount( nMax ) ), stream );
+			dev.mark( "qnodes", stream );
+			HIPRT_CUDA_CHECK( cudaGetLastError() );
+		}
 	}
 	else
 	{
@@ -370,7 +393,7 @@ void buildScene(
 // Refit in place (hiprtBuildOperationUpdate): same primitive count and order as the build, moved positions. The kernels take
 // the node arrays from the device header, so a compacted, loaded or imported structure is updated where it actually lies.
 void updateGeometry(
-	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions, void*, cudaStream_t stream, void* storage )
+	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions, void*, cudaStream_t stream, void* storage, void* qRegion )
 {
 	(void)dev;
 	const uint32_t nMax = uint32_t( std::max( geometryPrimCount( input ), importLeafCount( input ) ) );
@@ -387,6 +410,7 @@ void updateGeometry(
 		src.triangleStride = m.triangleStride;
 		src.pairs		   = nullptr; // the pairing is read back from the leaves
 		refitKernel<TriangleMeshSource><<<grid, 128, 0, stream>>>( src, header, &header->boxNodeCount );
+		compressBoxNodes( header, qRegion, uint32_t( maxBoxNodeCount( nMax ) ), stream ); // (no-op without a Q region)
 	}
 	else
 	{

@@ -43,19 +43,24 @@ struct DeviceInfo
 
 // ---- sizes -------------------------------------------------------------------------------------
 size_t geometryPrimCount( const hiprtGeometryBuildInput& input ); // triangles (or pairs if given) / AABBs
-size_t geometryStorageSize( const hiprtGeometryBuildInput& input );
+size_t geometryStorageSize( const hiprtGeometryBuildInput& input );	   // the public structure: header.size
+size_t geometryAllocationSize( const hiprtGeometryBuildInput& input ); // + the traversal-only Q region of triangle meshes (qnode.h)
+void*  geometryQRegion( const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* storage ); // nullptr: this build has none
 size_t geometryTempSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options );
 size_t sceneStorageSize( const hiprtSceneBuildInput& input );
 size_t sceneTempSize( const hiprtSceneBuildInput& input, hiprtBuildOptions options );
 
 // ---- builds (asynchronous on `stream`) -----------------------------------------------------------
+// qRegion: geometryQRegion() of the same input (the Q records are generated as the last step), or nullptr
 void buildGeometry(
-	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage );
+	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage,
+	void* qRegion = nullptr );
 void buildScene(
 	const DeviceInfo& dev, const hiprtSceneBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage );
 // refit in place (hiprtBuildOperationUpdate)
 void updateGeometry(
-	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage );
+	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage,
+	void* qRegion = nullptr );
 void updateScene(
 	const DeviceInfo& dev, const hiprtSceneBuildInput& input, hiprtBuildOptions options, void* temp, cudaStream_t stream, void* storage );
 // many small geometries in one launch (one CTA per geometry)

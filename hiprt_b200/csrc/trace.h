@@ -10,13 +10,14 @@ namespace hiprt
 // triangles: the geometry holds triangle pairs (fast kernel) rather than custom primitives (generic kernel)
 // format: hiprtB200HitFormat of the output records (`hits` then points to 48-, 16- or 4-byte records); formats other than the
 // full hiprtHit exist for triangle geometries only
+// qRegion: the geometry's traversal-only Q region (qnode.h) when it has one -- box nodes are then read from its 64-byte records
 void traceGeometry(
 	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, void* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount,
-	cudaStream_t stream, uint32_t format = 0 );
+	cudaStream_t stream, uint32_t format = 0, const void* qRegion = nullptr );
 // instrumented variant of the triangle kernel: adds {box-node visits, leaf visits} of the launch to stats[0..1]
 void traceGeometryStats(
 	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream,
-	unsigned long long* stats );
+	unsigned long long* stats, const void* qRegion = nullptr );
 // times: optional device array of one time per ray (motion blur); nullptr = every ray at `time`
 void traceScene(
 	hiprtScene scene, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, hiprtRayMask mask, uint32_t* workCounter, uint32_t smCount,

@@ -9,6 +9,7 @@
 #include <hiprt/hiprt_device.h>
 
 #include "builders.h"
+#include "qnode.h"
 #include "trace.h"
 
 #include <algorithm>
@@ -165,6 +166,9 @@ __global__ void __launch_bounds__( Block ) traceGeometryKernel(
 //    per ray at the end by re-running the reference-order test on the winning triangle.
 // The winner is the minimum of (t, primID), as in hiprt::acceptCloser.
 constexpr uint32_t GeneralOctant = 8;
+#ifndef HIPRT_B200_SORT_ANY_HIT
+#define HIPRT_B200_SORT_ANY_HIT 0 // 1 = any-hit rays also visit children nearest first (the round-1 kernel)
+#endif
 
 // 32-byte read-only load (LDG.E.256, sm_100+): a 128-byte box node is 4 of these instead of 7 16-byte loads, a
 // 64-byte triangle pair 2 instead of 4 -- the traversal is bound by L1TEX wavefronts (one per distinct line and
@@ -256,26 +260,9 @@ __device__ __forceinline__ bool slabTest( const float* b, const float3 o, const 
 	}
 }
 
-// One box-node visit: tests the four children, leaves the hit ones sorted (nearest last) in c[4-n..3].
-template <uint32_t Octant, bool Hints = false>
-__device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxNodes, uint32_t node, const float3 o, const float3 invD, float maxT, uint32_t c[4] )
+// Exchange network shared by the exact and the quantised visit: leaves the hit children sorted, nearest last.
+__device__ __forceinline__ void sortChildren( float d[4], uint32_t c[4] )
 {
-	const void* p  = boxNodes + ( node >> 4 );
-	const F8	w0 = ldg8<Hints>( p, 0 ), w1 = ldg8<Hints>( p, 1 ), w2 = ldg8<Hints>( p, 2 ), w3 = ldg8<Hints>( p, 3 );
-	const float b[24] = { w0.v[4], w0.v[5], w0.v[6], w0.v[7], w1.v[0], w1.v[1], w1.v[2], w1.v[3], w1.v[4], w1.v[5], w1.v[6], w1.v[7],
-						  w2.v[0], w2.v[1], w2.v[2], w2.v[3], w2.v[4], w2.v[5], w2.v[6], w2.v[7], w3.v[0], w3.v[1], w3.v[2], w3.v[3] };
-	c[0] = __float_as_uint( w0.v[0] ), c[1] = __float_as_uint( w0.v[1] ), c[2] = __float_as_uint( w0.v[2] ), c[3] = __float_as_uint( w0.v[3] );
-	float	 d[4];
-	uint32_t n = 0;
-#pragma unroll
-	for ( int s = 0; s < 4; ++s )
-	{
-		float	   t0;
-		const bool hit = slabTest<Octant>( b + 6 * s, o, invD, maxT, t0 ) && c[s] != InvalidValue; // (unused slots need not hold the empty box)
-		d[s]		   = hit ? t0 : __int_as_float( 0xff800000 );
-		c[s]		   = hit ? c[s] : InvalidValue;
-		n += hit ? 1u : 0u;
-	}
 #define HIPRT_B200_CSWAP( A, B )                                     \
 	{                                                                \
 		const bool	   sw = d[B] < d[A];                             \
@@ -289,7 +276,183 @@ __device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxN
 	HIPRT_B200_CSWAP( 2, 3 )
 	HIPRT_B200_CSWAP( 1, 2 )
 #undef HIPRT_B200_CSWAP
+}
+
+// One box-node visit: tests the four children, leaves the hit ones sorted (nearest last) in c[4-n..3].
+// Sort == false (any-hit queries: the answer is occluded / not occluded, whichever order finds it): no ordering network and no
+// entry distances -- returns the 4-bit mask of hit children and leaves c[] as loaded.
+template <uint32_t Octant, bool Hints = false, bool Sort = true>
+__device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxNodes, uint32_t node, const float3 o, const float3 invD, float maxT, uint32_t c[4] )
+{
+	const void* p  = boxNodes + ( node >> 4 );
+	const F8	w0 = ldg8<Hints>( p, 0 ), w1 = ldg8<Hints>( p, 1 ), w2 = ldg8<Hints>( p, 2 ), w3 = ldg8<Hints>( p, 3 );
+	const float b[24] = { w0.v[4], w0.v[5], w0.v[6], w0.v[7], w1.v[0], w1.v[1], w1.v[2], w1.v[3], w1.v[4], w1.v[5], w1.v[6], w1.v[7],
+						  w2.v[0], w2.v[1], w2.v[2], w2.v[3], w2.v[4], w2.v[5], w2.v[6], w2.v[7], w3.v[0], w3.v[1], w3.v[2], w3.v[3] };
+	c[0] = __float_as_uint( w0.v[0] ), c[1] = __float_as_uint( w0.v[1] ), c[2] = __float_as_uint( w0.v[2] ), c[3] = __float_as_uint( w0.v[3] );
+	if constexpr ( !Sort )
+	{
+		uint32_t mask = 0;
+#pragma unroll
+		for ( int s = 0; s < 4; ++s )
+		{
+			float t0;
+			if ( slabTest<Octant>( b + 6 * s, o, invD, maxT, t0 ) && c[s] != InvalidValue ) mask |= 1u << s;
+		}
+		return mask;
+	}
+	float	 d[4];
+	uint32_t n = 0;
+#pragma unroll
+	for ( int s = 0; s < 4; ++s )
+	{
+		float	   t0;
+		const bool hit = slabTest<Octant>( b + 6 * s, o, invD, maxT, t0 ) && c[s] != InvalidValue; // (unused slots need not hold the empty box)
+		d[s]		   = hit ? t0 : __int_as_float( 0xff800000 );
+		c[s]		   = hit ? c[s] : InvalidValue;
+		n += hit ? 1u : 0u;
+	}
+	sortChildren( d, c );
 	return n;
+}
+
+// One box-node visit through the 64-byte quantised record (qnode.h): two 32-byte loads instead of four. The plane distance of
+// plane index q on axis a is ((origin + q * cell) - o) * invD = val * A + B with val = 1 + q * 2^-15 (a float assembled from the
+// byte by ONE byte-permute), A = cell * 2^15 * invD (exact: cell is a power of two) and B = (origin - o) * invD - A, one FFMA
+// per plane, rounded down for entry and up for exit planes. Entry / exit distances are then widened by 2^-20 relative: together
+// with the grid cell of margin the builder leaves around every child box this makes the test conservative with respect to the
+// exact float32 slab test (see qnode.h for the argument). Same contract as visitBox4.
+template <bool Hints, bool Sort>
+__device__ __forceinline__ uint32_t visitBox4Q( const QBox4Node* __restrict__ qNodes, uint32_t node, const float3 o, const float3 invD, float maxT, uint32_t c[4] )
+{
+	const void* p  = qNodes + ( node >> 4 );
+	const F8	w0 = ldg8<Hints>( p, 0 ), w1 = ldg8<Hints>( p, 1 );
+	const float ax = __fmul_rn( w0.v[3], invD.x ), ay = __fmul_rn( w0.v[4], invD.y ), az = __fmul_rn( w0.v[5], invD.z );
+	const float bx = __fsub_rn( __fmul_rn( __fsub_rn( w0.v[0], o.x ), invD.x ), ax );
+	const float by = __fsub_rn( __fmul_rn( __fsub_rn( w0.v[1], o.y ), invD.y ), ay );
+	const float bz = __fsub_rn( __fmul_rn( __fsub_rn( w0.v[2], o.z ), invD.z ), az );
+	c[0] = __float_as_uint( w0.v[6] ), c[1] = __float_as_uint( w0.v[7] ), c[2] = __float_as_uint( w1.v[0] ), c[3] = __float_as_uint( w1.v[1] );
+	const uint32_t lox = __float_as_uint( w1.v[2] ), loy = __float_as_uint( w1.v[3] ), loz = __float_as_uint( w1.v[4] );
+	const uint32_t hix = __float_as_uint( w1.v[5] ), hiy = __float_as_uint( w1.v[6] ), hiz = __float_as_uint( w1.v[7] );
+	// entry planes: lo where the ray travels in +axis, hi otherwise
+	const bool	   nx = invD.x < 0.0f, ny = invD.y < 0.0f, nz = invD.z < 0.0f;
+	const uint32_t enx = nx ? hix : lox, eny = ny ? hiy : loy, enz = nz ? hiz : loz;
+	const uint32_t exx = nx ? lox : hix, exy = ny ? loy : hiy, exz = nz ? loz : hiz;
+	constexpr float Shrink = 0.99999904632568359375f, Grow = 1.00000095367431640625f, Tiny = 1.0e-30f; // 1 -+ 2^-20
+	float			d[4];
+	uint32_t		n = 0;
+#pragma unroll
+	for ( int s = 0; s < 4; ++s )
+	{
+		const uint32_t sel = 0x7604u | ( uint32_t( s ) << 4 ); // result bytes {0x00, byte s, 0x80, 0x3F}: 1 + q * 2^-15
+		const float	   t0x = __fmaf_rd( __uint_as_float( __byte_perm( enx, 0x3F800000u, sel ) ), ax, bx );
+		const float	   t0y = __fmaf_rd( __uint_as_float( __byte_perm( eny, 0x3F800000u, sel ) ), ay, by );
+		const float	   t0z = __fmaf_rd( __uint_as_float( __byte_perm( enz, 0x3F800000u, sel ) ), az, bz );
+		const float	   t1x = __fmaf_ru( __uint_as_float( __byte_perm( exx, 0x3F800000u, sel ) ), ax, bx );
+		const float	   t1y = __fmaf_ru( __uint_as_float( __byte_perm( exy, 0x3F800000u, sel ) ), ay, by );
+		const float	   t1z = __fmaf_ru( __uint_as_float( __byte_perm( exz, 0x3F800000u, sel ) ), az, bz );
+		const float	   t0  = __fmaf_rd( fmaxf( fmaxf( fmaxf( t0x, t0y ), t0z ), 0.0f ), Shrink, -Tiny );
+		const float	   t1  = __fmaf_ru( fminf( fminf( fminf( t1x, t1y ), t1z ), maxT ), Grow, Tiny );
+		const bool	   hit = t0 <= t1; // unused slots hold an inverted box (entry plane 255 cells behind the exit plane): never hit
+		if constexpr ( Sort )
+		{
+			d[s] = hit ? t0 : __int_as_float( 0xff800000 );
+			c[s] = hit ? c[s] : InvalidValue;
+			n += hit ? 1u : 0u;
+		}
+		else
+			n |= hit ? ( 1u << s ) : 0u;
+	}
+	if constexpr ( Sort ) sortChildren( d, c );
+	return n;
+}
+
+// The quantised walk is valid for rays whose exact slab arithmetic is free of NaN / infinity (qnode.h): every direction
+// component finite, non-zero and of sane magnitude, origin finite and within the coordinate range the Q grid covers.
+__device__ __forceinline__ bool regularForQ( const hiprtRay& ray )
+{
+	const float dx = fabsf( ray.direction.x ), dy = fabsf( ray.direction.y ), dz = fabsf( ray.direction.z );
+	constexpr float Lo = 8.6736173798840355e-19f, Hi = 1152921504606846976.0f; // 2^-60, 2^60
+	return dx >= Lo && dx <= Hi && dy >= Lo && dy <= Hi && dz >= Lo && dz <= Hi && fabsf( ray.origin.x ) <= QMaxCoordinate &&
+		   fabsf( ray.origin.y ) <= QMaxCoordinate && fabsf( ray.origin.z ) <= QMaxCoordinate; // (comparisons are false for NaN)
+}
+
+// One triangle-pair leaf against the ray: shortens ray.maxT and records the winner as the traversal loops below expect.
+// CheckBox (quantised walk only): the leaf's own box -- the box of its vertices, exactly what the builder stored in the parent
+// node -- first goes through the EXACT slab test; a leaf the exact traversal would not have reached is skipped.
+// The box test runs against the ray's ORIGINAL extent `boxMaxT`, not the current one: the exact walk tested this box when it
+// visited the parent, i.e. against an extent that was at least the current one -- an exact tie (a duplicated triangle, or a
+// flat box whose slab distance lies an ulp beyond the triangle's t) must not be culled because its twin was intersected first.
+template <hiprtTraversalType Type, bool Hints, bool CheckBox>
+__device__ __forceinline__ bool visitPairLeaf(
+	const TrianglePairNode* __restrict__ leaves, uint32_t addr, hiprtRay& ray, const float3 invD, uint32_t& bestRef, uint32_t& bestPrim, float boxMaxT = 0.0f )
+{
+	const void*	   p  = leaves + addr;
+	const F8	   l0 = ldg8<Hints>( p, 0 ), l1 = ldg8<Hints>( p, 1 );
+	const uint32_t prim0 = __float_as_uint( l1.v[5] ), prim1 = __float_as_uint( l1.v[6] );
+	const float3   pv0 = make_float3( l0.v[0], l0.v[1], l0.v[2] ), pv1 = make_float3( l0.v[3], l0.v[4], l0.v[5] );
+	const float3   pv2 = make_float3( l0.v[6], l0.v[7], l1.v[0] ), pv3 = make_float3( l1.v[1], l1.v[2], l1.v[3] );
+	if constexpr ( CheckBox )
+	{
+		// (a lone triangle repeats v2 in v3: the box of four vertices is the box of three)
+		const float b[6] = { fminf( fminf( pv0.x, pv1.x ), fminf( pv2.x, pv3.x ) ), fminf( fminf( pv0.y, pv1.y ), fminf( pv2.y, pv3.y ) ),
+							 fminf( fminf( pv0.z, pv1.z ), fminf( pv2.z, pv3.z ) ), fmaxf( fmaxf( pv0.x, pv1.x ), fmaxf( pv2.x, pv3.x ) ),
+							 fmaxf( fmaxf( pv0.y, pv1.y ), fmaxf( pv2.y, pv3.y ) ), fmaxf( fmaxf( pv0.z, pv1.z ), fmaxf( pv2.z, pv3.z ) ) };
+		float		t0;
+		if ( !slabTest<GeneralOctant>( b, ray.origin, invD, boxMaxT, t0 ) ) return false;
+	}
+	bool		found = false;
+	HitTriangle h;
+	if ( intersectTriangle( pv0, pv1, pv2, ray, h ) && ( h.t < ray.maxT || prim0 < bestPrim ) )
+	{
+		ray.maxT = h.t, bestRef = addr << 1, bestPrim = prim0;
+		found = true;
+	}
+	if ( prim0 != prim1 && !( Type == hiprtTraversalTerminateAtAnyHit && found ) )
+	{
+		if ( intersectTriangle( pv1, pv3, pv2, ray, h ) && ( h.t < ray.maxT || prim1 < bestPrim ) )
+		{
+			ray.maxT = h.t, bestRef = ( addr << 1 ) | 1u, bestPrim = prim1;
+			found = true;
+		}
+	}
+	return found;
+}
+
+// Exact traversal of ONE lane's ray, callable from divergent code (no warp votes): what a lane of the quantised kernels runs
+// for a ray regularForQ() rejects. Stack = the lane's shared-memory column, then its local array. Returns false on overflow.
+template <hiprtTraversalType Type, uint32_t SharedDepth, bool Hints>
+__device__ __forceinline__ bool traceLaneExact(
+	const Box4Node* __restrict__ boxNodes, const TrianglePairNode* __restrict__ leaves, hiprtRay& ray, uint32_t* const stackBase, uint32_t* localStack,
+	uint32_t& bestRef, uint32_t& bestPrim )
+{
+	constexpr uint32_t TotalDepth = 64;
+	const float3	   invD		  = rcp3( ray.direction );
+	uint32_t		   top = 0, node = RootIndex;
+	while ( node != InvalidValue )
+	{
+		if ( isBoxIndex( node ) )
+		{
+			uint32_t c[4];
+			visitBox4<GeneralOctant, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c );
+			if ( top + 3 > TotalDepth ) return false;
+#pragma unroll
+			for ( int k = 3; k >= 0; --k )
+				if ( c[k] != InvalidValue )
+				{
+					if ( top < SharedDepth )
+						stackBase[top * 32u] = c[k];
+					else
+						localStack[top - SharedDepth] = c[k];
+					++top;
+				}
+		}
+		else if ( visitPairLeaf<Type, Hints, false>( leaves, node >> 3, ray, invD, bestRef, bestPrim ) && Type == hiprtTraversalTerminateAtAnyHit )
+			return true;
+		if ( top == 0 ) break;
+		--top;
+		node = top < SharedDepth ? stackBase[top * 32u] : localStack[top - SharedDepth];
+	}
+	return true;
 }
 
 // Traversal of one ray per lane; every lane of the warp must call it (warp votes inside), `live` = has a ray.
@@ -297,7 +460,9 @@ __device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxN
 // Refill  > 0: lane-granular persistent threads -- whenever at least `Refill` lanes are idle (their ray is finished) those
 // lanes write their hits and fetch the next rays from `workCounter`, the others keep their state; returns when the ray
 // buffer is exhausted and every lane is done. Pays off for incoherent rays only (see the kernel below).
-template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum, uint32_t Refill = 0, uint32_t Format = hiprtB200HitFormatFull, bool Hints = false, bool Stats = false>
+// Q: box nodes are visited through the quantised 64-byte records `qNodes` (qnode.h); a lane whose ray regularForQ() rejects
+// runs the exact traversal of that ray on its own (divergent, rare) and rejoins the warp as an idle lane.
+template <hiprtTraversalType Type, uint32_t SharedDepth, uint32_t BoxQuorum, uint32_t Refill = 0, uint32_t Format = hiprtB200HitFormatFull, bool Hints = false, bool Stats = false, bool Q = false>
 __device__ __forceinline__ void traceTrianglesWarp(
 	const Box4Node* __restrict__ boxNodes,
 	const TrianglePairNode* __restrict__ leaves,
@@ -308,9 +473,12 @@ __device__ __forceinline__ void traceTrianglesWarp(
 	uint32_t* const stackBase,
 	uint32_t*		workCounter = nullptr,
 	uint32_t		numRays		= 0,
-	unsigned long long* stats	= nullptr ) // Stats: {box-node visits, leaf visits} of the launch are added here
+	unsigned long long* stats	= nullptr, // Stats: {box-node visits, leaf visits} of the launch are added here
+	const QBox4Node* __restrict__ qNodes = nullptr,
+	bool				qInvalid		 = false ) // the Q region is marked unusable: every ray takes the exact path
 {
 	constexpr uint32_t TotalDepth = 64; // the reference's private stack size
+	constexpr bool	   Sort		  = Type != hiprtTraversalTerminateAtAnyHit || HIPRT_B200_SORT_ANY_HIT;
 	uint32_t		   localStack[TotalDepth - SharedDepth];
 	uint32_t		   top = 0;
 	uint32_t		   boxVisits = 0, leafVisits = 0;
@@ -334,7 +502,18 @@ __device__ __forceinline__ void traceTrianglesWarp(
 		const uint32_t first	 = __shfl_sync( FullMask, mine, liveLanes ? __ffs( liveLanes ) - 1 : 0 );
 		octant					 = __all_sync( FullMask, !live || ( regular && mine == first ) ) ? first : GeneralOctant;
 	};
-	if ( Refill == 0 ) chooseOctant();
+	if ( Refill == 0 && !Q ) chooseOctant();
+	// (Q) a ray the quantised walk must not see: traced exactly by its lane right here; the lane then waits as a finished one
+#define HIPRT_B200_EXACT_IF_IRREGULAR()                                                                                                    \
+	if constexpr ( Q )                                                                                                                     \
+	{                                                                                                                                      \
+		if ( live && node != InvalidValue && ( qInvalid || !regularForQ( ray ) ) )                                                         \
+		{                                                                                                                                  \
+			overflow = !traceLaneExact<Type, SharedDepth, Hints>( boxNodes, leaves, ray, stackBase, localStack, bestRef, bestPrim );       \
+			node	 = InvalidValue;                                                                                                       \
+		}                                                                                                                                  \
+	}
+	HIPRT_B200_EXACT_IF_IRREGULAR()
 
 	// result of the lane's finished ray: uv mapping and normal by re-running the reference-order test on the winning triangle
 	auto finish = [&]() {
@@ -393,8 +572,9 @@ __device__ __forceinline__ void traceTrianglesWarp(
 						node	 = RootIndex;
 						live	 = true;
 					}
+					HIPRT_B200_EXACT_IF_IRREGULAR()
 				}
-				if ( !__any_sync( FullMask, node != InvalidValue ) ) break;
+				if ( !__any_sync( FullMask, node != InvalidValue ) && exhausted ) break;
 			}
 		}
 		else
@@ -414,20 +594,65 @@ __device__ __forceinline__ void traceTrianglesWarp(
 				uint32_t c[4];
 				uint32_t n;
 				if constexpr ( Stats ) ++boxVisits;
+				if constexpr ( Q )
+					n = visitBox4Q<Hints, Sort>( qNodes, node, ray.origin, invD, ray.maxT, c );
+				else
+				{
 				switch ( octant ) // warp-uniform
 				{
-				case 0: n = visitBox4<0, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 1: n = visitBox4<1, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 2: n = visitBox4<2, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 3: n = visitBox4<3, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 4: n = visitBox4<4, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 5: n = visitBox4<5, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 6: n = visitBox4<6, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				case 7: n = visitBox4<7, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
-				default: n = visitBox4<GeneralOctant, Hints>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 0: n = visitBox4<0, Hints, Sort>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 1: n = visitBox4<1, Hints, Sort>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 2: n = visitBox4<2, Hints, Sort>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 3: n = visitBox4<3, Hints, Sort>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 4: n = visitBox4<4, Hints, Sort>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 5: n = visitBox4<5, Hints, Sort>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 6: n = visitBox4<6, Hints, Sort>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				case 7: n = visitBox4<7, Hints, Sort>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				default: n = visitBox4<GeneralOctant, Hints, Sort>( boxNodes, node, ray.origin, invD, ray.maxT, c ); break;
+				}
+				}
+				if constexpr ( !Sort )
+				{
+					// n = mask of hit children: pushed in slot order (predicated stores), the last one pushed is popped again
+					if ( top + 4 <= SharedDepth )
+					{
+#pragma unroll
+						for ( int k = 0; k < 4; ++k )
+							if ( ( n >> k ) & 1u )
+							{
+								stackBase[top * 32u] = c[k];
+								++top;
+							}
+						node = InvalidValue;
+						if ( top != 0 )
+						{
+							--top;
+							node = stackBase[top * 32u];
+						}
+					}
+					else if ( top + 3 > TotalDepth )
+					{
+						overflow = true;
+						node	 = InvalidValue;
+						top		 = 0;
+					}
+					else
+					{
+#pragma unroll
+						for ( int k = 0; k < 4; ++k )
+							if ( ( n >> k ) & 1u )
+							{
+								if ( top < SharedDepth )
+									stackBase[top * 32u] = c[k];
+								else
+									localStack[top - SharedDepth] = c[k];
+								++top;
+							}
+						node = pop();
+					}
 				}
 				// hit children: c[4-n..3], nearest first. Far-to-near onto the stack, then the nearest is popped.
-				if ( top + 4 <= SharedDepth )
+				else if ( top + 4 <= SharedDepth )
 				{
 					uint32_t* slot = stackBase + top * 32u;
 					slot[0] = c[3], slot[32] = c[2], slot[64] = c[1], slot[96] = c[0];
@@ -465,28 +690,8 @@ __device__ __forceinline__ void traceTrianglesWarp(
 		// ---- leaf phase
 		if ( node != InvalidValue && !isBoxIndex( node ) )
 		{
-			const uint32_t addr = node >> 3;
-			const void*	   p	= leaves + addr;
 			if constexpr ( Stats ) ++leafVisits;
-			const F8	   l0 = ldg8<Hints>( p, 0 ), l1 = ldg8<Hints>( p, 1 );
-			const uint32_t prim0 = __float_as_uint( l1.v[5] ), prim1 = __float_as_uint( l1.v[6] );
-			const float3   pv0 = make_float3( l0.v[0], l0.v[1], l0.v[2] ), pv1 = make_float3( l0.v[3], l0.v[4], l0.v[5] );
-			const float3   pv2 = make_float3( l0.v[6], l0.v[7], l1.v[0] ), pv3 = make_float3( l1.v[1], l1.v[2], l1.v[3] );
-			bool		   found = false;
-			HitTriangle	   h;
-			if ( intersectTriangle( pv0, pv1, pv2, ray, h ) && ( h.t < ray.maxT || prim0 < bestPrim ) )
-			{
-				ray.maxT = h.t, bestRef = addr << 1, bestPrim = prim0;
-				found = true;
-			}
-			if ( prim0 != prim1 && !( Type == hiprtTraversalTerminateAtAnyHit && found ) )
-			{
-				if ( intersectTriangle( pv1, pv3, pv2, ray, h ) && ( h.t < ray.maxT || prim1 < bestPrim ) )
-				{
-					ray.maxT = h.t, bestRef = ( addr << 1 ) | 1u, bestPrim = prim1;
-					found = true;
-				}
-			}
+			const bool found = visitPairLeaf<Type, Hints, Q>( leaves, node >> 3, ray, invD, bestRef, bestPrim, maxT0 );
 			if ( Type == hiprtTraversalTerminateAtAnyHit && found )
 			{
 				node = InvalidValue;
@@ -497,6 +702,7 @@ __device__ __forceinline__ void traceTrianglesWarp(
 		}
 	}
 
+#undef HIPRT_B200_EXACT_IF_IRREGULAR
 	if ( Refill == 0 && live ) finish();
 	if constexpr ( Stats )
 	{
@@ -516,15 +722,24 @@ __device__ __forceinline__ void traceTrianglesWarp(
 // Refill > 0 (persistent only): a warp whose fetched batch is INCOHERENT (mixed direction octants: AO / diffuse bounces)
 // keeps that batch and from then on refills idle lanes one by one; ncu shows 15 of 32 lanes active on 8-spp AO rays without
 // it. Coherent batches (primary, shadow rays) stay warp-granular: refilling them lane by lane was measured 12-18 % slower.
-template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill = 0, uint32_t Format = hiprtB200HitFormatFull, bool Hints = false, bool Stats = false>
+// Q: `qRegion` = the geometry's Q region (QHeader + QBox4Node per box node, qnode.h); box nodes are read from there.
+template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill = 0, uint32_t Format = hiprtB200HitFormatFull, bool Hints = false, bool Stats = false, bool Q = false>
 __global__ void __launch_bounds__( Block, Refill != 0 ? 1024u / Block : 1u ) traceTrianglesKernel(
-	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, void* __restrict__ hits, uint32_t* workCounter, unsigned long long* stats )
+	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, void* __restrict__ hits, uint32_t* workCounter, unsigned long long* stats,
+	const void* __restrict__ qRegion )
 {
 	__shared__ uint32_t sStack[Block * SharedDepth];
 	const GeomHeader*	header					 = reinterpret_cast<const GeomHeader*>( geom );
 	const Box4Node* __restrict__ boxNodes		 = header->boxNodes;
 	const TrianglePairNode* __restrict__ leaves = reinterpret_cast<const TrianglePairNode*>( header->primNodes );
 	uint32_t* const stackBase = sStack + ( threadIdx.x & 31u ) + ( threadIdx.x >> 5 ) * 32u * SharedDepth;
+	const QBox4Node* __restrict__ qNodes = nullptr;
+	bool qInvalid						 = false;
+	if constexpr ( Q )
+	{
+		qNodes	 = reinterpret_cast<const QBox4Node*>( static_cast<const uint8_t*>( qRegion ) + sizeof( QHeader ) );
+		qInvalid = __ldg( &static_cast<const QHeader*>( qRegion )->invalid ) != 0u;
+	}
 	if constexpr ( Persistent )
 	{
 		const uint32_t lane = threadIdx.x & 31u;
@@ -545,17 +760,17 @@ __global__ void __launch_bounds__( Block, Refill != 0 ? 1024u / Block : 1u ) tra
 				const bool	   coherent = __all_sync( FullMask, mine == first );
 				if ( !coherent )
 				{
-					traceTrianglesWarp<Type, SharedDepth, BoxQuorum, Refill, Format, Hints, Stats>( boxNodes, leaves, rays, hits, index, live, stackBase, workCounter, numRays, stats );
+					traceTrianglesWarp<Type, SharedDepth, BoxQuorum, Refill, Format, Hints, Stats, Q>( boxNodes, leaves, rays, hits, index, live, stackBase, workCounter, numRays, stats, qNodes, qInvalid );
 					return; // the refilling traversal drains the ray buffer
 				}
 			}
-			traceTrianglesWarp<Type, SharedDepth, BoxQuorum, 0, Format, Hints, Stats>( boxNodes, leaves, rays, hits, index, live, stackBase, nullptr, 0, stats );
+			traceTrianglesWarp<Type, SharedDepth, BoxQuorum, 0, Format, Hints, Stats, Q>( boxNodes, leaves, rays, hits, index, live, stackBase, nullptr, 0, stats, qNodes, qInvalid );
 		}
 	}
 	else
 	{
 		const uint32_t index = blockIdx.x * Block + threadIdx.x;
-		traceTrianglesWarp<Type, SharedDepth, BoxQuorum, 0, Format, Hints, Stats>( boxNodes, leaves, rays, hits, index, index < numRays, stackBase, nullptr, 0, stats );
+		traceTrianglesWarp<Type, SharedDepth, BoxQuorum, 0, Format, Hints, Stats, Q>( boxNodes, leaves, rays, hits, index, index < numRays, stackBase, nullptr, 0, stats, qNodes, qInvalid );
 	}
 }
 
@@ -610,38 +825,50 @@ static void launchGeometry( hiprtGeometry geom, const hiprtRay* rays, uint32_t n
 
 // The configuration the round-1 sweeps settled on: blocks of 128 threads, 32 stack entries per lane in
 // shared memory, box-phase quorum 16, persistent warps, lane refill (threshold 8) for incoherent batches.
-// HIPRT_B200_TRACE_VARIANT: 1 = generic traversal objects (what a user kernel compiles), 2 = fast kernel without cache hints.
-template <hiprtTraversalType Type, uint32_t Format, bool Hints, bool Stats = false>
+// HIPRT_B200_TRACE_VARIANT: 1 = generic traversal objects (what a user kernel compiles), 2 = fast kernel without cache hints,
+// 3 = fast kernel on the public 128-byte box nodes even when the geometry has a Q region (the round-1 kernel).
+template <hiprtTraversalType Type, uint32_t Format, bool Hints, bool Stats = false, bool Q = false>
 static void launchTrianglesT(
-	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream, unsigned long long* stats = nullptr )
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream, unsigned long long* stats = nullptr,
+	const void* qRegion = nullptr )
 {
 	constexpr uint32_t Block = 128;
-	auto			   kernel = traceTrianglesKernel<Type, Block, 32, 16, true, 8, Format, Hints, Stats>;
+	auto			   kernel = traceTrianglesKernel<Type, Block, 32, 16, true, 8, Format, Hints, Stats, Q>;
 	static int		   blocksPerSm = 0; // same value for every caller: a benign race
 	if ( blocksPerSm == 0 ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSm, kernel, int( Block ), 0 );
 	cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), stream );
 	const uint32_t blocks = std::min( DivideRoundUp( numRays, Block ), smCount * uint32_t( std::max( blocksPerSm, 1 ) ) );
-	kernel<<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits, workCounter, stats );
+	kernel<<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits, workCounter, stats, qRegion );
 }
 
-template <uint32_t Format, bool Hints>
-static void launchTriangles( hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, bool any, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream )
+template <uint32_t Format, bool Hints, bool Q = false>
+static void launchTriangles(
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, bool any, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream, const void* qRegion = nullptr )
 {
 	if ( any )
-		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, Format, Hints>( geom, rays, numRays, hits, workCounter, smCount, stream );
+		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, Format, Hints, false, Q>( geom, rays, numRays, hits, workCounter, smCount, stream, nullptr, qRegion );
 	else
-		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, Format, Hints>( geom, rays, numRays, hits, workCounter, smCount, stream );
+		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, Format, Hints, false, Q>( geom, rays, numRays, hits, workCounter, smCount, stream, nullptr, qRegion );
 }
 
 // Instrumented launch (SURVEY.md 8d "counted by an instrumented build"): the same kernel with per-lane visit counters, summed
-// into stats[0] (box-node visits) and stats[1] (leaf visits). Used by bench.py outside the timed region for the cache-level
-// traffic of a ray batch (128 B per box visit + 64 B per leaf visit).
+// into stats[0] (box-node visits) and stats[1] (leaf visits; on the quantised walk this counts the leaves REACHED, of which the
+// exact box test then admits the same ones as the exact walk). Used by bench.py outside the timed region for the cache-level
+// traffic of a ray batch (64 or 128 B per box visit + 64 B per leaf visit).
 void traceGeometryStats(
 	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream,
-	unsigned long long* stats )
+	unsigned long long* stats, const void* qRegion )
 {
 	if ( numRays == 0 ) return;
-	if ( type == hiprtTraversalTerminateAtAnyHit )
+	const bool any = type == hiprtTraversalTerminateAtAnyHit;
+	if ( qRegion && traceVariant() != 3 )
+	{
+		if ( any )
+			launchTrianglesT<hiprtTraversalTerminateAtAnyHit, hiprtB200HitFormatFull, true, true, true>( geom, rays, numRays, hits, workCounter, smCount, stream, stats, qRegion );
+		else
+			launchTrianglesT<hiprtTraversalTerminateAtClosestHit, hiprtB200HitFormatFull, true, true, true>( geom, rays, numRays, hits, workCounter, smCount, stream, stats, qRegion );
+	}
+	else if ( any )
 		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, hiprtB200HitFormatFull, true, true>( geom, rays, numRays, hits, workCounter, smCount, stream, stats );
 	else
 		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, hiprtB200HitFormatFull, true, true>( geom, rays, numRays, hits, workCounter, smCount, stream, stats );
@@ -649,9 +876,10 @@ void traceGeometryStats(
 
 // Generic kernel output in another record format: traced into full hits is not possible without a staging buffer, so the
 // generic (custom-primitive) path supports the full format only; api.cpp rejects the others for such geometries.
+// qRegion: the geometry's Q region when it has one (api.cpp's handle map), else nullptr.
 void traceGeometry(
 	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, void* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount,
-	cudaStream_t stream, uint32_t format )
+	cudaStream_t stream, uint32_t format, const void* qRegion )
 {
 	if ( numRays == 0 ) return;
 	const bool any = type == hiprtTraversalTerminateAtAnyHit;
@@ -659,6 +887,15 @@ void traceGeometry(
 	if ( triangles && ( variant != 1 || format != hiprtB200HitFormatFull ) )
 	{
 		const bool hints = variant != 2;
+		if ( qRegion && hints && variant != 3 )
+		{
+			switch ( format )
+			{
+			case hiprtB200HitFormatCompact: launchTriangles<hiprtB200HitFormatCompact, true, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, qRegion ); return;
+			case hiprtB200HitFormatPrimID: launchTriangles<hiprtB200HitFormatPrimID, true, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, qRegion ); return;
+			default: launchTriangles<hiprtB200HitFormatFull, true, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, qRegion ); return;
+			}
+		}
 		switch ( format )
 		{
 		case hiprtB200HitFormatCompact:

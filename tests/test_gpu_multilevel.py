@@ -144,7 +144,9 @@ def test_custom_spheres_in_a_scene_against_the_oracle(ctx):
     for name, tt in (("device", got["t"][sel]), ("oracle", ref["t"][sel])):
         err = np.abs(tt - t64) / np.abs(t64)
         assert (err <= bound).all(), (name, float((err / bound).max()))
-    assert np.median(bound) < 1e-4  # the bar is tight for the typical hit, loose only at grazing incidence
+    # (camera 9 units away, radii ~0.1: b^2 and 4ac agree to ~3 digits, so the formula's own forward error is ~2e-3 for the
+    # typical hit -- the bar is set by the test kernel's float32 sphere formula, not by the traversal)
+    assert np.median(bound) < 1e-2
     api.lib().hiprtDestroyFuncTable(ctx.h, table)
     scene.destroy()
     g_mesh.destroy()
