@@ -506,10 +506,12 @@ def main():
                 peaks = load_json("r02_cache_peaks.json") or {}
                 cl = {"box_visits_per_primary_ray": round(bp / n_primary, 3), "leaf_visits_per_primary_ray": round(lp / n_primary, 3),
                       "box_visits_per_secondary_ray": round(bs / max(n_secondary, 1), 3), "leaf_visits_per_secondary_ray": round(ls / max(n_secondary, 1), 3),
-                      "bytes_model": "128 B x box visits + 64 B x leaf visits (SURVEY.md 8d), counted by hiprtB200TraceGeometryStats"}
-                for tag, b, l, ms in (("primary", bp, lp, prim_ms_avg), ("secondary", bs, ls, sec_ms_avg)):
-                    gbs = (128 * b + 64 * l) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-                    cl[tag] = {"achieved_gbs": round(gbs, 1)}
+                      "bytes_model": "box_node_bytes x box visits + 64 B x leaf visits (SURVEY.md 8d), counted by hiprtB200TraceGeometryStats"}
+                # any-hit launches walk the 64-byte quantised records (csrc/qnode.h), closest-hit launches the public 128-byte nodes
+                q_any = os.environ.get("HIPRT_B200_TRACE_VARIANT") not in ("1", "2", "3")
+                for tag, b, l, ms, node_bytes in (("primary", bp, lp, prim_ms_avg, 128), ("secondary", bs, ls, sec_ms_avg, 64 if q_any else 128)):
+                    gbs = (node_bytes * b + 64 * l) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+                    cl[tag] = {"achieved_gbs": round(gbs, 1), "box_node_bytes": node_bytes}
                     for level in ("l1_resident_gather_gbs", "l2_resident_gather_gbs"):
                         if peaks.get(level):
                             cl[tag]["frac_of_" + level] = round(gbs / peaks[level], 4)

@@ -7,7 +7,7 @@
 // regenerated after every build / update / compaction / load / relocation (api.cpp keeps the handle -> region map).
 //
 // Results stay bit-identical to the exact traversal:
-//   * the quantised box of a child CONTAINS its exact box with (all but) one grid cell of margin per side, the plane distances
+//   * the quantised box of a child CONTAINS its exact box with at least half a grid cell of margin per side, the plane distances
 //     are evaluated with directed rounding and widened by a relative 2^-20, so a child whose exact slab test passes always
 //     passes the quantised one: the quantised walk visits a superset of the exact walk's nodes;
 //   * a leaf that is reached is first put through the EXACT slab test of its own box (recomputed from the leaf's vertices,

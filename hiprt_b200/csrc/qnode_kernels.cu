@@ -70,7 +70,7 @@ __global__ void __launch_bounds__( 128 ) compressBoxNodesKernel( const GeomHeade
 #pragma unroll
 		for ( int a = 0; a < 3; ++a )
 		{
-			// 250 cells span the node, two more on either side are margin; the cell never drops below 2^-20 of the coordinate
+			// at most 250 cells span the node, two more below it leave room for the margin; the cell never drops below 2^-20 of the coordinate
 			// magnitude (8 ulp), where quantisation could not separate planes anyway
 			const double ext  = hi[a] - lo[a];
 			double		 cell, invCell;
@@ -86,12 +86,12 @@ __global__ void __launch_bounds__( 128 ) compressBoxNodesKernel( const GeomHeade
 				{
 					const double l = double( w[4 + 6 * s + a] ), h = double( w[4 + 6 * s + 3 + a] );
 					// plane ql lies at least one whole cell below l, plane qh at least one whole cell above h
-					ql = uint32_t( fmin( fmax( floor( ( l - double( org ) ) * invCell ) - 1.0, 0.0 ), 255.0 ) );
-					qh = uint32_t( fmin( fmax( ceil( ( h - double( org ) ) * invCell ) + 1.0, 0.0 ), 255.0 ) );
-					// The margin the traversal's error analysis needs is a fraction of a cell (qnode.h); floor - 1 / ceil + 1 leave a
-					// whole one up to the rounding of the double subtraction above, so half a cell is what is asserted. (Cannot trigger
-					// for finite nested boxes: origin sits >= 2 cells below the node and 250 + 4 < 255 cells reach past it.)
-					if ( double( org ) + ql * cell > l - 0.5 * cell || double( org ) + qh * cell < h + 0.5 * cell ) atomicOr( &qHeader->invalid, 1u );
+					ql = uint32_t( fmin( fmax( floor( ( l - double( org ) ) * invCell - 0.5 ), 0.0 ), 255.0 ) );
+					qh = uint32_t( fmin( fmax( ceil( ( h - double( org ) ) * invCell + 0.5 ), 0.0 ), 255.0 ) );
+					// The margin the traversal's error analysis needs is a small fraction of a cell (its own rounding noise is below
+					// 2^-8 of one, qnode.h): the planes are placed between half a cell and one and a half cells outside the box, a
+					// quarter is asserted. (Cannot trigger for finite nested boxes: origin sits 2 cells below the node, 254 cells reach past it.)
+					if ( double( org ) + ql * cell > l - 0.25 * cell || double( org ) + qh * cell < h + 0.25 * cell ) atomicOr( &qHeader->invalid, 1u );
 				}
 				q[a] |= ql << ( 8 * s );
 				q[3 + a] |= qh << ( 8 * s );

@@ -319,7 +319,7 @@ __device__ __forceinline__ uint32_t visitBox4( const Box4Node* __restrict__ boxN
 // plane index q on axis a is ((origin + q * cell) - o) * invD = val * A + B with val = 1 + q * 2^-15 (a float assembled from the
 // byte by ONE byte-permute), A = cell * 2^15 * invD (exact: cell is a power of two) and B = (origin - o) * invD - A, one FFMA
 // per plane, rounded down for entry and up for exit planes. Entry / exit distances are then widened by 2^-20 relative: together
-// with the grid cell of margin the builder leaves around every child box this makes the test conservative with respect to the
+// with the (at least) half grid cell of margin the builder leaves around every child box this makes the test conservative with respect to the
 // exact float32 slab test (see qnode.h for the argument). Same contract as visitBox4.
 template <bool Hints, bool Sort>
 __device__ __forceinline__ uint32_t visitBox4Q( const QBox4Node* __restrict__ qNodes, uint32_t node, const float3 o, const float3 invD, float maxT, uint32_t c[4] )
@@ -841,6 +841,13 @@ static void launchTrianglesT(
 	kernel<<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits, workCounter, stats, qRegion );
 }
 
+// Which queries walk the Q records (qnode.h) when the geometry has them. ncu on the C3 AO rays (profiles/r02_ncu_trace_c3_ao_q.csv):
+// the records halve the L1 data-pipe load (81 % -> 46 %) but their visit costs more ALU-pipe instructions (byte -> float, entry /
+// exit selection), and with the child ordering network of closest-hit queries on top the ALU pipe becomes the limiter (75 %):
+// closest-hit came out 13 % SLOWER on incoherent rays and 2 % slower on primary rays, any-hit (no ordering) 12 % faster. So
+// any-hit queries take the Q walk, closest-hit queries the exact one. HIPRT_B200_TRACE_VARIANT=4 forces the Q walk for both.
+static bool useQ( bool any, const void* qRegion ) { return qRegion != nullptr && ( any || traceVariant() == 4 ); }
+
 template <uint32_t Format, bool Hints, bool Q = false>
 static void launchTriangles(
 	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, bool any, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream, const void* qRegion = nullptr )
@@ -861,7 +868,7 @@ void traceGeometryStats(
 {
 	if ( numRays == 0 ) return;
 	const bool any = type == hiprtTraversalTerminateAtAnyHit;
-	if ( qRegion && traceVariant() != 3 )
+	if ( useQ( any, qRegion ) && traceVariant() != 3 )
 	{
 		if ( any )
 			launchTrianglesT<hiprtTraversalTerminateAtAnyHit, hiprtB200HitFormatFull, true, true, true>( geom, rays, numRays, hits, workCounter, smCount, stream, stats, qRegion );
@@ -887,7 +894,7 @@ void traceGeometry(
 	if ( triangles && ( variant != 1 || format != hiprtB200HitFormatFull ) )
 	{
 		const bool hints = variant != 2;
-		if ( qRegion && hints && variant != 3 )
+		if ( useQ( any, qRegion ) && hints && variant != 3 )
 		{
 			switch ( format )
 			{
