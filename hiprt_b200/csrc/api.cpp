@@ -1256,7 +1256,7 @@ hiprtError hiprtB200ResolveAoFrame(
 hiprtError hiprtB200WaitFlags(
 	hiprtContext context, const uint32_t* flags, uint32_t count, uint32_t strideWords, uint32_t value, uint32_t* timeoutOut, hiprtApiStream stream )
 {
-	if ( !context || !flags || count == 0 || count > 1024 || strideWords == 0 ) return hiprtErrorInvalidParameter;
+	if ( !context || !flags || count == 0 || count > 1024 || strideWords == 0 || ( value == 0 && !timeoutOut ) ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
 		waitFlags( flags, count, strideWords, value, timeoutOut, static_cast<cudaStream_t>( stream ) );
 		checkCuda( cudaGetLastError(), "wait launch" );

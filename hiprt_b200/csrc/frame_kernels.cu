@@ -57,6 +57,9 @@ __global__ void __launch_bounds__( 256 ) resolveAoFrameKernel(
 		if ( atomicAdd( blockCounter, 1u ) + 1u == gridDim.x )
 		{
 			*blockCounter = 0; // ready for the next frame
+			// doneValue == 0: the frame number lives on the device (blockCounter[1]) and counts the launches -- a launch recorded
+			// in a CUDA graph carries the same arguments every replay
+			if ( doneValue == 0u ) doneValue = ++blockCounter[1];
 			__threadfence_system();
 			asm volatile( "st.release.sys.global.u32 [%0], %1;" ::"l"( doneFlag ), "r"( doneValue ) : "memory" );
 		}
@@ -78,6 +81,11 @@ __global__ void waitFlagsKernel( const uint32_t* flags, uint32_t count, uint32_t
 {
 	const uint32_t i = threadIdx.x;
 	bool		   ok = true;
+	// value == 0: the expected frame number lives on the device (timeoutOut[1]) and counts the launches (CUDA graph replays)
+	const bool counting = value == 0u;
+	if ( counting ) value = timeoutOut[1] + 1u;
+	__syncthreads();
+	if ( counting && i == 0 ) timeoutOut[1] = value;
 	if ( i < count )
 	{
 		ok = false;

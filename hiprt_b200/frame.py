@@ -88,10 +88,17 @@ class AoFrame:
     FLAG_STRIDE = 16  # uint32 words between the completion flags of two ranks (one 64-byte line each)
 
     def __init__(self, ctx, geom, width, height, eye, look, spp=16, rank=0, world=1, tile=32, dist=None, exchange="p2p",
-                 primary_format=api.FORMAT_FULL, ao_format=api.FORMAT_PRIM_ID, light=None):
+                 primary_format=api.FORMAT_FULL, ao_format=api.FORMAT_PRIM_ID, light=None, overlap=True):
         """light=None: `spp` AO rays per hit pixel; light=(x, y, z): ONE shadow ray per hit pixel toward that point light
-        (the resolve then yields visibility 0 / 1)."""
+        (the resolve then yields visibility 0 / 1).
+        overlap: the two trace launches of a frame are independent (the secondary rays of the frame are resident, as the primary
+        ones are), so they are queued on two streams: the closest-hit launch ends in a long tail of a few warps with grazing
+        rays (tools/probe_tail.py: one warp of horizon rays runs 0.10 ms on its own) under which the any-hit launch fills the
+        machine. The resolve waits for both."""
         t = ctx.torch
+        self.overlap = overlap
+        self.side = t.cuda.Stream(device=ctx.device) if overlap else None
+        self.fork, self.join = (t.cuda.Event(), t.cuda.Event()) if overlap else (None, None)
         if light is not None:
             spp = 1
         self.light = light
@@ -114,8 +121,9 @@ class AoFrame:
         self.d_primary_rec = t.empty((self.n_primary, api.FORMAT_WORDS[primary_format]), dtype=t.int32, device=ctx.device)
         self.d_ao_rec = t.empty((max(self.n_ao, 1), api.FORMAT_WORDS[ao_format]), dtype=t.int32, device=ctx.device)
         self.block_counter = t.zeros(16, dtype=t.int32, device=ctx.device)
-        self.timeout = t.zeros(1, dtype=t.int32, device=ctx.device)
+        self.timeout = t.zeros(2, dtype=t.int32, device=ctx.device)
         self.frame_no = 0
+        self.graph = None
         self._setup_exchange()
 
     # ---- framebuffer placement -------------------------------------------------------------------
@@ -167,23 +175,61 @@ class AoFrame:
                 self.piece_pixels = [t.from_numpy(shard_pixels(self.width, self.height, r, self.world, tile=self.tile)).to(ctx.device) for r in range(self.world)]
 
     # ---- one frame ---------------------------------------------------------------------------------
+    def capture(self):
+        """Records one frame (two trace launches on two streams, resolve + exchange, the wait on rank 0) into a CUDA graph;
+        step() then replays it with one launch. The completion flags count on the device (doneValue = 0 mode), so every replay
+        releases / waits for the next frame number. Only the peer-store exchange can be recorded (NCCL calls are not)."""
+        t = self.ctx.torch
+        if self.exchange != "p2p":
+            return False
+        t.cuda.synchronize()
+        graph = t.cuda.CUDAGraph()
+        cap = t.cuda.Stream(device=self.ctx.device)
+        cap.wait_stream(t.cuda.current_stream())
+        with t.cuda.graph(graph, stream=cap):
+            self._enqueue(None, None)
+        t.cuda.synchronize()
+        self.graph = graph
+        return True
+
     def step(self, stream=None, marks=None):
         """Queues one frame on the current stream (asynchronous); on rank 0 the stream ends with the complete framebuffer.
-        marks: optional (event, event) recorded after the primary and after the secondary launch."""
+        marks: optional (event, event) recorded after the primary and after the secondary launch (not with a captured graph)."""
+        if self.graph is not None and marks is None:
+            self.frame_no += 1
+            self.graph.replay()
+            return
+        self._enqueue(stream, marks)
+
+    def _enqueue(self, stream, marks):
         ctx = self.ctx
         self.frame_no += 1
-        ctx.trace_format(self.geom, self.d_primary, self.primary_format, self.d_primary_rec, api.CLOSEST_HIT, stream)
-        if marks:
-            marks[0].record()
-        if self.n_ao:
-            ctx.trace_format(self.geom, self.d_ao, self.ao_format, self.d_ao_rec, api.ANY_HIT, stream)
-        if marks:
-            marks[1].record()
+        frame_value = 0  # counting mode: every launch releases / waits for the next frame number, kept on the device
+        if self.overlap and self.n_ao:
+            main = stream if stream is not None else ctx.torch.cuda.current_stream()
+            self.fork.record(main)
+            self.side.wait_event(self.fork)
+            ctx.trace_format(self.geom, self.d_primary, self.primary_format, self.d_primary_rec, api.CLOSEST_HIT, main)
+            if marks:
+                marks[0].record(main)
+            ctx.trace_format(self.geom, self.d_ao, self.ao_format, self.d_ao_rec, api.ANY_HIT, self.side)
+            self.join.record(self.side)
+            main.wait_event(self.join)
+            if marks:
+                marks[1].record(main)
+        else:
+            ctx.trace_format(self.geom, self.d_primary, self.primary_format, self.d_primary_rec, api.CLOSEST_HIT, stream)
+            if marks:
+                marks[0].record()
+            if self.n_ao:
+                ctx.trace_format(self.geom, self.d_ao, self.ao_format, self.d_ao_rec, api.ANY_HIT, stream)
+            if marks:
+                marks[1].record()
         if self.exchange == "p2p":
             ctx.resolve_ao_frame(self.d_primary_rec, self.primary_format, self.d_ao_rec, self.d_first, self.d_pixels, self.spp, self.fb_ptr,
-                                 self.my_flag_ptr, self.frame_no, self.block_counter, stream)
+                                 self.my_flag_ptr, frame_value, self.block_counter, stream)
             if self.rank == 0:
-                ctx.wait_flags(self.flags_ptr, self.world, self.FLAG_STRIDE, self.frame_no, self.timeout, stream)
+                ctx.wait_flags(self.flags_ptr, self.world, self.FLAG_STRIDE, frame_value, self.timeout, stream)
         else:
             ctx.resolve_ao_frame(self.d_primary_rec, self.primary_format, self.d_ao_rec, self.d_first, self.local_index, self.spp,
                                  self.local_fb.data_ptr(), 0, 0, self.block_counter, stream)
@@ -198,7 +244,7 @@ class AoFrame:
     def image(self):
         """Rank 0: the framebuffer as float32 [height, width] on the host (ao in [0, 1], -1 = primary miss)."""
         self.ctx.torch.cuda.synchronize()
-        assert int(self.timeout.item()) == 0, "a rank did not deliver its tiles (hiprtB200WaitFlags ran into its bound)"
+        assert int(self.timeout[0].item()) == 0, "a rank did not deliver its tiles (hiprtB200WaitFlags ran into its bound)"
         return self.framebuffer.cpu().numpy().reshape(self.height, self.width)
 
     def close(self):

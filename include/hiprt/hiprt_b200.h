@@ -147,6 +147,8 @@ HIPRT_API hiprtError hiprtB200SharedClose( hiprtContext context, void* devicePtr
 // through hiprtB200SharedOpen): the stores then travel over NVLink while the rest of the grid is still resolving. When the
 // last block has issued its stores the kernel releases `doneFlag` (also peer-mappable; may be null) by storing `doneValue` at
 // system scope. `blockCounter` is one zero-initialised device uint32 (the kernel leaves it at zero again).
+// doneValue == 0 selects the counting mode for launches recorded in a CUDA graph (same arguments every replay): `blockCounter`
+// then points to TWO zero-initialised words, the second one is incremented by every launch and its new value is what is released.
 HIPRT_API hiprtError hiprtB200ResolveAoFrame(
 	hiprtContext	   context,
 	const void*		   primaryRecords,
@@ -165,6 +167,8 @@ HIPRT_API hiprtError hiprtB200ResolveAoFrame(
 // Blocks `stream` (a spinning one-block kernel, bounded) until the `count` flags flags[k * strideWords] have all reached `value`
 // (flag >= value: frame numbers only grow): the owner of the framebuffer waits for every GPU's hiprtB200ResolveAoFrame.
 // If the bound is hit (a rank died), *timeoutOut (device uint32, may be null) is set to 1 and the stream continues.
+// value == 0 selects the counting mode (CUDA graph replays): `timeoutOut` then points to TWO zero-initialised words, the second one
+// is incremented by every launch and its new value is the frame number waited for.
 HIPRT_API hiprtError hiprtB200WaitFlags(
 	hiprtContext context, const uint32_t* flags, uint32_t count, uint32_t strideWords, uint32_t value, uint32_t* timeoutOut, hiprtApiStream stream );
 

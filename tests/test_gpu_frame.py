@@ -55,6 +55,12 @@ def test_single_gpu_frame_matches_the_oracle(ctx, exchange):
     ref = _oracle_image()
     assert (ref >= 0).mean() > 0.3 and (ref[ref >= 0] < 1).mean() > 0.02  # terrain in view, some occlusion
     assert np.array_equal(img, ref)
+    # the frame as one CUDA graph launch (peer-store exchange only): replays keep counting frames on the device
+    assert fr.capture() == (exchange == "p2p")
+    fr.framebuffer.fill_(-7.0)
+    for _ in range(3):
+        fr.step()
+    assert np.array_equal(fr.image(), ref)
     fr.close()
     geom.destroy()
 
@@ -115,6 +121,16 @@ def _two_rank_worker(rank, world, port, exchange, out_path):
         dist.barrier()
         fr.step()
         torch.cuda.synchronize()
+    dist.barrier()
+    if fr.exchange == "p2p":  # graph replays on both ranks: the flags keep counting
+        assert fr.capture()
+        if rank == 0:
+            fr.framebuffer.fill_(-7.0)
+        torch.cuda.synchronize()
+        for _ in range(3):
+            dist.barrier()
+            fr.step()
+            torch.cuda.synchronize()
     if rank == 0:
         np.save(out_path, fr.image())
         with open(out_path + ".exchange", "w") as f:
