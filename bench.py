@@ -46,9 +46,11 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "c3_terrain_10M_ao"
 BYTES_PER_RAY = 80  # algorithmic HBM traffic of a traced ray: 32 B hiprtRay in + 48 B hiprtHit out
-# compulsory HBM bytes per primitive (pair) of each build phase (vertices are gathered ONCE, by `boxes`:
-# 24 B of indices + 24 B box out + the pair's 4 distinct vertices = 48 B; H-PLOC replaces emit: 200 B model)
-BUILD_BYTES_PER_PRIM = {"pair": 32, "boxes": 96, "morton+histogram": 32, "sort": 68, "emit+refit": 128, "hploc": 200, "collapse+pack": 123 + 152}
+# compulsory HBM bytes per primitive (pair) of each build phase. `boxes`: 24 B of indices in + the 32-byte
+# {box, indices} record out + every VERTEX once (12 B x vertices / pairs, filled in from the mesh: shared vertices are served by
+# L2 after their first touch -- round 1 counted 4 vertices per pair and read 1.02 of the HBM peak); H-PLOC replaces emit: 200 B model;
+# qnodes: 128 B box node in + 64 B record out per BOX NODE (~ 1/3 per primitive pair)
+BUILD_BYTES_PER_PRIM = {"pair": 32, "boxes": 56, "morton+histogram": 32, "sort": 68, "emit+refit": 128, "hploc": 200, "collapse+pack": 123 + 152, "qnodes": 64}
 
 
 def metric_name(wl, spp):
@@ -503,15 +505,18 @@ def main():
         n_prims = int(geom.header()["primNodeCount"])
         # build passes against the HBM roofline: algorithmic bytes per primitive pair, ONLY the phases that ran
         build_roofline, build_bytes = {}, 0
+        per_prim = dict(BUILD_BYTES_PER_PRIM)
+        per_prim["boxes"] = 56 + 12.0 * len(verts) / n_prims
+        per_prim["qnodes"] = 192.0 * int(geom.header()["boxNodeCount"]) / n_prims
         for name, v in phases.items():
             ms = float(np.mean(v))
-            nbytes = BUILD_BYTES_PER_PRIM.get(name, 0) * n_prims
+            nbytes = per_prim.get(name, 0) * n_prims
             build_bytes += nbytes
-            build_roofline[name] = {"ms": round(ms, 4), "bytes_per_prim": BUILD_BYTES_PER_PRIM.get(name, 0),
+            build_roofline[name] = {"ms": round(ms, 4), "bytes_per_prim": round(per_prim.get(name, 0), 1),
                                     "achieved_gbs": round(nbytes / (ms * 1e-3) / 1e9, 1) if ms > 0 else 0.0,
                                     "frac": round(nbytes / (ms * 1e-3) / 1e9 / peak, 4) if ms > 0 else 0.0}
         sort_emit = [k for k in ("sort", "emit+refit", "hploc") if k in phases]
-        se_bytes = sum(BUILD_BYTES_PER_PRIM[k] for k in sort_emit) * n_prims
+        se_bytes = sum(per_prim[k] for k in sort_emit) * n_prims
         se_ms = sum(float(np.mean(phases[k])) for k in sort_emit)
         ao = image[image >= 0]
         line = {

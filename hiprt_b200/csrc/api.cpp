@@ -782,7 +782,7 @@ hiprtError hiprtCompactScenes( hiprtContext context, uint32_t numScenes, hiprtAp
 			h.boxNodes	= reinterpret_cast<Box4Node*>( copy( headers[i].boxNodes, size_t( h.boxNodeCount ) * sizeof( Box4Node ) ) );
 			h.primNodes = reinterpret_cast<InstanceNode*>( copy( headers[i].primNodes, size_t( h.primNodeCount ) * sizeof( InstanceNode ) ) );
 			h.instances = reinterpret_cast<InstanceRecord*>( copy( headers[i].instances, size_t( h.primCount ) * sizeof( InstanceRecord ) ) );
-			h.frames	= reinterpret_cast<SRTFrame*>( copy( headers[i].frames, size_t( h.frameCount ) * sizeof( SRTFrame ) ) );
+			h.frames	= headers[i].frames ? reinterpret_cast<SRTFrame*>( copy( headers[i].frames, size_t( h.frameCount ) * sizeof( SRTFrame ) ) ) : nullptr;
 			h.size		= sizes[i];
 			checkCuda( cudaMemcpyAsync( dst, &h, sizeof( SceneHeader ), cudaMemcpyHostToDevice, s ), "write header" );
 			*scenesOut[i] = reinterpret_cast<hiprtScene>( dst );

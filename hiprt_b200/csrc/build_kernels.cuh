@@ -107,7 +107,9 @@ __global__ void __launch_bounds__( 256 ) initSceneKernel(
 		header->boxNodes	   = boxNodes;
 		header->primNodes	   = instNodes;
 		header->instances	   = records;
-		header->frames		   = frames;
+		// no frames -> null, as the reference's arena hands out for an empty array (MemoryArena.h:38-40): the transform queries of
+		// the device API (hiprtVectorObjectToWorld ...) take a null frame array for "identity" (Transform.h:421)
+		header->frames		   = ( src.frameCount != 0 && apiFrames != nullptr ) ? frames : nullptr;
 		header->size		   = size;
 		header->referenceCount = 0;
 		header->primCount	   = instanceCount;
@@ -945,7 +947,7 @@ __global__ void __launch_bounds__( 256 ) updateSceneInputsKernel(
 		rec.z = uint32_t( ptr ), rec.w = uint32_t( ptr >> 32 );
 		reinterpret_cast<uint4*>( records )[index] = rec;
 	}
-	if ( index < src.frameCount && apiFrames != nullptr )
+	if ( index < src.frameCount && apiFrames != nullptr && frames != nullptr )
 	{
 		const DFrame f = matrixFrames ? frameFromMatrix( static_cast<const hiprtFrameMatrix*>( apiFrames )[index] )
 									  : frameFromSRT( static_cast<const hiprtFrameSRT*>( apiFrames )[index] );

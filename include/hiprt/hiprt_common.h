@@ -7,6 +7,10 @@
 
 #if defined( __CUDACC__ )
 #define HIPRT_B200_DEVICE_CODE 1
+// what HIPRT user code tests to tell kernel translation units from host ones (reference: hiprt/hiprt_common.h:27-29)
+#if !defined( __KERNELCC__ )
+#define __KERNELCC__
+#endif
 #endif
 
 #if !defined( __CUDACC_RTC__ )
@@ -53,6 +57,28 @@ constexpr uint32_t DefaultAlignment			 = 64u;
 constexpr uint32_t InstanceIDBits			 = 24u;
 constexpr uint32_t WarpSize					 = 32u;
 constexpr uint32_t BranchingFactor			 = 4u;
+
+// type selection usable in NVRTC translation units, where <type_traits> is not available (reference: hiprt/hiprt_common.h:343-378)
+template <bool B, class T, class F>
+struct conditional
+{
+	using type = T;
+};
+template <class T, class F>
+struct conditional<false, T, F>
+{
+	using type = F;
+};
+template <class T, class U>
+struct is_same
+{
+	static constexpr bool value = false;
+};
+template <class T>
+struct is_same<T, T>
+{
+	static constexpr bool value = true;
+};
 
 template <typename T, typename U>
 constexpr HIPRT_HOST_DEVICE T RoundUp( T value, U factor )

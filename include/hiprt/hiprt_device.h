@@ -19,6 +19,7 @@
 #include <hiprt/hiprt_common.h>
 #include <hiprt/hiprt_types.h>
 #include <hiprt/hiprt_vec.h>
+#include <hiprt/hiprt_math.h> // the reference injects its vector arithmetic into every trace-kernel compilation: user kernels call hiprt::dot etc.
 #include <hiprt/hiprt_b200_layout.h>
 #include <hiprt/hiprt_b200_frame.h>
 
@@ -61,12 +62,14 @@ namespace hiprt
 // compensated cross/dot built from explicit fmaf, so results do not depend on -fmad.
 HIPRT_DEVICE HIPRT_INLINE float3 sub3( const float3 a, const float3 b ) { return make_float3( a.x - b.x, a.y - b.y, a.z - b.z ); }
 HIPRT_DEVICE HIPRT_INLINE float3 mul3( const float3 a, const float3 b ) { return make_float3( a.x * b.x, a.y * b.y, a.z * b.z ); }
-HIPRT_DEVICE HIPRT_INLINE float	 sumOfProducts( float a, float b, float c, float d )
+// (the traversal's own copies, with explicit roundings: hiprt::sumOfProducts / differenceOfProducts of hiprt_math.h are the
+// user-facing ones and follow the translation unit's contraction setting)
+HIPRT_DEVICE HIPRT_INLINE float	 sumOfProductsRn( float a, float b, float c, float d )
 {
 	const float cd = __fmul_rn( c, d );
 	return __fadd_rn( fmaf( a, b, cd ), fmaf( c, d, -cd ) );
 }
-HIPRT_DEVICE HIPRT_INLINE float differenceOfProducts( float a, float b, float c, float d )
+HIPRT_DEVICE HIPRT_INLINE float differenceOfProductsRn( float a, float b, float c, float d )
 {
 	const float cd = __fmul_rn( c, d );
 	return __fsub_rn( fmaf( a, b, -cd ), fmaf( c, d, -cd ) );
@@ -74,11 +77,11 @@ HIPRT_DEVICE HIPRT_INLINE float differenceOfProducts( float a, float b, float c,
 HIPRT_DEVICE HIPRT_INLINE float3 cross3( const float3 a, const float3 b )
 {
 	return make_float3(
-		differenceOfProducts( a.y, b.z, a.z, b.y ),
-		differenceOfProducts( a.z, b.x, a.x, b.z ),
-		differenceOfProducts( a.x, b.y, a.y, b.x ) );
+		differenceOfProductsRn( a.y, b.z, a.z, b.y ),
+		differenceOfProductsRn( a.z, b.x, a.x, b.z ),
+		differenceOfProductsRn( a.x, b.y, a.y, b.x ) );
 }
-HIPRT_DEVICE HIPRT_INLINE float	 dot3( const float3 a, const float3 b ) { return fmaf( a.x, b.x, sumOfProducts( a.y, b.y, a.z, b.z ) ); }
+HIPRT_DEVICE HIPRT_INLINE float	 dot3( const float3 a, const float3 b ) { return fmaf( a.x, b.x, sumOfProductsRn( a.y, b.y, a.z, b.z ) ); }
 HIPRT_DEVICE HIPRT_INLINE float3 rcp3( const float3 a )
 {
 	return make_float3( __fdiv_rn( 1.0f, a.x ), __fdiv_rn( 1.0f, a.y ), __fdiv_rn( 1.0f, a.z ) );

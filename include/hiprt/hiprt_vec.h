@@ -17,31 +17,40 @@ using hiprtFloat4 = float4;
 #else
 namespace hiprt
 {
+// (the reference names the host-side template hiprt::Vector<T, N>: hiprt/hiprt_vec.h:32-52; user host code spells it that way)
+template <typename T, uint32_t N>
+struct Vector;
 template <typename T>
-struct alignas( 2 * sizeof( T ) ) Vec2
+struct alignas( 2 * sizeof( T ) ) Vector<T, 2>
 {
 	T x, y;
 };
 template <typename T>
-struct Vec3
+struct Vector<T, 3>
 {
 	T x, y, z;
 };
 template <typename T>
-struct alignas( 4 * sizeof( T ) ) Vec4
+struct alignas( 4 * sizeof( T ) ) Vector<T, 4>
 {
 	T x, y, z, w;
 };
+template <typename T>
+using Vec2 = Vector<T, 2>;
+template <typename T>
+using Vec3 = Vector<T, 3>;
+template <typename T>
+using Vec4 = Vector<T, 4>;
 } // namespace hiprt
-using hiprtInt2	  = hiprt::Vec2<int>;
-using hiprtInt3	  = hiprt::Vec3<int>;
-using hiprtInt4	  = hiprt::Vec4<int>;
-using hiprtUint2  = hiprt::Vec2<unsigned int>;
-using hiprtUint3  = hiprt::Vec3<unsigned int>;
-using hiprtUint4  = hiprt::Vec4<unsigned int>;
-using hiprtFloat2 = hiprt::Vec2<float>;
-using hiprtFloat3 = hiprt::Vec3<float>;
-using hiprtFloat4 = hiprt::Vec4<float>;
+using hiprtInt2	  = hiprt::Vector<int, 2>;
+using hiprtInt3	  = hiprt::Vector<int, 3>;
+using hiprtInt4	  = hiprt::Vector<int, 4>;
+using hiprtUint2  = hiprt::Vector<unsigned int, 2>;
+using hiprtUint3  = hiprt::Vector<unsigned int, 3>;
+using hiprtUint4  = hiprt::Vector<unsigned int, 4>;
+using hiprtFloat2 = hiprt::Vector<float, 2>;
+using hiprtFloat3 = hiprt::Vector<float, 3>;
+using hiprtFloat4 = hiprt::Vector<float, 4>;
 #endif
 
 HIPRT_STATIC_ASSERT( sizeof( hiprtFloat2 ) == 8 && alignof( hiprtFloat2 ) == 8 );

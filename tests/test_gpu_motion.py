@@ -133,6 +133,31 @@ def test_transform_queries(ctx):
     geom.destroy()
 
 
+def test_transform_queries_of_a_scene_without_frames_are_the_identity(ctx):
+    """A scene built without instanceFrames has a NULL frame array in its header, as the reference's arena hands out for an empty
+    array (MemoryArena.h:38-40), and the transform queries treat that as the identity (Transform.h:421) -- found by the reference's
+    own unit tests (NormalsCornellBox, ShadowRay / AoRayCornellBox call hiprtVectorObjectToWorld on such a scene)."""
+    verts, idx = scenes.sphere_mesh(16, 8)
+    geom = ctx.build(to_dev(ctx, verts), to_dev(ctx, idx))
+    scene = ctx.build_scene([geom, geom], None)
+    assert int(scene.header()["frames"]) == 0 and int(scene.header()["frameCount"]) == 0
+    (fn,) = build_kernels(ctx, ["transformQueryKernel"])
+    pts = np.random.default_rng(4).uniform(-2, 2, (128, 3)).astype(np.float32)
+    d_in = to_dev(ctx, pts)
+    for inst in (0, 1):
+        d_out = ctx.torch.zeros((len(pts) * 4, 3), dtype=ctx.torch.float32, device=ctx.device)
+        Launcher().launch(fn, len(pts), 64, [scene.h, C.c_uint32(inst), dev_ptr(d_in), dev_ptr(d_out), C.c_uint32(len(pts)), C.c_float(0.0)])
+        ctx.torch.cuda.synchronize()
+        out = d_out.cpu().numpy().reshape(len(pts), 4, 3)
+        for k in range(4):
+            assert np.array_equal(out[:, k], pts)
+    compact = ctx.compact_scene(scene.h)
+    scene.h = compact
+    assert int(scene.header()["frames"]) == 0
+    scene.destroy()
+    geom.destroy()
+
+
 def test_library_entry_point_traces_at_a_time(ctx):
     """hiprtB200TraceSceneAtTime (uniform time, and one time per ray) against the user kernel built on hiprtSceneTraversalClosest( ..., time )."""
     geom, scene, _ = build_animated_scene(ctx)
