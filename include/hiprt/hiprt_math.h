@@ -16,11 +16,8 @@
 #include <cmath>
 #endif
 
-// ---- construction -----------------------------------------------------------------------------------------------
+// ---- construction: from a scalar, from / with smaller vectors (the all-components forms follow below) ------------------------
 #define HIPRT_B200_MAKE( S, N2, N3, N4, V2, V3, V4 )                                                                  \
-	HIPRT_HOST_DEVICE HIPRT_INLINE V2 N2( const S x, const S y ) { return V2{ x, y }; }                              \
-	HIPRT_HOST_DEVICE HIPRT_INLINE V3 N3( const S x, const S y, const S z ) { return V3{ x, y, z }; }                \
-	HIPRT_HOST_DEVICE HIPRT_INLINE V4 N4( const S x, const S y, const S z, const S w ) { return V4{ x, y, z, w }; }  \
 	HIPRT_HOST_DEVICE HIPRT_INLINE V2 N2( const S c ) { return V2{ c, c }; }                                          \
 	HIPRT_HOST_DEVICE HIPRT_INLINE V3 N3( const S c ) { return V3{ c, c, c }; }                                       \
 	HIPRT_HOST_DEVICE HIPRT_INLINE V4 N4( const S c ) { return V4{ c, c, c, c }; }                                    \
@@ -102,6 +99,28 @@ HIPRT_B200_NEGATE( hiprtFloat2, hiprtFloat3, hiprtFloat4 )
 
 namespace hiprt
 {
+// all-components forms: CUDA's own where they exist (brought into this namespace so that the overloads below do not hide them and
+// unqualified calls under `using namespace hiprt` stay unambiguous), ours for plain host translation units
+#if defined( __CUDACC__ ) || defined( __VECTOR_FUNCTIONS_H__ )
+using ::make_int2;
+using ::make_int3;
+using ::make_int4;
+using ::make_uint2;
+using ::make_uint3;
+using ::make_uint4;
+using ::make_float2;
+using ::make_float3;
+using ::make_float4;
+#else
+#define HIPRT_B200_MAKE_ALL( S, N2, N3, N4, V2, V3, V4 )                                                             \
+	HIPRT_HOST_DEVICE HIPRT_INLINE V2 N2( const S x, const S y ) { return V2{ x, y }; }                              \
+	HIPRT_HOST_DEVICE HIPRT_INLINE V3 N3( const S x, const S y, const S z ) { return V3{ x, y, z }; }                \
+	HIPRT_HOST_DEVICE HIPRT_INLINE V4 N4( const S x, const S y, const S z, const S w ) { return V4{ x, y, z, w }; }
+HIPRT_B200_MAKE_ALL( int, make_int2, make_int3, make_int4, hiprtInt2, hiprtInt3, hiprtInt4 )
+HIPRT_B200_MAKE_ALL( unsigned int, make_uint2, make_uint3, make_uint4, hiprtUint2, hiprtUint3, hiprtUint4 )
+HIPRT_B200_MAKE_ALL( float, make_float2, make_float3, make_float4, hiprtFloat2, hiprtFloat3, hiprtFloat4 )
+#undef HIPRT_B200_MAKE_ALL
+#endif
 HIPRT_B200_MAKE( int, make_int2, make_int3, make_int4, hiprtInt2, hiprtInt3, hiprtInt4 )
 HIPRT_B200_MAKE( unsigned int, make_uint2, make_uint3, make_uint4, hiprtUint2, hiprtUint3, hiprtUint4 )
 HIPRT_B200_MAKE( float, make_float2, make_float3, make_float4, hiprtFloat2, hiprtFloat3, hiprtFloat4 )

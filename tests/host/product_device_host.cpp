@@ -20,6 +20,43 @@ static inline float	   __fmul_rn( float a, float b ) { return a * b; }
 static inline float	   __fadd_rn( float a, float b ) { return a + b; }
 static inline float	   __fsub_rn( float a, float b ) { return a - b; }
 static inline float	   __fdiv_rn( float a, float b ) { return a / b; }
+static inline int __float_as_int( float f )
+{
+	int i;
+	memcpy( &i, &f, 4 );
+	return i;
+}
+static inline float __int_as_float( int i )
+{
+	float f;
+	memcpy( &f, &i, 4 );
+	return f;
+}
+// (single host thread: the float atomics of hiprt_math.h only need to compile)
+static inline int atomicMin( int* p, int v )
+{
+	const int old = *p;
+	*p			  = v < old ? v : old;
+	return old;
+}
+static inline int atomicMax( int* p, int v )
+{
+	const int old = *p;
+	*p			  = v > old ? v : old;
+	return old;
+}
+static inline unsigned int atomicMin( unsigned int* p, unsigned int v )
+{
+	const unsigned int old = *p;
+	*p					   = v < old ? v : old;
+	return old;
+}
+static inline unsigned int atomicMax( unsigned int* p, unsigned int v )
+{
+	const unsigned int old = *p;
+	*p					   = v > old ? v : old;
+	return old;
+}
 static inline uint32_t __float_as_uint( float f )
 {
 	uint32_t u;
