@@ -940,6 +940,7 @@ void traceGeometry(
 // triangle) and completed once at the end. An instance is entered by pushing a marker; popping it restores the world ray.
 // Arithmetic (transform, slab, triangle) is that of the generic hiprtSceneTraversalT, winner = min (t, instanceID, primID).
 constexpr uint32_t InstanceExitMarker = 0xFFFFFFFEu; // instance-typed index no scene can hold (2^24 instance limit)
+constexpr uint32_t DeferredMarker	  = 0xFFFFFFFEu; // primID written for a ray that is finished by traceSceneDeferredKernel
 
 // world -> object ray of an instance leaf: inverse matrix for static instances; animated ones (key-frame range in the node)
 // are posed at the ray's time (hiprtB200TraceSceneAtTime; the plain entry points trace at time 0)
@@ -959,7 +960,8 @@ __device__ __forceinline__ void traceSceneWarp(
 	bool			live,
 	hiprtRayMask	rayMask,
 	uint32_t* const stackBase,
-	float			time )
+	float			time,
+	uint32_t*		deferredCount ) // rays that met an instance of a SCENE are counted here and left to traceSceneDeferredKernel
 {
 	constexpr uint32_t TotalDepth = 64;
 	uint32_t		   localStack[TotalDepth - SharedDepth];
@@ -978,6 +980,7 @@ __device__ __forceinline__ void traceSceneWarp(
 	uint32_t	curInst	 = InvalidValue; // instance leaf (node index) the ray is inside of
 	uint32_t	curId	 = InvalidValue;
 	bool		overflow = false;
+	bool		deferred = false;
 	uint32_t	node	 = live ? RootIndex : InvalidValue;
 
 	auto push = [&]( uint32_t v ) {
@@ -1052,6 +1055,14 @@ __device__ __forceinline__ void traceSceneWarp(
 				const InstanceNode* in	 = instNodes + ( node >> 4 );
 				const uint4			meta = __ldg( reinterpret_cast<const uint4*>( in ) + 3 ); // {geometry.lo, geometry.hi, mask, bits}
 				bool				enter = ( meta.z & rayMask ) != 0u;
+				if ( enter && ( ( meta.w >> 24 ) & 1u ) )
+				{
+					// an instance of a scene (multi-level instancing): this kernel walks one instance level; the ray is handed to
+					// the generic multi-level traversal that runs after it (traceSceneDeferredKernel)
+					deferred = true;
+					enter	 = false;
+					top		 = 0;
+				}
 				if ( enter )
 				{
 					const GeomHeader* g = reinterpret_cast<const GeomHeader*>( ( uint64_t( meta.y ) << 32 ) | meta.x );
@@ -1119,7 +1130,12 @@ __device__ __forceinline__ void traceSceneWarp(
 
 	if ( !live ) return;
 	hiprtHit hit;
-	if ( bestRef != InvalidValue && !overflow )
+	if ( deferred )
+	{
+		hit.primID = DeferredMarker;
+		atomicAdd( deferredCount, 1u );
+	}
+	else if ( bestRef != InvalidValue && !overflow )
 	{
 		const InstanceNode* in	 = instNodes + ( bestInst >> 4 );
 		const uint4			meta = __ldg( reinterpret_cast<const uint4*>( in ) + 3 );
@@ -1134,7 +1150,7 @@ __device__ __forceinline__ void traceSceneWarp(
 }
 
 template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum>
-__global__ void __launch_bounds__( Block ) traceSceneFastKernel(
+__global__ void __launch_bounds__( Block, 768 / Block ) traceSceneFastKernel( // 6 blocks of 128 per SM: caps the kernel at 80 registers (84 cost a block)
 	hiprtScene scene, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, hiprtRayMask mask, uint32_t* workCounter,
 	const float* __restrict__ times, float time )
 {
@@ -1149,7 +1165,29 @@ __global__ void __launch_bounds__( Block ) traceSceneFastKernel(
 		if ( base >= numRays ) return;
 		const float rayTime = ( times && base + lane < numRays ) ? __ldg( times + base + lane ) : time;
 		traceSceneWarp<Type, SharedDepth, BoxQuorum>(
-			reinterpret_cast<const SceneHeader*>( scene ), rays, hits, base + lane, base + lane < numRays, mask, stackBase, rayTime );
+			reinterpret_cast<const SceneHeader*>( scene ), rays, hits, base + lane, base + lane < numRays, mask, stackBase, rayTime, workCounter + 1 );
+	}
+}
+
+// Second launch of every library scene trace: finishes the rays the fast kernel deferred (multi-level instancing: instances of
+// scenes, hiprt_device_impl.h:1105-1193 in the reference) with the generic traversal object and an instance stack, as a user kernel
+// would. When the fast kernel deferred nothing -- every single-level scene -- each block reads one word and leaves.
+template <hiprtTraversalType Type>
+__global__ void __launch_bounds__( TraceBlock ) traceSceneDeferredKernel(
+	hiprtScene scene, const hiprtRay* __restrict__ rays, uint32_t numRays, hiprtHit* __restrict__ hits, hiprtRayMask mask, const uint32_t* deferredCount,
+	const float* __restrict__ times, float time )
+{
+	if ( *reinterpret_cast<const volatile uint32_t*>( deferredCount ) == 0u ) return;
+	__shared__ uint32_t sStack[TraceBlock * SharedStackDepth];
+	for ( uint32_t index = blockIdx.x * TraceBlock + threadIdx.x; index < numRays; index += gridDim.x * TraceBlock )
+	{
+		if ( hits[index].primID != DeferredMarker ) continue;
+		HybridStack				  stack( sStack );
+		hiprtPrivateInstanceStack instanceStack;
+		const hiprtRay			  ray = loadRay( rays, index );
+		hiprtSceneTraversalT<HybridStack, hiprtPrivateInstanceStack, Type> tr(
+			scene, ray, stack, instanceStack, mask, hiprtTraversalHintDefault, nullptr, nullptr, 0, times ? __ldg( times + index ) : time );
+		storeHit( hits, index, tr.getNextHit() );
 	}
 }
 
@@ -1162,9 +1200,11 @@ static void launchSceneFast(
 	auto			   kernel = traceSceneFastKernel<Type, Block, 32, 16>;
 	static int		   blocksPerSm = 0; // same value for every caller: a benign race
 	if ( blocksPerSm == 0 ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSm, kernel, int( Block ), 0 );
-	cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), stream );
+	cudaMemsetAsync( workCounter, 0, 2 * sizeof( uint32_t ), stream ); // [0] ray batches handed out, [1] rays deferred to the multi-level pass
 	const uint32_t blocks = std::min( DivideRoundUp( numRays, Block ), smCount * uint32_t( std::max( blocksPerSm, 1 ) ) );
 	kernel<<<blocks, Block, 0, stream>>>( scene, rays, numRays, hits, mask, workCounter, times, time );
+	traceSceneDeferredKernel<Type><<<std::min( DivideRoundUp( numRays, TraceBlock ), smCount * 4u ), TraceBlock, 0, stream>>>(
+		scene, rays, numRays, hits, mask, workCounter + 1, times, time );
 }
 
 void traceScene(

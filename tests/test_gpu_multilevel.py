@@ -61,6 +61,25 @@ def test_three_level_scene_against_the_oracle(ctx):
     assert (dt[hit] <= 1e-4).all(), dt[hit].max()
     assert (~same & hit).sum() <= 0.002 * hit.sum(), (~same & hit).sum()
     assert (got["instanceIDs"][hit, 3] == api.INVALID).all() and (got["instanceIDs"][hit, :3] != api.INVALID).all()
+    # the library's own rays-in / hits-out entry point on the same scene: its fast kernel walks one instance level and hands every
+    # ray that meets an instance of a scene to the multi-level pass that follows it (traceSceneDeferredKernel) -- same hits as the
+    # user kernel above, bit for bit, for closest hit; same occlusion for any hit
+    lib = ctx.hits_to_host(ctx.trace(top, ctx.rays_to_device(rays)))
+    assert np.array_equal(lib["primID"], got["primID"]) and np.array_equal(lib["instanceIDs"][hit], got["instanceIDs"][hit])
+    for f in ("t", "uv", "normal"):
+        assert lib[f][hit].tobytes() == got[f][hit].tobytes(), f
+    occluded = ctx.hits_to_host(ctx.trace(top, ctx.rays_to_device(rays), kind=api.ANY_HIT))["primID"] != api.INVALID
+    assert np.array_equal(occluded, hit)
+    # a mixed top level: one instance of a scene next to instances of geometries
+    mixed_frames = scenes.random_matrix_frames(3, seed=9, extent=5.0, scale_range=(0.9, 1.1))
+    mixed = ctx.build_scene([leaf, geoms[0], geoms[1]], mixed_frames, instance_types=[api.INSTANCE_SCENE, api.INSTANCE_GEOMETRY, api.INSTANCE_GEOMETRY])
+    rays2 = scenes.pinhole_rays(160, 160, (0.0, 2.0, 20.0), (0, 0, 0))
+    user = launch_scene_kernel(ctx, fn, mixed, rays2)
+    lib2 = ctx.hits_to_host(ctx.trace(mixed, ctx.rays_to_device(rays2)))
+    h2 = user["primID"] != api.INVALID
+    assert h2.mean() > 0.02 and np.array_equal(lib2["primID"], user["primID"]) and np.array_equal(lib2["instanceIDs"][h2], user["instanceIDs"][h2])
+    assert lib2["t"][h2].tobytes() == user["t"][h2].tobytes()
+    mixed.destroy()
     for s in (top, mid, leaf):
         s.destroy()
     for g in geoms:
