@@ -62,6 +62,21 @@ __device__ __forceinline__ hiprtRay loadRay( const hiprtRay* rays, uint32_t inde
 	ray.direction = make_float3( r1.x, r1.y, r1.z ), ray.maxT = r1.w;
 	return ray;
 }
+// A default-constructed hiprtHit initialises instanceIDs[0] only (the union's first member, as in the reference's hiprt_types.h:237-258);
+// the library kernels write all four words of the record, so the deeper levels are set to "none" explicitly.
+__device__ __forceinline__ hiprtHit emptyHit()
+{
+	hiprtHit hit;
+	hit.instanceIDs[1] = hit.instanceIDs[2] = hit.instanceIDs[3] = InvalidValue;
+	return hit;
+}
+// (hits of the single-level traversal objects: only instanceIDs[0] is theirs)
+__device__ __forceinline__ void storeHit( hiprtHit* hits, uint32_t index, const hiprtHit& hit );
+__device__ __forceinline__ void storeSingleLevelHit( hiprtHit* hits, uint32_t index, hiprtHit hit )
+{
+	hit.instanceIDs[1] = hit.instanceIDs[2] = hit.instanceIDs[3] = InvalidValue;
+	storeHit( hits, index, hit );
+}
 __device__ __forceinline__ void storeHit( hiprtHit* hits, uint32_t index, const hiprtHit& hit )
 {
 	float4* hp = reinterpret_cast<float4*>( hits + index );
@@ -118,7 +133,7 @@ __global__ void __launch_bounds__( Block ) traceGeometryKernel(
 					hiprtGeomTraversalT<Stack, hiprtCustomNode, Type> tr( geom, ray, stack );
 					hit = tr.getNextHit();
 				}
-				storeHit( hits, index, hit );
+				storeSingleLevelHit( hits, index, hit );
 			}
 			__syncwarp();
 		}
@@ -140,7 +155,7 @@ __global__ void __launch_bounds__( Block ) traceGeometryKernel(
 			hiprtGeomTraversalT<Stack, hiprtCustomNode, Type> tr( geom, ray, stack );
 			hit = tr.getNextHit();
 		}
-		storeHit( hits, index, hit );
+		storeSingleLevelHit( hits, index, hit );
 	}
 }
 
@@ -517,7 +532,7 @@ __device__ __forceinline__ void traceTrianglesWarp(
 
 	// result of the lane's finished ray: uv mapping and normal by re-running the reference-order test on the winning triangle
 	auto finish = [&]() {
-		hiprtHit hit;
+		hiprtHit hit = emptyHit();
 		if ( bestRef != InvalidValue && !overflow )
 		{
 			if constexpr ( Format == hiprtB200HitFormatPrimID )
@@ -791,11 +806,7 @@ __global__ void __launch_bounds__( TraceBlock ) traceSceneKernel(
 	if ( times ) time = __ldg( times + index );
 	hiprtSceneTraversalT<HybridStack, hiprtEmptyInstanceStack, Type> tr(
 		scene, ray, stack, noInstanceStack, mask, hiprtTraversalHintDefault, nullptr, nullptr, 0, time );
-	const hiprtHit hit = tr.getNextHit();
-	float4*		   hp  = reinterpret_cast<float4*>( hits + index );
-	hp[0] = make_float4( __uint_as_float( hit.instanceIDs[0] ), __uint_as_float( hit.instanceIDs[1] ), __uint_as_float( hit.instanceIDs[2] ), __uint_as_float( hit.instanceIDs[3] ) );
-	hp[1] = make_float4( __uint_as_float( hit.primID ), 0.0f, hit.uv.x, hit.uv.y );
-	hp[2] = make_float4( hit.normal.x, hit.normal.y, hit.normal.z, hit.t );
+	storeSingleLevelHit( hits, index, tr.getNextHit() );
 }
 
 static int traceVariant()
@@ -1129,7 +1140,7 @@ __device__ __forceinline__ void traceSceneWarp(
 	}
 
 	if ( !live ) return;
-	hiprtHit hit;
+	hiprtHit hit = emptyHit();
 	if ( deferred )
 	{
 		hit.primID = DeferredMarker;

@@ -75,6 +75,7 @@ def test_record_formats_agree_with_the_full_hit(ctx):
     rays = frame.frame_rays(W, H, EYE, LOOK, px)
     d_rays = ctx.rays_to_device(rays)
     full = ctx.hits_to_host(ctx.trace(geom, d_rays))
+    assert (full["instanceIDs"] == api.INVALID).all()  # a geometry trace reports no instance at any level (all four words are written)
     for kind in (api.CLOSEST_HIT, api.ANY_HIT):
         ref = ctx.hits_to_host(ctx.trace(geom, d_rays, kind=kind))
         compact = t.empty((len(rays), 4), dtype=t.int32, device=ctx.device)
