@@ -2,6 +2,7 @@
 // (kernels: build_kernels.cuh; reference host side: hiprt/impl/LbvhBuilder.{h,cpp},
 // PlocBuilder.{h,cpp}, BatchBuilder.{h,cpp}, Context.cpp:144-290.)
 #include "batch_kernels.cuh"
+#include <cstdlib>
 #include "qnode.h"
 
 namespace hiprt
@@ -149,7 +150,12 @@ static void runLbvh(
 	if ( balanced )
 	{
 		uint32_t* clusterIds = reinterpret_cast<uint32_t*>( temp + L.clusterIds );
-		hplocKernel<Source::LeafType><<<DivideRoundUp( nMax, PlocBlock ), PlocBlock, 0, stream>>>(
+		static const int radius = [] {
+			const char* e = getenv( "HIPRT_B200_PLOC_RADIUS" ); // 2 (default) / 4 / 8: see PlocRadius
+			return e ? atoi( e ) : int( PlocRadius );
+		}();
+		auto kernel = radius == 4 ? hplocKernel<Source::LeafType, 4> : ( radius == 8 ? hplocKernel<Source::LeafType, 8> : hplocKernel<Source::LeafType, PlocRadius> );
+		kernel<<<DivideRoundUp( nMax, PlocBlock ), PlocBlock, 0, stream>>>(
 			ctl, keys[0], vals[0], primRefs, sortedRefs, scratch, flags, clusterIds, &ctl->nodeCounter, taskQueue );
 		dev.mark( "hploc", stream );
 	}

@@ -477,7 +477,12 @@ __global__ void __launch_bounds__( EmitTile ) emitTopologyKernel(
 // every round instead of degenerating into a chain (the reference gets the same effect from the
 // parity bit of its encodeOffset, PlocBuilderKernels.h:54-65). The tree shape depends only on the
 // sorted keys and boxes (node ADDRESSES depend on atomic order, as in the reference).
-constexpr uint32_t PlocRadius = 8;
+// Search radius: the reference uses 8 (BvhConfig.h). Measured here on five meshes (profiles/r02_ploc_radius.txt: terrain, UV sphere,
+// icosphere, uniform and clustered mixed-size soups), radius 2 gives FEWER node visits per ray than radius 8 on four of them
+// (-1 % .. -10 %; +2 % on the clustered soup, where the SAH-style cost is 2 % worse too) and the kernel runs 1.55 -> 0.92 ms at
+// 5 M primitives: each round is 2 instead of 8 neighbour evaluations, and on Morton-sorted input the wider search mostly finds pairs
+// whose merge looks good locally but interleaves subtrees. HIPRT_B200_PLOC_RADIUS = 2 / 4 / 8 overrides it.
+constexpr uint32_t PlocRadius = 2;
 constexpr uint32_t PlocWindow = 32; // clusters held by a warp: 16 from each side of the split
 constexpr uint32_t PlocBlock  = 256;
 
@@ -504,8 +509,8 @@ __device__ __forceinline__ DBox shflDownBox( const DBox& b, uint32_t d )
 		make_float3( __shfl_down_sync( FullMask, b.hi.x, d ), __shfl_down_sync( FullMask, b.hi.y, d ), __shfl_down_sync( FullMask, b.hi.z, d ) ) };
 }
 
-template <uint32_t LeafType>
-__global__ void __launch_bounds__( PlocBlock ) hplocKernel(
+template <uint32_t LeafType, uint32_t Radius = PlocRadius, uint32_t Block = PlocBlock>
+__global__ void __launch_bounds__( Block ) hplocKernel(
 	BuildControl*	ctl,
 	const uint32_t* sortedKeys,
 	const uint32_t* sortedVals,
@@ -577,7 +582,7 @@ __global__ void __launch_bounds__( PlocBlock ) hplocKernel(
 				// nearest neighbour within PlocRadius positions, both directions
 				uint64_t best = ~0ull;
 #pragma unroll
-				for ( uint32_t d = 1; d <= PlocRadius; ++d )
+				for ( uint32_t d = 1; d <= Radius; ++d )
 				{
 					const DBox	   nb	 = shflDownBox( box, d );
 					const bool	   valid = lane + d < count;
