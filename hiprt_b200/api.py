@@ -186,6 +186,7 @@ SIGNATURES = {
     "hiprtB200ResolveAoFrame": [_vp, _vp, C.c_int, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _u32, _vp, _vp],
     "hiprtB200WaitFlags": [_vp, _vp, _u32, _u32, _u32, _vp, _vp],
     "hiprtB200GetTempLayout": [_sz, _sz, _P(_sz), _u32],
+    "hiprtB200GetHighQualityTempLayout": [_sz, _sz, C.c_int, _P(_sz), _u32],
     "hiprtB200GetDeviceHeaders": [_P(_P(C.c_char_p)), _P(_P(C.c_char_p))],
     "hiprtB200LinkTraceKernels": [C.c_int, C.c_int, C.c_char_p, C.c_char_p, _sz, _u32, _u32, _P(FuncNameSet), _vp, _P(_sz), C.c_char_p, _sz],
     "hiprtB200GetLastErrorString": [_vp],
@@ -226,6 +227,12 @@ def temp_layout(prim_count, paired_triangles=0):
     out = (C.c_size_t * 14)()
     lib().hiprtB200GetTempLayout(prim_count, paired_triangles, out, 14)
     return dict(zip(TEMP_LAYOUT_FIELDS, [int(v) for v in out]))
+
+
+def high_quality_temp_layout(prim_count, paired_triangles=0, spatial_splits=True):
+    out = (C.c_size_t * 8)()
+    lib().hiprtB200GetHighQualityTempLayout(C.c_size_t(prim_count), C.c_size_t(paired_triangles), int(spatial_splits), out, 8)
+    return dict(zip(["control", "state", "primRefs", "nodes", "leaves", "maxRefs", "taskQueue", "total"], [int(v) for v in out]))
 
 
 def _ptr(t):

@@ -402,8 +402,7 @@ bool usesBatch( size_t primCount, hiprtBuildOptions o )
 
 void checkBuildFlags( Context* c, hiprtBuildOptions o )
 {
-	if ( ( o.buildFlags & 3 ) == hiprtBuildFlagBitPreferHighQualityBuild )
-		c->log( hiprtLogLevelInfo, "PreferHighQualityBuild is served by the balanced (H-PLOC) builder" );
+	if ( ( o.buildFlags & 3 ) == hiprtBuildFlagBitPreferHighQualityBuild ) c->log( hiprtLogLevelInfo, "HighQualityBuild (SBVH)" );
 }
 } // namespace
 
@@ -455,7 +454,7 @@ hiprtError hiprtCreateGeometries(
 		checkBuildFlags( ctx( context ), buildOptions );
 		std::vector<size_t> sizes( numGeometries );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
-			sizes[i] = geometryAllocationSize( buildInputs[i] );
+			sizes[i] = geometryAllocationSize( buildInputs[i], buildOptions );
 		const std::vector<void*> ptrs = ctx( context )->allocatePool( sizes );
 		for ( uint32_t i = 0; i < numGeometries; ++i )
 			*geometriesOut[i] = reinterpret_cast<hiprtGeometry>( ptrs[i] );
@@ -1270,6 +1269,13 @@ hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount,
 	const size_t	 v[14] = { L.control, L.pairs,	  L.pairScan,	L.primRefs,	  L.keys[0], L.vals[0], L.keys[1],
 							   L.vals[1], L.sortScratch, L.sortedRefs, L.scratch, L.flags,	 L.taskQueue, L.total };
 	memcpy( offsetsOut, v, sizeof( v ) );
+	return hiprtSuccess;
+}
+
+hiprtError hiprtB200GetHighQualityTempLayout( size_t primCount, size_t pairedTriangleCount, int spatialSplits, size_t* offsetsOut, uint32_t numOffsets )
+{
+	if ( !offsetsOut || numOffsets < 8 ) return hiprtErrorInvalidParameter;
+	highQualityTempLayout( primCount, pairedTriangleCount, spatialSplits != 0, offsetsOut );
 	return hiprtSuccess;
 }
 

@@ -2,6 +2,7 @@
 // (kernels: build_kernels.cuh; reference host side: hiprt/impl/LbvhBuilder.{h,cpp},
 // PlocBuilder.{h,cpp}, BatchBuilder.{h,cpp}, Context.cpp:144-290.)
 #include "batch_kernels.cuh"
+#include "sbvh_kernels.cuh"
 #include <cstdlib>
 #include "qnode.h"
 
@@ -35,6 +36,49 @@ TempLayout tempLayout( size_t n, size_t pairTriangles )
 }
 
 // ------------------------------------------------------------------------------------------------
+// High-quality build (SBVH): temporary buffer and launch. `maxRefs` = leafCapacity(): the reference budget.
+struct SbvhLayout
+{
+	size_t control, state, pairs, pairScan, primRefs, refs[2], refTask[2], tasks[2], objectBins, spatialBins, nodes, leaves, taskQueue, total;
+};
+static SbvhLayout sbvhLayout( size_t n, size_t pairTriangles, size_t maxRefs, bool spatial )
+{
+	SbvhLayout L{};
+	size_t	   off	= 0;
+	auto	   take = [&]( size_t bytes ) {
+		  const size_t o = off;
+		  off += alignUp( bytes );
+		  return o;
+	};
+	const size_t maxTasks = std::max<size_t>( maxRefs / 2, 1 );
+	L.control	  = take( sizeof( BuildControl ) );
+	L.state		  = take( sizeof( sbvh::State ) );
+	L.pairs		  = take( pairTriangles * sizeof( uint2 ) );
+	L.pairScan	  = take( DivideRoundUp( pairTriangles, size_t( PairTile ) ) * sizeof( uint32_t ) );
+	L.primRefs	  = take( n * 32 );
+	L.refs[0]	  = take( maxRefs * 32 );
+	L.refs[1]	  = take( maxRefs * 32 );
+	L.refTask[0]  = take( maxRefs * 4 );
+	L.refTask[1]  = take( maxRefs * 4 );
+	L.tasks[0]	  = take( maxTasks * sizeof( sbvh::Task ) );
+	L.tasks[1]	  = take( maxTasks * sizeof( sbvh::Task ) );
+	L.objectBins  = take( maxTasks * 3 * sbvh::MinBins * 32 );
+	L.spatialBins = take( spatial ? maxTasks * 3 * sbvh::MinBins * 32 : 0 );
+	L.nodes		  = take( maxRefs * 32 );
+	L.leaves	  = take( maxRefs * 32 );
+	L.taskQueue	  = take( maxBoxNodeCount( maxRefs ) * 8 );
+	L.total		  = off;
+	return L;
+}
+
+void highQualityTempLayout( size_t n, size_t pairTriangles, bool spatial, size_t out[8] )
+{
+	const size_t	 maxRefs = spatial ? n + n / 2 : n;
+	const SbvhLayout L		 = sbvhLayout( n, pairTriangles, maxRefs, spatial );
+	out[0] = L.control, out[1] = L.state, out[2] = L.primRefs, out[3] = L.nodes, out[4] = L.leaves, out[5] = maxRefs, out[6] = L.taskQueue, out[7] = L.total;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Custom BVH import (hiprtBuildFlagBitCustomBvhImport): the caller's binary tree decides the leaf count, which exceeds the
 // primitive count when several leaves reference one primitive (spatial splits). Storage is sized for whichever is larger.
 static bool isImport( hiprtBuildOptions options ) { return ( options.buildFlags & 3u ) == hiprtBuildFlagBitCustomBvhImport; }
@@ -56,12 +100,19 @@ size_t geometryPrimCount( const hiprtGeometryBuildInput& input )
 	throw std::runtime_error( "unsupported primitive type" );
 }
 
-// PreferBalancedBuild -> H-PLOC; PreferHighQualityBuild is served by the same builder (the SBVH
-// builder is out of scope: SURVEY.md section 2 row 14); anything else -> LBVH (Context.cpp:174-198).
-static bool usesBalancedBuilder( hiprtBuildOptions options )
+// PreferBalancedBuild -> H-PLOC; PreferHighQualityBuild -> SBVH (sbvh_kernels.cuh); anything else -> LBVH (Context.cpp:174-198).
+static bool usesBalancedBuilder( hiprtBuildOptions options ) { return ( options.buildFlags & 3u ) == hiprtBuildFlagBitPreferBalancedBuild; }
+static bool usesSbvhBuilder( hiprtBuildOptions options ) { return ( options.buildFlags & 3u ) == hiprtBuildFlagBitPreferHighQualityBuild; }
+
+// Leaves a build of `input` may create: one per primitive, except that a high-quality build with spatial splits may reference a
+// primitive from several leaves -- half as many again at most (SbvhAlpha = 1.5, BvhConfig.h:48; SbvhBuilder.h:158-160) -- and
+// an imported hierarchy brings its own leaf count.
+static size_t leafCapacity( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
 {
-	const uint32_t kind = options.buildFlags & 3u;
-	return kind == hiprtBuildFlagBitPreferBalancedBuild || kind == hiprtBuildFlagBitPreferHighQualityBuild;
+	const size_t n = geometryPrimCount( input );
+	if ( isImport( options ) ) return std::max( n, importLeafCount( input ) );
+	if ( usesSbvhBuilder( options ) && !( options.buildFlags & hiprtBuildFlagBitDisableSpatialSplits ) ) return n + n / 2;
+	return n;
 }
 
 static bool wantsPairing( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
@@ -73,19 +124,19 @@ static bool wantsPairing( const hiprtGeometryBuildInput& input, hiprtBuildOption
 		   !( options.buildFlags & hiprtBuildFlagBitDisableTrianglePairing ) && !isImport( options );
 }
 
-size_t geometryStorageSize( const hiprtGeometryBuildInput& input )
+size_t geometryStorageSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
 {
-	const size_t n		  = std::max( geometryPrimCount( input ), importLeafCount( input ) );
+	const size_t n		  = leafCapacity( input, options );
 	const size_t leafSize = input.type == hiprtPrimitiveTypeTriangleMesh ? sizeof( TrianglePairNode ) : sizeof( CustomNode );
 	return alignUp( sizeof( GeomHeader ) ) + alignUp( maxBoxNodeCount( n ) * sizeof( Box4Node ) ) + alignUp( n * leafSize );
 }
 
 // What hiprtCreateGeometry allocates: the public structure (`size` of the header, what hiprtSaveGeometry writes) followed, for
 // triangle meshes, by the traversal-only Q region of the library's own trace kernels (qnode.h).
-size_t geometryAllocationSize( const hiprtGeometryBuildInput& input )
+size_t geometryAllocationSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
 {
-	const size_t n = std::max( geometryPrimCount( input ), importLeafCount( input ) );
-	return geometryStorageSize( input ) + ( input.type == hiprtPrimitiveTypeTriangleMesh ? qRegionSize( maxBoxNodeCount( n ) ) : 0 );
+	const size_t n = leafCapacity( input, options );
+	return geometryStorageSize( input, options ) + ( input.type == hiprtPrimitiveTypeTriangleMesh ? qRegionSize( maxBoxNodeCount( n ) ) : 0 );
 }
 
 // Where the Q region of a geometry built from `input` lies inside its allocation, or nullptr when such a build has none
@@ -93,14 +144,67 @@ size_t geometryAllocationSize( const hiprtGeometryBuildInput& input )
 void* geometryQRegion( const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* storage )
 {
 	if ( input.type != hiprtPrimitiveTypeTriangleMesh || isImport( options ) || geometryPrimCount( input ) < 2 ) return nullptr;
-	return static_cast<uint8_t*>( storage ) + geometryStorageSize( input );
+	return static_cast<uint8_t*>( storage ) + geometryStorageSize( input, options );
 }
 
 size_t geometryTempSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options )
 {
 	if ( isImport( options ) ) return tempLayout( std::max<size_t>( importLeafCount( input ), 1 ), 0 ).total;
 	const size_t n = geometryPrimCount( input );
+	if ( usesSbvhBuilder( options ) ) return sbvhLayout( n, wantsPairing( input, options ) ? n : 0, leafCapacity( input, options ), leafCapacity( input, options ) > n ).total;
 	return tempLayout( n, wantsPairing( input, options ) ? n : 0 ).total;
+}
+
+// Binary tree by sbvh::buildKernel (one cooperative launch, all levels), then the shared collapse + pack.
+template <typename Source>
+static void runSbvh(
+	const DeviceInfo& dev, Source src, uint32_t nMax, uint32_t maxRefs, bool spatial, uint8_t* temp, const SbvhLayout& L, cudaStream_t stream,
+	uint32_t* boxNodeCounter, uint32_t* primNodeCounter, Box4Node* boxNodes, void* leafNodes )
+{
+	BuildControl*  ctl		 = reinterpret_cast<BuildControl*>( temp + L.control );
+	uint64_t*	   taskQueue = reinterpret_cast<uint64_t*>( temp + L.taskQueue );
+	const uint32_t maxBox	 = uint32_t( maxBoxNodeCount( maxRefs ) );
+	HIPRT_CUDA_CHECK( cudaMemsetAsync( temp + L.state, 0, sizeof( sbvh::State ), stream ) );
+	HIPRT_CUDA_CHECK( cudaMemsetAsync( taskQueue, 0xFF, size_t( maxBox ) * 8, stream ) );
+
+	sbvh::Params P{};
+	P.state		  = reinterpret_cast<sbvh::State*>( temp + L.state );
+	P.ctl		  = ctl;
+	P.primRefs	  = temp + L.primRefs;
+	P.refs[0] = temp + L.refs[0], P.refs[1] = temp + L.refs[1];
+	P.refTask[0] = reinterpret_cast<uint32_t*>( temp + L.refTask[0] ), P.refTask[1] = reinterpret_cast<uint32_t*>( temp + L.refTask[1] );
+	P.tasks[0] = reinterpret_cast<sbvh::Task*>( temp + L.tasks[0] ), P.tasks[1] = reinterpret_cast<sbvh::Task*>( temp + L.tasks[1] );
+	P.objectBins  = reinterpret_cast<float*>( temp + L.objectBins );
+	P.spatialBins = spatial ? reinterpret_cast<float*>( temp + L.spatialBins ) : nullptr;
+	P.nodes		  = temp + L.nodes;
+	P.leaves	  = temp + L.leaves;
+	P.taskQueue	  = taskQueue;
+	P.maxRefs	  = maxRefs;
+
+	// every CTA of the grid must be resident (the levels are separated by grid barriers): sized from the occupancy of this kernel,
+	// launched cooperatively so that the runtime refuses rather than deadlocks if the device cannot hold it
+	static int perSm = 0; // per Source instantiation; same value every time: a benign race
+	if ( perSm == 0 )
+	{
+		int v = 0;
+		HIPRT_CUDA_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &v, sbvh::buildKernel<Source>, int( sbvh::Block ), 0 ) );
+		if ( v < 1 ) throw std::runtime_error( "high-quality build: kernel does not fit an SM" );
+		perSm = std::min( v, 4 );
+	}
+	const uint32_t wanted = DivideRoundUp( std::max( nMax, 1u ), sbvh::Block );
+	const uint32_t grid	  = std::max( 1u, std::min( wanted, dev.smCount * uint32_t( perSm ) ) );
+	void*		   args[] = { &src, &P };
+	HIPRT_CUDA_CHECK( cudaLaunchCooperativeKernel( reinterpret_cast<const void*>( sbvh::buildKernel<Source> ), dim3( grid ), dim3( sbvh::Block ), args, 0, stream ) );
+	dev.mark( "sbvh", stream );
+
+	const uint32_t warpsNeeded	 = DivideRoundUp( maxBox, 8u );
+	const uint32_t blocks		 = std::max( 1u, std::min( DivideRoundUp( warpsNeeded, CollapseBlock / 32 ), dev.smCount * 16 ) );
+	const uint32_t residentWarps = dev.smCount * 40;
+	const uint32_t claimSize	 = std::max( 8u, std::min( 32u, ( maxBox / ( residentWarps * 16 ) ) & ~7u ) );
+	collapsePackKernel<Source><<<blocks, CollapseBlock, 0, stream>>>(
+		src, ctl, boxNodeCounter, primNodeCounter, temp + L.nodes, temp + L.leaves, taskQueue, maxBox, claimSize, boxNodes, leafNodes );
+	dev.mark( "collapse+pack", stream );
+	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
 
 // Sort + emit + collapse for primitives whose 32-byte box records are already in temp.
@@ -249,19 +353,22 @@ void buildGeometry(
 	if ( nMax == 0 ) throw std::runtime_error( "empty geometry" );
 	const bool		 pairing  = wantsPairing( input, options );
 	const bool		 balanced = usesBalancedBuilder( options );
+	const bool		 sbvhTree = usesSbvhBuilder( options ) && !import && nMax > 1;
+	const uint32_t	 maxLeaves = uint32_t( leafCapacity( input, options ) ); // = nMax unless a high-quality build may duplicate references
 	const TempLayout L		  = tempLayout( nMax, pairing ? nMax : 0 );
+	const SbvhLayout S		  = sbvhTree ? sbvhLayout( nMax, pairing ? nMax : 0, maxLeaves, maxLeaves > nMax ) : SbvhLayout{};
 	uint8_t*		 temp	 = static_cast<uint8_t*>( tempBuffer );
 	uint8_t*		 out	 = static_cast<uint8_t*>( storage );
 
 	GeomHeader* header	  = reinterpret_cast<GeomHeader*>( out );
 	Box4Node*	boxNodes  = reinterpret_cast<Box4Node*>( out + alignUp( sizeof( GeomHeader ) ) );
-	void*		leafNodes = out + alignUp( sizeof( GeomHeader ) ) + alignUp( maxBoxNodeCount( nMax ) * sizeof( Box4Node ) );
-	BuildControl* ctl	  = reinterpret_cast<BuildControl*>( temp + L.control );
+	void*		leafNodes = out + alignUp( sizeof( GeomHeader ) ) + alignUp( maxBoxNodeCount( maxLeaves ) * sizeof( Box4Node ) );
+	BuildControl* ctl	  = reinterpret_cast<BuildControl*>( temp + L.control ); // (first in both layouts)
 
 	const bool	   isMesh	= input.type == hiprtPrimitiveTypeTriangleMesh;
 	const uint32_t geomType = ( input.geomType << 1 ) | ( isMesh ? 1u : 0u );
 	dev.beginProfile( stream );
-	initGeometryKernel<<<1, 1, 0, stream>>>( ctl, header, boxNodes, leafNodes, geometryStorageSize( input ), nMax, geomType );
+	initGeometryKernel<<<1, 1, 0, stream>>>( ctl, header, boxNodes, leafNodes, geometryStorageSize( input, options ), nMax, geomType );
 
 	const uint32_t streamGrid = std::min<uint32_t>( DivideRoundUp( nMax, 256u ), dev.smCount * 8 );
 	if ( isMesh )
@@ -286,20 +393,23 @@ void buildGeometry(
 		}
 		if ( pairing )
 		{
-			uint2*	  pairs = reinterpret_cast<uint2*>( temp + L.pairs );
-			uint32_t* scan	= reinterpret_cast<uint32_t*>( temp + L.pairScan );
+			uint2*	  pairs = reinterpret_cast<uint2*>( temp + ( sbvhTree ? S.pairs : L.pairs ) );
+			uint32_t* scan	= reinterpret_cast<uint32_t*>( temp + ( sbvhTree ? S.pairScan : L.pairScan ) );
 			const uint32_t tiles = DivideRoundUp( nMax, PairTile );
 			HIPRT_CUDA_CHECK( cudaMemsetAsync( scan, 0, size_t( tiles ) * 4, stream ) );
 			pairTrianglesKernel<<<tiles, PairBlock, 0, stream>>>( src, nMax, pairs, scan, ctl );
 			src.pairs = pairs;
 			dev.mark( "pair", stream );
 		}
-		primBoxesKernel<TriangleMeshSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
+		primBoxesKernel<TriangleMeshSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + ( sbvhTree ? S.primRefs : L.primRefs ) );
 		dev.mark( "boxes", stream );
-		runLbvh( dev, src, balanced, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
+		if ( sbvhTree )
+			runSbvh( dev, src, nMax, maxLeaves, maxLeaves > nMax, temp, S, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
+		else
+			runLbvh( dev, src, balanced, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
 		if ( qRegion )
 		{
-			compressBoxNodes( header, qRegion, uint32_t( maxBoxNodeCount( nMax ) ), stream );
+			compressBoxNodes( header, qRegion, uint32_t( maxBoxNodeCount( maxLeaves ) ), stream );
 			dev.mark( "qnodes", stream );
 			HIPRT_CUDA_CHECK( cudaGetLastError() );
 		}
@@ -319,8 +429,11 @@ void buildGeometry(
 			HIPRT_CUDA_CHECK( cudaGetLastError() );
 			return;
 		}
-		primBoxesKernel<AabbListSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
-		runLbvh( dev, src, balanced, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
+		primBoxesKernel<AabbListSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + ( sbvhTree ? S.primRefs : L.primRefs ) );
+		if ( sbvhTree )
+			runSbvh( dev, src, nMax, maxLeaves, maxLeaves > nMax, temp, S, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
+		else
+			runLbvh( dev, src, balanced, nMax, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, leafNodes );
 	}
 }
 
@@ -348,7 +461,12 @@ static SceneLayout sceneLayout( const hiprtSceneBuildInput& input )
 }
 
 size_t sceneStorageSize( const hiprtSceneBuildInput& input ) { return sceneLayout( input ).total; }
-size_t sceneTempSize( const hiprtSceneBuildInput& input, hiprtBuildOptions ) { return tempLayout( input.instanceCount, 0 ).total; }
+size_t sceneTempSize( const hiprtSceneBuildInput& input, hiprtBuildOptions options )
+{
+	// a high-quality scene build bins whole instances (no spatial splits: the instance-node array holds one node per instance)
+	if ( usesSbvhBuilder( options ) && !isImport( options ) ) return sbvhLayout( input.instanceCount, 0, input.instanceCount, false ).total;
+	return tempLayout( input.instanceCount, 0 ).total;
+}
 
 void buildScene(
 	const DeviceInfo& dev, const hiprtSceneBuildInput& input, hiprtBuildOptions options, void* tempBuffer, cudaStream_t stream, void* storage )
@@ -393,16 +511,25 @@ void buildScene(
 		return;
 	}
 	const uint32_t streamGrid = std::min<uint32_t>( DivideRoundUp( n, 256u ), dev.smCount * 8 );
+	if ( usesSbvhBuilder( options ) )
+	{
+		const SbvhLayout Q = sbvhLayout( n, 0, n, false );
+		primBoxesKernel<InstanceSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + Q.primRefs );
+		runSbvh( dev, src, n, n, false, temp, Q, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
+		return;
+	}
 	primBoxesKernel<InstanceSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
 	runLbvh( dev, src, balanced, n, temp, L, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
 }
 // Refit in place (hiprtBuildOperationUpdate): same primitive count and order as the build, moved positions. The kernels take
 // the node arrays from the device header, so a compacted, loaded or imported structure is updated where it actually lies.
 void updateGeometry(
-	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions, void*, cudaStream_t stream, void* storage, void* qRegion )
+	const DeviceInfo& dev, const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void*, cudaStream_t stream, void* storage, void* qRegion )
 {
 	(void)dev;
-	const uint32_t nMax = uint32_t( std::max( geometryPrimCount( input ), importLeafCount( input ) ) );
+	// (an upper bound of the box-node count, for the grids below; whatever the options say now, the structure may have been built
+	// with duplicated references or imported)
+	const uint32_t nMax = uint32_t( std::max( { leafCapacity( input, options ), importLeafCount( input ), geometryPrimCount( input ) + geometryPrimCount( input ) / 2 } ) );
 	if ( nMax == 0 ) throw std::runtime_error( "empty geometry" );
 	const GeomHeader* header = static_cast<const GeomHeader*>( storage );
 	const uint32_t	  grid	 = DivideRoundUp( uint32_t( maxBoxNodeCount( nMax ) ), 128u ); // upper bound; trimmed by header->boxNodeCount

@@ -43,8 +43,9 @@ struct DeviceInfo
 
 // ---- sizes -------------------------------------------------------------------------------------
 size_t geometryPrimCount( const hiprtGeometryBuildInput& input ); // triangles (or pairs if given) / AABBs
-size_t geometryStorageSize( const hiprtGeometryBuildInput& input );	   // the public structure: header.size
-size_t geometryAllocationSize( const hiprtGeometryBuildInput& input ); // + the traversal-only Q region of triangle meshes (qnode.h)
+// (the options matter: a high-quality build with spatial splits may create up to 1.5 leaves per primitive)
+size_t geometryStorageSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options );	  // the public structure: header.size
+size_t geometryAllocationSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options ); // + the traversal-only Q region of triangle meshes (qnode.h)
 void*  geometryQRegion( const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* storage ); // nullptr: this build has none
 size_t geometryTempSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options );
 size_t sceneStorageSize( const hiprtSceneBuildInput& input );
@@ -93,6 +94,9 @@ struct TempLayout
 	size_t total;
 };
 TempLayout tempLayout( size_t primCount, size_t triangleCountForPairing );
+// the same for a high-quality build (sbvh_kernels.cuh): control, state (sbvh::State), primRefs, nodes (binary nodes, 32 B),
+// leaves (leaf records, 32 B), maxRefs (a count, not an offset), taskQueue, total
+void highQualityTempLayout( size_t primCount, size_t triangleCountForPairing, bool spatialSplits, size_t out[8] );
 
 struct BuildControl
 {

@@ -176,6 +176,10 @@ HIPRT_API hiprtError hiprtB200WaitFlags(
 // (parity tests read sorted Morton keys, binary nodes etc. from there). 16 size_t values,
 // see hiprt_b200/csrc/builders.h TempLayout.
 HIPRT_API hiprtError hiprtB200GetTempLayout( size_t primCount, size_t pairedTriangleCount, size_t* offsetsOut, uint32_t numOffsets );
+// The same for a PreferHighQualityBuild of `primCount` primitives: 8 values -- control, state, primRefs, binary nodes, leaf records,
+// the reference budget (a count), the collapse queue, total (hiprt_b200/csrc/builders.h highQualityTempLayout).
+HIPRT_API hiprtError
+hiprtB200GetHighQualityTempLayout( size_t primCount, size_t pairedTriangleCount, int spatialSplits, size_t* offsetsOut, uint32_t numOffsets );
 
 // The device-side API header tree (hiprt_device.h and what it includes) as embedded strings,
 // for callers that NVRTC-compile their own kernels. Returns the number of headers.

@@ -106,6 +106,10 @@ def lib():
         L.orc_scene_create_multilevel.restype = vp
         L.orc_geometry_create_aabbs.argtypes = [vp, u32, u32, u32]
         L.orc_geometry_create_aabbs.restype = vp
+        L.orc_geometry_create_sbvh.argtypes = [vp, u32, u32, vp, u32, u32, vp, u32, i32]
+        L.orc_geometry_create_sbvh.restype = vp
+        L.orc_geometry_create_aabbs_sbvh.argtypes = [vp, u32, u32, u32, i32]
+        L.orc_geometry_create_aabbs_sbvh.restype = vp
         L.orc_trace_general.argtypes = [vp, i32, vp, u32, u32, i32, CUSTOM_INTERSECT_FN, HIT_FILTER_FN, vp, u32, vp, vp]
         L.orc_geometry_set_geom_type.argtypes = [vp, u32]
         _lib = L
@@ -141,14 +145,24 @@ def morton(pos, ext):
 class Geometry:
     """LBVH-built triangle geometry of the oracle."""
 
-    def __init__(self, vertices, indices=None, pairs=None, allow_pairing=True):
+    def __init__(self, vertices, indices=None, pairs=None, allow_pairing=True, high_quality=False, spatial_splits=True):
+        """high_quality: the SBVH restatement (PreferHighQualityBuild) instead of the LBVH; `sbvh_stats` then holds
+        (levels, references incl. duplicates, spatial splits, splits by arrival, inconsistencies)."""
         self.vertices = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
         self.indices = None if indices is None else np.ascontiguousarray(indices, np.uint32).reshape(-1, 3)
         self.pairs_in = None if pairs is None else np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
         ntri = 0 if self.indices is None else len(self.indices)
+        self.high_quality = high_quality
+        if high_quality:
+            self.h = lib().orc_geometry_create_sbvh(
+                _p(self.vertices), len(self.vertices), 12, _p(self.indices), ntri, 12,
+                _p(self.pairs_in), 0 if self.pairs_in is None else len(self.pairs_in), int(allow_pairing) | (2 if spatial_splits else 0))
+            return
         self.h = lib().orc_geometry_create(
             _p(self.vertices), len(self.vertices), 12, _p(self.indices), ntri, 12,
             _p(self.pairs_in), 0 if self.pairs_in is None else len(self.pairs_in), int(allow_pairing))
+
+    sbvh_stats = property(lambda s: s._read(3, np.uint32, 5) if s.prim_count > 1 else np.zeros(5, np.uint32))
 
     def __del__(self):
         try:
@@ -180,7 +194,9 @@ class Geometry:
     keys = property(lambda s: s._read(2, np.uint32, s.prim_count))
     sorted_keys = property(lambda s: s._read(3, np.uint32, s.prim_count))
     sorted_vals = property(lambda s: s._read(4, np.uint32, s.prim_count))
-    scratch = property(lambda s: s._read(5, SCRATCH_DTYPE, max(s.prim_count - 1, 0)))
+    scratch = property(lambda s: s._read(5, SCRATCH_DTYPE, s._count(4)))
+    leaf_record_boxes = property(lambda s: s._read(11, np.float32, 6 * s._count(5)).reshape(-1, 2, 3))
+    leaf_record_prims = property(lambda s: s._read(12, np.uint32, s._count(5)))
     box_nodes = property(lambda s: s._read(6, BOX4_DTYPE, s.box_count))
     leaves = property(lambda s: s._read(7, TRIPAIR_DTYPE, s.leaf_count))
     scene_box = property(lambda s: s._read(8, np.float32, 6).reshape(2, 3))
@@ -267,10 +283,13 @@ class AabbGeometry:
     """Custom primitives: an AABB list (float32 [n, 6] min xyz, max xyz) built by the oracle's LBVH pipeline with custom leaves.
     Hits come from the intersection function passed to trace_general."""
 
-    def __init__(self, aabbs, geom_type=0):
+    def __init__(self, aabbs, geom_type=0, high_quality=False, spatial_splits=True):
         self.aabbs = np.ascontiguousarray(aabbs, np.float32).reshape(-1, 6)
         self.geom_type = geom_type
-        self.h = lib().orc_geometry_create_aabbs(_p(self.aabbs), len(self.aabbs), 24, geom_type)
+        if high_quality:
+            self.h = lib().orc_geometry_create_aabbs_sbvh(_p(self.aabbs), len(self.aabbs), 24, geom_type, 2 if spatial_splits else 0)
+        else:
+            self.h = lib().orc_geometry_create_aabbs(_p(self.aabbs), len(self.aabbs), 24, geom_type)
 
     def _read(self, what, dtype, n):
         out = np.zeros(n, dtype)
@@ -278,7 +297,7 @@ class AabbGeometry:
         return out
 
     box_nodes = property(lambda s: s._read(6, BOX4_DTYPE, int(lib().orc_geometry_count(s.h, 1))))
-    leaves = property(lambda s: s._read(10, np.uint32, len(s.aabbs)))  # CustomNode: the primitive index, in leaf order
+    leaves = property(lambda s: s._read(10, np.uint32, int(lib().orc_geometry_count(s.h, 2))))  # CustomNode: the primitive index, in leaf order
 
     def __del__(self):
         try:

@@ -68,10 +68,13 @@ def tea16(v0, v1):
     return v0, v1
 
 
-def validate_wide_bvh(boxes, leaves, prim_count_expected=None):
+def validate_wide_bvh(boxes, leaves, prim_count_expected=None, duplicated_references=False):
     """Structural check of a 4-wide BVH read back from the device (any builder): every leaf is referenced
     exactly once, every child box equals the exact union of what is below it (boxes are fp32 min/max, so
-    equality is exact), parent links are consistent. Returns the SAH-style cost sum(child areas)/root area."""
+    equality is exact), parent links are consistent. Returns the SAH-style cost sum(child areas)/root area.
+    duplicated_references: a high-quality build with spatial splits -- a primitive may sit in several leaves, each with the
+    part of its box the leaf is responsible for, and an inner child box is the union of the BINS' boxes, which contains
+    (rather than equals) the union of the boxes below it."""
     INVALID = 0xFFFFFFFF
     child = boxes["child"]
     valid = child != INVALID
@@ -80,7 +83,7 @@ def validate_wide_bvh(boxes, leaves, prim_count_expected=None):
     is_leaf = valid & (ctype != 5)
     assert np.array_equal(valid.sum(1), boxes["childCount"]), "childCount does not match the valid slots"
     # leaves: referenced exactly once
-    leaf_addr = child[is_leaf] >> 3
+    leaf_addr = child[is_leaf] >> np.where(ctype[is_leaf] == 6, 4, 3)  # (instance nodes are addressed like box nodes)
     assert len(leaf_addr) == len(leaves) and np.array_equal(np.sort(leaf_addr), np.arange(len(leaves))), "leaves not referenced exactly once"
     # box children: referenced exactly once, never the root
     box_addr = child[is_box] >> 4
@@ -94,14 +97,23 @@ def validate_wide_bvh(boxes, leaves, prim_count_expected=None):
     lo = np.where(valid[..., None], boxes["box"][:, :, 0, :], np.inf).min(1)
     hi = np.where(valid[..., None], boxes["box"][:, :, 1, :], -np.inf).max(1)
     cb = boxes["box"][is_box]
-    assert np.array_equal(cb[:, 0], lo[box_addr]) and np.array_equal(cb[:, 1], hi[box_addr]), "inner child box is not the union of its children"
+    if duplicated_references:
+        assert np.all(cb[:, 0] <= cb[:, 1]), "empty inner child box"
+    else:
+        assert np.array_equal(cb[:, 0], lo[box_addr]) and np.array_equal(cb[:, 1], hi[box_addr]), "inner child box is not the union of its children"
     if leaves.dtype.names and "v" in leaves.dtype.names:
         v = leaves["v"]
         lb = boxes["box"][is_leaf]
-        assert np.array_equal(lb[:, 0], v[leaf_addr].min(1)) and np.array_equal(lb[:, 1], v[leaf_addr].max(1)), "leaf box is not the box of its vertices"
+        if duplicated_references:
+            assert np.all(lb[:, 0] >= v[leaf_addr].min(1)) and np.all(lb[:, 1] <= v[leaf_addr].max(1)) and np.all(lb[:, 0] <= lb[:, 1]), "leaf box leaves the box of its vertices"
+        else:
+            assert np.array_equal(lb[:, 0], v[leaf_addr].min(1)) and np.array_equal(lb[:, 1], v[leaf_addr].max(1)), "leaf box is not the box of its vertices"
         prims = np.concatenate([leaves["primIndex0"], leaves["primIndex1"][leaves["primIndex1"] != leaves["primIndex0"]]])
         if prim_count_expected is not None:
-            assert np.array_equal(np.sort(prims), np.arange(prim_count_expected)), "triangles are not covered exactly once"
+            if duplicated_references:
+                assert np.array_equal(np.unique(prims), np.arange(prim_count_expected)), "triangles are not all covered"
+            else:
+                assert np.array_equal(np.sort(prims), np.arange(prim_count_expected)), "triangles are not covered exactly once"
     ext = np.maximum(boxes["box"][:, :, 1, :] - boxes["box"][:, :, 0, :], 0)
     area = 2 * (ext[..., 0] * ext[..., 1] + ext[..., 0] * ext[..., 2] + ext[..., 1] * ext[..., 2])
     root_ext = hi[0] - lo[0]
