@@ -39,7 +39,7 @@ TempLayout tempLayout( size_t n, size_t pairTriangles )
 // High-quality build (SBVH): temporary buffer and launch. `maxRefs` = leafCapacity(): the reference budget.
 struct SbvhLayout
 {
-	size_t control, state, pairs, pairScan, primRefs, refs[2], refTask[2], tasks[2], objectBins, spatialBins, nodes, leaves, taskQueue, total;
+	size_t control, state, timeline, pairs, pairScan, primRefs, refs[2], refTask[2], tasks[2], objectBins, spatialBins, nodes, leaves, taskQueue, total;
 };
 static SbvhLayout sbvhLayout( size_t n, size_t pairTriangles, size_t maxRefs, bool spatial )
 {
@@ -53,6 +53,7 @@ static SbvhLayout sbvhLayout( size_t n, size_t pairTriangles, size_t maxRefs, bo
 	const size_t maxTasks = std::max<size_t>( maxRefs / 2, 1 );
 	L.control	  = take( sizeof( BuildControl ) );
 	L.state		  = take( sizeof( sbvh::State ) );
+	L.timeline	  = take( sbvh::TimelineLevels * sbvh::TimelineSlots * sizeof( uint64_t ) );
 	L.pairs		  = take( pairTriangles * sizeof( uint2 ) );
 	L.pairScan	  = take( DivideRoundUp( pairTriangles, size_t( PairTile ) ) * sizeof( uint32_t ) );
 	L.primRefs	  = take( n * 32 );
@@ -180,6 +181,9 @@ static void runSbvh(
 	P.leaves	  = temp + L.leaves;
 	P.taskQueue	  = taskQueue;
 	P.maxRefs	  = maxRefs;
+	static const bool wantTimeline = getenv( "HIPRT_B200_SBVH_TIMELINE" ) != nullptr; // tools/profile_sbvh.py
+	P.timeline	  = wantTimeline ? reinterpret_cast<uint64_t*>( temp + L.timeline ) : nullptr;
+	if ( wantTimeline ) HIPRT_CUDA_CHECK( cudaMemsetAsync( temp + L.timeline, 0, sbvh::TimelineLevels * sbvh::TimelineSlots * sizeof( uint64_t ), stream ) );
 
 	// every CTA of the grid must be resident (the levels are separated by grid barriers): sized from the occupancy of this kernel,
 	// launched cooperatively so that the runtime refuses rather than deadlocks if the device cannot hold it

@@ -14,7 +14,7 @@
 //     turns every later pass into a gather).
 //   * Binning is privatised per CTA while a CTA's span of references stays inside one task (the top of the tree): shared-memory
 //     bins, flushed once per task change. Below that, tasks are many and the global atomics spread out.
-//   * Split search: one sub-warp of `bins` lanes per task, prefix / suffix unions by shuffles (the reference: one thread per task
+//   * Split search: one sub-warp of 8 / 16 / 32 lanes (the bin count rounded up) per task, prefix / suffix unions by shuffles (the reference: one thread per task
 //     looping over bins held in local memory).
 //   * Child segments, nodes, tasks and leaf records are allocated in the split phase, so a node is written once, complete.
 // The result is the same pair of record arrays every other builder hands to collapsePackKernel (build_kernels.cuh): binary
@@ -36,6 +36,8 @@ constexpr uint32_t MaxBins = 32; // BvhConfig.h:47
 constexpr float	   Beta	   = 1.0e-4f; // overlap of the object split's children, relative to the scene area, that makes a task try spatial splits
 constexpr float	   Gamma   = 1.0e-3f; // axes shorter than this fraction of the scene extent are not split spatially
 constexpr float	   Epsilon = 1.0e-2f; // centroid bins are scaled by (1 - Epsilon)
+constexpr uint32_t TimelineSlots  = 8;	// per level: start, reset, object bins, object split, spatial bins, demand, split, distribute
+constexpr uint32_t TimelineLevels = 128;
 
 // A task = one binary node whose references are still to be partitioned. 128 bytes, two 64-byte halves.
 struct alignas( 128 ) Task
@@ -68,7 +70,7 @@ struct LevelCounts
 	uint32_t taskCount;
 	uint32_t activeRefs;   // references of this level's tasks
 	uint32_t spatialTasks; // tasks of this level that try spatial splits
-	uint32_t pad;
+	uint32_t demand;	   // references those splits would duplicate
 };
 
 struct State
@@ -97,6 +99,7 @@ struct Params
 	void*		   nodes;		// binary nodes out (scratch records)
 	void*		   leaves;		// leaf records out
 	uint64_t*	   taskQueue;	// collapse queue: slot 0 receives the root task
+	uint64_t*	   timeline; // optional: %globaltimer after every grid barrier, TimelineSlots values per level (profiling)
 	uint32_t	   maxRefs; // capacity of the reference / node / leaf arrays (sized on the host from the primitive count BEFORE pairing)
 };
 
@@ -134,18 +137,18 @@ __device__ __forceinline__ uint32_t centroidBin( float lo, float hi, float taskL
 	return uint32_t( v );
 }
 __device__ __forceinline__ float binPlane( float taskLo, float binSize, uint32_t i ) { return __fmaf_rn( binSize, float( i + 1u ), taskLo ); }
-// first and last spatial bin a box touches along one axis
+// First and last spatial bin a box touches along one axis: first = the first bin whose upper plane lies above `lo`, last = the first
+// whose upper plane reaches `hi` (the last bin if none does). The planes are non-decreasing in i, so the reference's linear scan over
+// the planes (SbvhBuilderKernels.h:273-281) is a lower-bound search: 5 probes instead of 31, the same result.
 __device__ __forceinline__ void spatialBinRange( float lo, float hi, float taskLo, float binSize, uint32_t bins, uint32_t& first, uint32_t& last )
 {
-	first = bins - 1u, last = bins - 1u;
-	bool gotFirst = false, gotLast = false;
-	for ( uint32_t i = 0; i + 1u < bins; ++i )
+	uint32_t f = 0, l = 0; // number of planes i in [0, bins - 1) with !( lo < plane_i ) / !( hi <= plane_i )
+	for ( uint32_t step = 16u; step > 0u; step >>= 1 )
 	{
-		const float position = binPlane( taskLo, binSize, i );
-		if ( !gotFirst && lo < position ) first = i, gotFirst = true;
-		if ( !gotLast && hi <= position ) last = i, gotLast = true;
+		if ( f + step < bins && !( lo < binPlane( taskLo, binSize, f + step - 1u ) ) ) f += step;
+		if ( l + step < bins && !( hi <= binPlane( taskLo, binSize, l + step - 1u ) ) ) l += step;
 	}
-	if ( first > last ) first = last;
+	first = min( f, l ), last = l;
 }
 __device__ __forceinline__ float sahCost( const DBox& l, uint32_t nl, const DBox& r, uint32_t nr )
 {
@@ -269,8 +272,7 @@ __device__ __forceinline__ void storeBox6( float* p, const DBox& b )
 __device__ __forceinline__ uint32_t binsOfLevel( uint32_t taskCount, uint32_t maxRefs )
 {
 	// the bin arrays hold 3 x MinBins bins for maxRefs / 2 tasks: fewer tasks, more bins each (SbvhBuilder.h:352)
-	const uint32_t fit = MinBins * ( maxRefs / 2u ) / max( taskCount, 1u );
-	return fit >= 32u ? 32u : ( fit >= 16u ? 16u : 8u );
+	return min( MinBins * ( maxRefs / 2u ) / max( taskCount, 1u ), MaxBins );
 }
 
 // Grid barrier: every CTA of the (cooperative, fully resident) grid arrives once per call. The counter only grows.
@@ -504,20 +506,32 @@ __device__ __forceinline__ void reduceChoice( SplitChoice& c, uint32_t width, ui
 // A lane keeps the best candidate of ITS bin index over the three axes (ties: the lower axis), the group then reduces.
 template <bool Spatial>
 __device__ __forceinline__ SplitChoice searchBins(
-	const float* taskBins, bool active, const DBox& taskBox, float startCost, float edgeThreshold, uint32_t width, uint32_t laneInGroup, uint32_t groupBase )
+	const float* taskBins, bool active, const DBox& taskBox, float startCost, float edgeThreshold, uint32_t binCount, uint32_t width, uint32_t laneInGroup,
+	uint32_t groupBase )
 {
 	SplitChoice best;
 	best.cost = startCost, best.key = InvalidValue, best.box0 = emptyBox(), best.box1 = emptyBox(), best.count0 = 0, best.count1 = 0;
+	// the bins of the three axes are fetched together: the phase is bound by the latency of these loads (the build runs at two
+	// CTAs per SM), three in flight per lane instead of one
+	BinAcc bins3[3];
+	bool   on3[3];
+#pragma unroll
 	for ( uint32_t axis = 0; axis < 3; ++axis )
 	{
-		bool axisOn = active;
-		if constexpr ( Spatial ) axisOn = active && !( __fsub_rn( axisOf( taskBox, true, axis ), axisOf( taskBox, false, axis ) ) < edgeThreshold );
-		BinAcc mine{ emptyBox(), 0u, 0u };
-		if ( axisOn ) mine = loadBin( taskBins + size_t( axis * width + laneInGroup ) * 8 );
+		on3[axis] = active;
+		if constexpr ( Spatial ) on3[axis] = active && !( __fsub_rn( axisOf( taskBox, true, axis ), axisOf( taskBox, false, axis ) ) < edgeThreshold );
+		bins3[axis] = BinAcc{ emptyBox(), 0u, 0u }; // (lanes past the last bin hold empty bins)
+		if ( on3[axis] && laneInGroup < binCount ) bins3[axis] = loadBin( taskBins + size_t( axis * binCount + laneInGroup ) * 8 );
+	}
+#pragma unroll
+	for ( uint32_t axis = 0; axis < 3; ++axis )
+	{
+		const bool	 axisOn = on3[axis];
+		const BinAcc mine	= bins3[axis];
 		const BinAcc left  = scanBins( mine, true, width, laneInGroup );
 		const BinAcc right = shflBin( scanBins( mine, false, width, laneInGroup ), 1, false, width ); // bins above mine
 		const uint32_t nl = left.enter, nr = Spatial ? right.exit : right.enter;
-		if ( axisOn && laneInGroup + 1u < width && nl > 0u && nr > 0u )
+		if ( axisOn && laneInGroup + 1u < binCount && nl > 0u && nr > 0u )
 		{
 			const float cost = sahCost( left.box, nl, right.box, nr );
 			if ( best.cost > cost ) best.cost = cost, best.key = axis * 32u + laneInGroup, best.box0 = left.box, best.box1 = right.box, best.count0 = nl, best.count1 = nr;
@@ -533,8 +547,9 @@ __device__ __forceinline__ void findObjectSplitPhase(
 {
 	Task*		   tasks		 = P.tasks[cur];
 	const uint32_t lane			 = laneId();
-	const uint32_t laneInGroup	 = lane % binCount, group = lane / binCount, groupsPerWarp = 32u / binCount;
-	const uint32_t groupBase	 = group * binCount;
+	const uint32_t width		 = binCount <= 8u ? 8u : ( binCount <= 16u ? 16u : 32u ); // lanes per task
+	const uint32_t laneInGroup	 = lane % width, group = lane / width, groupsPerWarp = 32u / width;
+	const uint32_t groupBase	 = group * width;
 	const uint32_t warpsInGrid	 = gridDim.x * ( Block / 32u );
 	const uint32_t warp			 = blockIdx.x * ( Block / 32u ) + ( threadIdx.x >> 5 );
 	uint32_t	   spatialTasks	 = 0;
@@ -546,7 +561,7 @@ __device__ __forceinline__ void findObjectSplitPhase(
 		const DBox	   box	  = loadBox6( task->box );
 		const uint32_t count  = __ldcg( &task->count );
 		const bool	   forced = level >= forceLevel;
-		SplitChoice	   c	  = searchBins<false>( P.objectBins + size_t( active ? t : 0u ) * 3u * binCount * 8, active && !forced, box, FltMax, 0.0f, binCount, laneInGroup, groupBase );
+		SplitChoice	   c	  = searchBins<false>( P.objectBins + size_t( active ? t : 0u ) * 3u * binCount * 8, active && !forced, box, FltMax, 0.0f, binCount, width, laneInGroup, groupBase );
 		uint32_t axis = c.key >> 5, index = c.key & 31u;
 		if ( c.key == InvalidValue )
 		{
@@ -568,7 +583,7 @@ __device__ __forceinline__ void findObjectSplitPhase(
 				task->split = axis | ( trySpatial ? 8u : 0u ) | ( index << 4 );
 				if ( trySpatial ) ++spatialTasks;
 			}
-			if ( trySpatial )
+			if ( trySpatial && laneInGroup < binCount )
 				for ( uint32_t a = 0; a < 3; ++a )
 					resetBin( P.spatialBins + ( size_t( t ) * 3u * binCount + a * binCount + laneInGroup ) * 8 );
 		}
@@ -580,17 +595,21 @@ __device__ __forceinline__ void findObjectSplitPhase(
 }
 
 // ---- phase: final split of every task, allocation of what it creates ----------------------------------------------------------------
-template <typename Source>
+// DemandOnly: the spatial search alone, to add up the references the level's spatial splits would duplicate (LevelCounts::demand);
+// the split phase proper repeats the search (cheap next to the binning) knowing whether the level's demand fits the budget.
+template <typename Source, bool DemandOnly>
 __device__ __forceinline__ void splitPhase(
-	const Params& P, uint32_t cur, uint32_t level, uint32_t remaining, uint32_t refCount, uint32_t taskCount, uint32_t binCount, float edgeThreshold )
+	const Params& P, uint32_t cur, uint32_t level, uint32_t remaining, uint32_t demand, uint32_t refCount, uint32_t taskCount, uint32_t binCount,
+	float edgeThreshold )
 {
 	Task*		   tasks	   = P.tasks[cur];
 	Task*		   nextTasks   = P.tasks[cur ^ 1u];
 	State*		   state	   = P.state;
 	LevelCounts*   next		   = &state->level[( level + 1u ) & 1u];
 	const uint32_t lane		   = laneId();
-	const uint32_t laneInGroup = lane % binCount, group = lane / binCount, groupsPerWarp = 32u / binCount;
-	const uint32_t groupBase   = group * binCount;
+	const uint32_t width	   = binCount <= 8u ? 8u : ( binCount <= 16u ? 16u : 32u ); // lanes per task
+	const uint32_t laneInGroup = lane % width, group = lane / width, groupsPerWarp = 32u / width;
+	const uint32_t groupBase   = group * width;
 	const uint32_t warpsInGrid = gridDim.x * ( Block / 32u );
 	const uint32_t warp		   = blockIdx.x * ( Block / 32u ) + ( threadIdx.x >> 5 );
 	for ( uint32_t base = warp * groupsPerWarp; base < taskCount; base += warpsInGrid * groupsPerWarp )
@@ -606,19 +625,29 @@ __device__ __forceinline__ void splitPhase(
 		SplitChoice c;
 		c.key = InvalidValue;
 		if ( anySpatial )
-			c = searchBins<true>( P.spatialBins + size_t( active ? t : 0u ) * 3u * binCount * 8, trySpatial, box, trySpatial ? __ldcg( &task->cost ) : 0.0f, edgeThreshold, binCount, laneInGroup, groupBase );
-		if ( !active || laneInGroup != 0 ) continue;
-
-		DBox	 box0 = loadBox6( task->box0 ), box1 = loadBox6( task->box1 );
-		uint32_t count0 = __ldcg( &task->count0 ), count1 = __ldcg( &task->count1 );
-		if ( trySpatial && c.key != InvalidValue )
+			c = searchBins<true>( P.spatialBins + size_t( active ? t : 0u ) * 3u * binCount * 8, trySpatial, box, trySpatial ? __ldcg( &task->cost ) : 0.0f, edgeThreshold, binCount, width, laneInGroup, groupBase );
+		const bool leader = active && laneInGroup == 0;
+		DBox	   box0 = emptyBox(), box1 = emptyBox();
+		uint32_t   count0 = 0, count1 = 0;
+		if ( leader )
+		{
+			box0 = loadBox6( task->box0 ), box1 = loadBox6( task->box1 );
+			count0 = __ldcg( &task->count0 ), count1 = __ldcg( &task->count1 );
+		}
+		if constexpr ( DemandOnly )
+		{
+			if ( leader && trySpatial && c.key != InvalidValue ) atomicAdd( &state->level[level & 1u].demand, c.count0 + c.count1 - count0 - count1 );
+			continue;
+		}
+		if ( leader && trySpatial && c.key != InvalidValue )
 		{
 			// Every reference the split duplicates must fit the reference budget (SbvhBuilderKernels.h:571-587, where the tasks of
-			// a level draw on the budget in atomic arrival order). Here a task may use the share of what is left at the start of
-			// the level that its reference count has among the level's references: the outcome does not depend on any order, the
-			// shares cannot overdraw, the root may use everything, and what a level leaves goes to the next.
+			// a level draw on the budget in atomic arrival order until it is gone). Here the outcome does not depend on any order:
+			// a level whose whole demand fits what is left gets all its spatial splits; in the level that would overdraw, a task
+			// may use the share of the rest that its reference count has among the level's references (the shares cannot
+			// overdraw either), and what a level leaves goes to the next.
 			const uint32_t duplicates = c.count0 + c.count1 - count0 - count1;
-			const uint32_t share	  = uint32_t( uint64_t( remaining ) * __ldcg( &task->count ) / refCount );
+			const uint32_t share	  = demand <= remaining ? remaining : uint32_t( uint64_t( remaining ) * __ldcg( &task->count ) / refCount );
 			if ( duplicates <= share )
 			{
 				atomicAdd( &state->totalRefs, duplicates );
@@ -629,6 +658,41 @@ __device__ __forceinline__ void splitPhase(
 			}
 		}
 		split &= ~8u;
+		// What the task creates -- a binary node + a task + a segment of references for a child with several references, a leaf
+		// record for a child with one -- is allocated once per warp: the four counters are single hot lines of the whole grid
+		// (ncu: a sixth of all stall samples of the build sat on per-task atomics here).
+		const uint32_t inner = leader ? uint32_t( count0 > 1u ) + uint32_t( count1 > 1u ) : 0u;
+		const uint32_t leafs = leader ? 2u - inner : 0u;
+		const uint32_t refs	 = leader ? ( count0 > 1u ? count0 : 0u ) + ( count1 > 1u ? count1 : 0u ) : 0u;
+		uint32_t	   innerScan = inner, leafScan = leafs, refScan = refs; // inclusive scans over the warp's leaders
+		for ( uint32_t d = width; d < 32u; d <<= 1 )
+		{
+			const uint32_t a = __shfl_up_sync( FullMask, innerScan, d ), b = __shfl_up_sync( FullMask, leafScan, d ), e = __shfl_up_sync( FullMask, refScan, d );
+			if ( lane >= d ) innerScan += a, leafScan += b, refScan += e;
+		}
+		uint32_t nodeBase = 0, taskBase = 0, refBase = 0, leafBase = 0;
+		if ( lane == 31u - ( 31u % width ) ) // the last leader lane holds the totals
+		{
+			if ( innerScan )
+			{
+				nodeBase = atomicAdd( &state->nodeCount, innerScan );
+				taskBase = atomicAdd( &next->taskCount, innerScan );
+				refBase	 = atomicAdd( &next->activeRefs, refScan );
+			}
+			if ( leafScan ) leafBase = atomicAdd( &state->leafCount, leafScan );
+		}
+		const uint32_t last = 31u - ( 31u % width );
+		nodeBase = __shfl_sync( FullMask, nodeBase, last ) + innerScan - inner;
+		taskBase = __shfl_sync( FullMask, taskBase, last ) + innerScan - inner;
+		refBase	 = __shfl_sync( FullMask, refBase, last ) + refScan - refs;
+		leafBase = __shfl_sync( FullMask, leafBase, last ) + leafScan - leafs;
+		if ( !leader ) continue;
+		if ( nodeBase + inner > P.maxRefs || taskBase + inner > P.maxRefs / 2u || refBase + refs > P.maxRefs || leafBase + leafs > P.maxRefs )
+		{
+			atomicMax( &state->error, 2u );
+			continue;
+		}
+
 		const uint32_t minWord = __ldcg( &task->out0 );
 		uint32_t	   child[2], out[2], nextTask[2];
 		for ( uint32_t side = 0; side < 2; ++side )
@@ -637,26 +701,18 @@ __device__ __forceinline__ void splitPhase(
 			nextTask[side]	 = InvalidValue;
 			if ( n > 1u )
 			{
-				const uint32_t node = atomicAdd( &state->nodeCount, 1u );
-				const uint32_t nt	= atomicAdd( &next->taskCount, 1u );
-				out[side]			= atomicAdd( &next->activeRefs, n );
-				child[side]			= makeNodeIndex( node, BoxType );
-				nextTask[side]		= nt;
-				if ( node >= P.maxRefs || nt >= P.maxRefs / 2u || out[side] + n > P.maxRefs )
-				{
-					atomicMax( &state->error, 2u );
-					continue;
-				}
-				Task* c2 = nextTasks + nt;
+				const uint32_t node = nodeBase++, nt = taskBase++;
+				out[side]	   = refBase, refBase += n;
+				child[side]	   = makeNodeIndex( node, BoxType );
+				nextTask[side] = nt;
+				Task* c2	   = nextTasks + nt;
 				storeBox6( c2->box, side ? box1 : box0 );
 				c2->count = n, c2->node = node, c2->split = 0u, c2->out0 = InvalidValue;
 			}
 			else
 			{
-				const uint32_t leaf = atomicAdd( &state->leafCount, 1u );
-				if ( leaf >= P.maxRefs ) atomicMax( &state->error, 2u );
-				out[side]	= leaf;
-				child[side] = makeNodeIndex( leaf, uint32_t( Source::LeafType ) );
+				out[side]	= leafBase++;
+				child[side] = makeNodeIndex( out[side], uint32_t( Source::LeafType ) );
 			}
 		}
 		task->child0 = child[0], task->child1 = child[1];
@@ -809,6 +865,14 @@ __global__ void __launch_bounds__( Block ) buildKernel( Source src, Params P )
 	HIPRT_SBVH_BARRIER();
 
 	uint32_t level = 0;
+	auto	 stamp = [&]( uint32_t slot ) {
+		if ( P.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && level < TimelineLevels )
+		{
+			uint64_t now;
+			asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( now ) );
+			P.timeline[level * TimelineSlots + slot] = now;
+		}
+	};
 	while ( true )
 	{
 		const uint32_t cur		 = level & 1u;
@@ -817,28 +881,44 @@ __global__ void __launch_bounds__( Block ) buildKernel( Source src, Params P )
 		if ( taskCount == 0u ) break;
 		const uint32_t binCount	 = binsOfLevel( taskCount, budget );
 		const uint32_t remaining = budget - min( ldVolatile( &state->totalRefs ), budget ); // (changes in the split phase only)
+		stamp( 0 );
 
 		resetBinsPhase( P, taskCount, binCount );
 		if ( blockIdx.x == 0 && threadIdx.x == 0 ) state->level[cur ^ 1u] = LevelCounts{ 0u, 0u, 0u, 0u };
 		HIPRT_SBVH_BARRIER();
+		stamp( 1 );
 
 		binPhase<Source, false>( P, src, cur, refCount, binCount, edgeThreshold, sBins, &sWord );
 		HIPRT_SBVH_BARRIER();
+		stamp( 2 );
 
 		findObjectSplitPhase( P, cur, level, forceLevel, taskCount, binCount, overlapThreshold );
 		HIPRT_SBVH_BARRIER();
+		stamp( 3 );
 
-		if ( ldVolatile( &state->level[cur].spatialTasks ) != 0u )
+		const uint32_t spatialTasks = ldVolatile( &state->level[cur].spatialTasks );
+		if ( spatialTasks != 0u )
 		{
 			binPhase<Source, true>( P, src, cur, refCount, binCount, edgeThreshold, sBins, &sWord );
 			HIPRT_SBVH_BARRIER();
 		}
+		stamp( 4 );
 
-		splitPhase<Source>( P, cur, level, remaining, refCount, taskCount, binCount, edgeThreshold );
+		uint32_t demand = 0;
+		if ( spatialTasks != 0u )
+		{
+			splitPhase<Source, true>( P, cur, level, remaining, 0u, refCount, taskCount, binCount, edgeThreshold );
+			HIPRT_SBVH_BARRIER();
+			demand = ldVolatile( &state->level[cur].demand );
+		}
+		stamp( 5 );
+		splitPhase<Source, false>( P, cur, level, remaining, demand, refCount, taskCount, binCount, edgeThreshold );
 		HIPRT_SBVH_BARRIER();
+		stamp( 6 );
 
 		distributePhase<Source>( P, src, cur, refCount, binCount );
 		HIPRT_SBVH_BARRIER();
+		stamp( 7 );
 		++level;
 	}
 
