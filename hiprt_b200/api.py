@@ -174,6 +174,7 @@ SIGNATURES = {
     "hiprtB200TraceSceneHost": [_vp, _vp, _vp, _u32, _vp, C.c_int, _u32, _vp],
     "hiprtB200TraceGeometryFormat": [_vp, _vp, _vp, _u32, _vp, C.c_int, C.c_int, _vp],
     "hiprtB200TraceGeometryFormatHost": [_vp, _vp, _vp, _u32, _vp, C.c_int, C.c_int, _vp],
+    "hiprtB200TraceGeometryIndirect": [_vp, _vp, _vp, _u32, _vp, _vp, C.c_int, C.c_int, _vp],
     "hiprtB200HitFormatSize": [C.c_int],
     "hiprtB200TraceGeometryStats": [_vp, _vp, _vp, _u32, _vp, C.c_int, _vp, _vp],
     "hiprtB200GetGeometrySize": [_vp, _vp, _P(_sz)],

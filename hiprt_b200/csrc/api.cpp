@@ -1114,6 +1114,22 @@ hiprtError hiprtB200TraceGeometryFormat(
 	} );
 }
 
+hiprtError hiprtB200TraceGeometryIndirect(
+	hiprtContext context, hiprtGeometry geometry, const hiprtRay* rays, uint32_t maxRays, const uint32_t* numRaysDevice, void* records, hiprtB200HitFormat format,
+	hiprtTraversalType type, hiprtApiStream stream )
+{
+	if ( !context || !geometry || !numRaysDevice || ( maxRays && ( !rays || !records ) ) || uint32_t( format ) > hiprtB200HitFormatPrimID ) return hiprtErrorInvalidParameter;
+	const void* q		 = nullptr;
+	const bool	triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ), &q );
+	if ( !triangles ) return hiprtErrorInvalidParameter;
+	return guarded( context, [&] {
+		traceGeometry(
+			geometry, true, rays, maxRays, records, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
+			uint32_t( format ), q, numRaysDevice );
+		checkCuda( cudaGetLastError(), "trace launch" );
+	} );
+}
+
 hiprtError hiprtB200TraceGeometryFormatHost(
 	hiprtContext context, hiprtGeometry geometry, const hiprtRay* hostRays, uint32_t numRays, void* hostRecords, hiprtB200HitFormat format, hiprtTraversalType type,
 	hiprtApiStream stream )

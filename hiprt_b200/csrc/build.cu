@@ -243,6 +243,10 @@ static void runLbvh(
 	dev.mark( "morton+histogram", stream );
 
 	const uint32_t tiles = rsort::tileCount( nMax );
+	// The staging buffer holds key + value of a whole tile: 48 KB, above the default dynamic shared-memory limit. Function attributes
+	// belong to the CUDA context the caller made current (an application may create one per hiprtContext and destroy it again, as the
+	// reference's unit tests do), so the attribute is set before every build rather than remembered: a host-side call of about a microsecond.
+	HIPRT_CUDA_CHECK( cudaFuncSetAttribute( rsort::onesweepPass, cudaFuncAttributeMaxDynamicSharedMemorySize, int( sizeof( rsort::Smem ) ) ) );
 	for ( int pass = 0; pass < rsort::Passes; ++pass )
 	{
 		const int in = pass & 1, out = in ^ 1;
@@ -605,12 +609,8 @@ void buildGeometriesBatch(
 	// pageable sources: the runtime stages them before returning, so the caller's arrays may go away
 	HIPRT_CUDA_CHECK( cudaMemcpyAsync( dInputs, inputs, size_t( count ) * sizeof( hiprtGeometryBuildInput ), cudaMemcpyHostToDevice, stream ) );
 	HIPRT_CUDA_CHECK( cudaMemcpyAsync( dStorage, storages, size_t( count ) * sizeof( void* ), cudaMemcpyHostToDevice, stream ) );
-	static bool configured = false; // same value every time: a benign race
-	if ( !configured )
-	{
-		HIPRT_CUDA_CHECK( cudaFuncSetAttribute( batchBuildKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int( sizeof( BatchSmem ) ) ) );
-		configured = true;
-	}
+	// (per CUDA context, see runLbvh: set every time)
+	HIPRT_CUDA_CHECK( cudaFuncSetAttribute( batchBuildKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int( sizeof( BatchSmem ) ) ) );
 	dev.beginProfile( stream );
 	const uint32_t gx = std::min( count, 65535u * 32u );
 	const dim3	   grid( gx, DivideRoundUp( count, gx ) );

@@ -165,8 +165,13 @@ __global__ void __launch_bounds__( PairBlock )
 			const uint32_t a = __ffs( active ) - 1;
 			if ( ( nextOk >> a ) & ( active >> ( a + 1 ) ) & 1u )
 			{
-				fastHeads |= 1u << a;
-				active &= ~( 3u << a );
+				// the whole run a, a+2, a+4 ... of such steps at once: each of them only removes (head, head + 1), so the
+				// greedy rule would take them one after the other with nothing in between (a regular mesh: one step per group)
+				const uint32_t steps = ( ( nextOk & active & ( active >> 1 ) ) >> a ) | 0xAAAAAAAAu; // odd offsets do not matter
+				const uint32_t count = ~steps ? __ffs( ~steps ) - 1u : 32u;							// first even offset that is no step
+				const uint32_t heads = ( 0x55555555u & ( count >= 32u ? 0xFFFFFFFFu : ( 1u << count ) - 1u ) ) << a;
+				fastHeads |= heads;
+				active &= ~( heads | ( heads << 1 ) );
 				continue;
 			}
 			active &= active - 1;

@@ -51,7 +51,7 @@ struct __align__( 16 ) Smem
 	union
 	{
 		uint32_t warpHist[Warps][Radix]; // ranking phase
-		uint32_t stage[Tile];			 // scatter phase (keys, then values)
+		uint2	 stage[Tile];			 // scatter phase: (key, value) by local rank
 	};
 	uint32_t digitStartLocal[Radix];  // first local rank of each digit inside the tile
 	uint32_t digitBaseGlobal[Radix];  // global position of the tile's first element of each digit minus its local start
@@ -97,8 +97,11 @@ __global__ void __launch_bounds__( Block ) onesweepPass(
 		key[i]			   = idx < n ? keysIn[idx] : 0xFFFFFFFFu; // padding sorts last and is never written
 	}
 
-	// ---- rank inside the warp with match_any; the lowest lane of each digit group bumps the counter.
-	// The matches of all items are independent and issued first; only the counter updates are serial.
+	// ---- rank inside the warp with match_any: the lowest lane of each digit group adds the group's size to the warp's counter of
+	// that digit with ONE shared-memory atomic and hands the previous value to its group by shuffle. The atomics of one warp retire
+	// in program order (item i before item i + 1: stability), and nothing else orders the items, so the twelve matches, atomics and
+	// shuffles pipeline (ncu on the read-modify-write loop this replaces -- LDS, __syncwarp, STS, __syncwarp per item -- showed the
+	// short-scoreboard stall on top).
 	uint32_t peers[Items];
 #pragma unroll
 	for ( int i = 0; i < Items; ++i )
@@ -106,12 +109,11 @@ __global__ void __launch_bounds__( Block ) onesweepPass(
 #pragma unroll
 	for ( int i = 0; i < Items; ++i )
 	{
-		const uint32_t d	= ( key[i] >> shift ) & ( Radix - 1 );
-		const uint32_t prev = s.warpHist[warp][d];
-		__syncwarp();
-		if ( ( peers[i] & laneMaskLt() ) == 0 ) s.warpHist[warp][d] = prev + __popc( peers[i] );
-		__syncwarp();
-		rank[i] = prev + __popc( peers[i] & laneMaskLt() );
+		const uint32_t d	  = ( key[i] >> shift ) & ( Radix - 1 );
+		const uint32_t leader = __ffs( peers[i] ) - 1u;
+		uint32_t	   prev	  = 0;
+		if ( lane == leader ) prev = atomicAdd( &s.warpHist[warp][d], uint32_t( __popc( peers[i] ) ) );
+		rank[i] = __shfl_sync( FullMask, prev, leader ) + __popc( peers[i] & laneMaskLt() );
 	}
 	__syncthreads();
 
@@ -203,37 +205,12 @@ __global__ void __launch_bounds__( Block ) onesweepPass(
 	__syncthreads(); // warpHist is dead from here on: the union becomes the staging buffer
 
 	const uint32_t valid = min( uint32_t( Tile ), n - tileBase );
-	// keys: stage by local rank, then write runs
-#pragma unroll
-	for ( int i = 0; i < Items; ++i )
-		s.stage[rank[i]] = key[i];
-	__syncthreads();
-#pragma unroll
-	for ( int i = 0; i < Items; ++i )
-	{
-		const uint32_t r = i * Block + tid;
-		if ( r < valid )
-		{
-			const uint32_t k = s.stage[r];
-			const uint32_t d = ( k >> shift ) & ( Radix - 1 );
-			keysOut[s.digitBaseGlobal[d] + r] = k;
-		}
-	}
-	__syncthreads();
-	// values: same route; the destination is recomputed from the staged key's digit
-	uint32_t destDigit[Items];
-#pragma unroll
-	for ( int i = 0; i < Items; ++i )
-	{
-		const uint32_t r = i * Block + tid;
-		destDigit[i]	 = r < valid ? ( ( s.stage[r] >> shift ) & ( Radix - 1 ) ) : 0;
-	}
-	__syncthreads();
+	// keys and values travel together: staged by local rank as 8-byte pairs, written as runs of one digit
 #pragma unroll
 	for ( int i = 0; i < Items; ++i )
 	{
 		const uint32_t idx = warpBase + i * 32 + lane;
-		s.stage[rank[i]]   = idx < n ? valsIn[idx] : 0u;
+		s.stage[rank[i]]   = make_uint2( key[i], idx < n ? valsIn[idx] : 0u );
 	}
 	__syncthreads();
 #pragma unroll
@@ -242,8 +219,10 @@ __global__ void __launch_bounds__( Block ) onesweepPass(
 		const uint32_t r = i * Block + tid;
 		if ( r < valid )
 		{
-			const uint32_t d = destDigit[i];
-			valsOut[s.digitBaseGlobal[d] + r] = s.stage[r];
+			const uint2	   kv  = s.stage[r];
+			const uint32_t dst = s.digitBaseGlobal[( kv.x >> shift ) & ( Radix - 1 )] + r;
+			keysOut[dst]	   = kv.x;
+			valsOut[dst]	   = kv.y;
 		}
 	}
 }

@@ -11,9 +11,10 @@ namespace hiprt
 // format: hiprtB200HitFormat of the output records (`hits` then points to 48-, 16- or 4-byte records); formats other than the
 // full hiprtHit exist for triangle geometries only
 // qRegion: the geometry's traversal-only Q region (qnode.h) when it has one -- box nodes are then read from its 64-byte records
+// numRaysDevice: optional device word holding the actual ray count (<= numRays, which then is the capacity): triangle geometries only
 void traceGeometry(
 	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, void* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount,
-	cudaStream_t stream, uint32_t format = 0, const void* qRegion = nullptr );
+	cudaStream_t stream, uint32_t format = 0, const void* qRegion = nullptr, const uint32_t* numRaysDevice = nullptr );
 // instrumented variant of the triangle kernel: adds {box-node visits, leaf visits} of the launch to stats[0..1]
 void traceGeometryStats(
 	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, hiprtHit* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream,

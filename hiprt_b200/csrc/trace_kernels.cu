@@ -741,9 +741,12 @@ __device__ __forceinline__ void traceTrianglesWarp(
 template <hiprtTraversalType Type, uint32_t Block, uint32_t SharedDepth, uint32_t BoxQuorum, bool Persistent, uint32_t Refill = 0, uint32_t Format = hiprtB200HitFormatFull, bool Hints = false, bool Stats = false, bool Q = false>
 __global__ void __launch_bounds__( Block, Refill != 0 ? 1024u / Block : 1u ) traceTrianglesKernel(
 	hiprtGeometry geom, const hiprtRay* __restrict__ rays, uint32_t numRays, void* __restrict__ hits, uint32_t* workCounter, unsigned long long* stats,
-	const void* __restrict__ qRegion )
+	const void* __restrict__ qRegion, const uint32_t* __restrict__ numRaysDevice )
 {
 	__shared__ uint32_t sStack[Block * SharedDepth];
+	// indirect launch (hiprtB200TraceGeometryIndirect): the ray count is a device word written by an earlier launch of the stream
+	// (a wavefront's append counter); `numRays` is then the capacity the grid was sized for
+	if ( numRaysDevice != nullptr ) numRays = min( numRays, __ldg( numRaysDevice ) );
 	const GeomHeader*	header					 = reinterpret_cast<const GeomHeader*>( geom );
 	const Box4Node* __restrict__ boxNodes		 = header->boxNodes;
 	const TrianglePairNode* __restrict__ leaves = reinterpret_cast<const TrianglePairNode*>( header->primNodes );
@@ -841,7 +844,7 @@ static void launchGeometry( hiprtGeometry geom, const hiprtRay* rays, uint32_t n
 template <hiprtTraversalType Type, uint32_t Format, bool Hints, bool Stats = false, bool Q = false>
 static void launchTrianglesT(
 	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream, unsigned long long* stats = nullptr,
-	const void* qRegion = nullptr )
+	const void* qRegion = nullptr, const uint32_t* numRaysDevice = nullptr )
 {
 	constexpr uint32_t Block = 128;
 	auto			   kernel = traceTrianglesKernel<Type, Block, 32, 16, true, 8, Format, Hints, Stats, Q>;
@@ -849,7 +852,7 @@ static void launchTrianglesT(
 	if ( blocksPerSm == 0 ) cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSm, kernel, int( Block ), 0 );
 	cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), stream );
 	const uint32_t blocks = std::min( DivideRoundUp( numRays, Block ), smCount * uint32_t( std::max( blocksPerSm, 1 ) ) );
-	kernel<<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits, workCounter, stats, qRegion );
+	kernel<<<blocks, Block, 0, stream>>>( geom, rays, numRays, hits, workCounter, stats, qRegion, numRaysDevice );
 }
 
 // Which queries walk the Q records (qnode.h) when the geometry has them. ncu on the C3 AO rays (profiles/r02_ncu_trace_c3_ao_q.csv):
@@ -861,12 +864,13 @@ static bool useQ( bool any, const void* qRegion ) { return qRegion != nullptr &&
 
 template <uint32_t Format, bool Hints, bool Q = false>
 static void launchTriangles(
-	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, bool any, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream, const void* qRegion = nullptr )
+	hiprtGeometry geom, const hiprtRay* rays, uint32_t numRays, void* hits, bool any, uint32_t* workCounter, uint32_t smCount, cudaStream_t stream, const void* qRegion = nullptr,
+	const uint32_t* numRaysDevice = nullptr )
 {
 	if ( any )
-		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, Format, Hints, false, Q>( geom, rays, numRays, hits, workCounter, smCount, stream, nullptr, qRegion );
+		launchTrianglesT<hiprtTraversalTerminateAtAnyHit, Format, Hints, false, Q>( geom, rays, numRays, hits, workCounter, smCount, stream, nullptr, qRegion, numRaysDevice );
 	else
-		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, Format, Hints, false, Q>( geom, rays, numRays, hits, workCounter, smCount, stream, nullptr, qRegion );
+		launchTrianglesT<hiprtTraversalTerminateAtClosestHit, Format, Hints, false, Q>( geom, rays, numRays, hits, workCounter, smCount, stream, nullptr, qRegion, numRaysDevice );
 }
 
 // Instrumented launch (SURVEY.md 8d "counted by an instrumented build"): the same kernel with per-lane visit counters, summed
@@ -897,9 +901,10 @@ void traceGeometryStats(
 // qRegion: the geometry's Q region when it has one (api.cpp's handle map), else nullptr.
 void traceGeometry(
 	hiprtGeometry geom, bool triangles, const hiprtRay* rays, uint32_t numRays, void* hits, hiprtTraversalType type, uint32_t* workCounter, uint32_t smCount,
-	cudaStream_t stream, uint32_t format, const void* qRegion )
+	cudaStream_t stream, uint32_t format, const void* qRegion, const uint32_t* numRaysDevice )
 {
 	if ( numRays == 0 ) return;
+	if ( numRaysDevice != nullptr && ( !triangles || traceVariant() == 1 ) ) return; // (api.cpp rejects indirect launches on custom-primitive geometries)
 	const bool any = type == hiprtTraversalTerminateAtAnyHit;
 	const int  variant = traceVariant();
 	if ( triangles && ( variant != 1 || format != hiprtB200HitFormatFull ) )
@@ -909,30 +914,30 @@ void traceGeometry(
 		{
 			switch ( format )
 			{
-			case hiprtB200HitFormatCompact: launchTriangles<hiprtB200HitFormatCompact, true, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, qRegion ); return;
-			case hiprtB200HitFormatPrimID: launchTriangles<hiprtB200HitFormatPrimID, true, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, qRegion ); return;
-			default: launchTriangles<hiprtB200HitFormatFull, true, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, qRegion ); return;
+			case hiprtB200HitFormatCompact: launchTriangles<hiprtB200HitFormatCompact, true, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, qRegion, numRaysDevice ); return;
+			case hiprtB200HitFormatPrimID: launchTriangles<hiprtB200HitFormatPrimID, true, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, qRegion, numRaysDevice ); return;
+			default: launchTriangles<hiprtB200HitFormatFull, true, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, qRegion, numRaysDevice ); return;
 			}
 		}
 		switch ( format )
 		{
 		case hiprtB200HitFormatCompact:
 			if ( hints )
-				launchTriangles<hiprtB200HitFormatCompact, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+				launchTriangles<hiprtB200HitFormatCompact, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, nullptr, numRaysDevice );
 			else
-				launchTriangles<hiprtB200HitFormatCompact, false>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+				launchTriangles<hiprtB200HitFormatCompact, false>( geom, rays, numRays, hits, any, workCounter, smCount, stream, nullptr, numRaysDevice );
 			return;
 		case hiprtB200HitFormatPrimID:
 			if ( hints )
-				launchTriangles<hiprtB200HitFormatPrimID, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+				launchTriangles<hiprtB200HitFormatPrimID, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, nullptr, numRaysDevice );
 			else
-				launchTriangles<hiprtB200HitFormatPrimID, false>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+				launchTriangles<hiprtB200HitFormatPrimID, false>( geom, rays, numRays, hits, any, workCounter, smCount, stream, nullptr, numRaysDevice );
 			return;
 		default:
 			if ( hints )
-				launchTriangles<hiprtB200HitFormatFull, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+				launchTriangles<hiprtB200HitFormatFull, true>( geom, rays, numRays, hits, any, workCounter, smCount, stream, nullptr, numRaysDevice );
 			else
-				launchTriangles<hiprtB200HitFormatFull, false>( geom, rays, numRays, hits, any, workCounter, smCount, stream );
+				launchTriangles<hiprtB200HitFormatFull, false>( geom, rays, numRays, hits, any, workCounter, smCount, stream, nullptr, numRaysDevice );
 			return;
 		}
 	}

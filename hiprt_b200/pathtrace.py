@@ -120,59 +120,88 @@ def _launch(fn, n_threads, block, args):
         raise RuntimeError(f"cuLaunchKernel failed: {rc}")
 
 
-def _bounce_kernel(ctx):
-    fn = getattr(ctx, "_pathtrace_bounce", None)
-    if fn is None:
+def _kernels(ctx):
+    """(bounce kernel, camera kernel) of pathtrace_kernels.cu, compiled once per context through hiprtBuildTraceKernels."""
+    fns = getattr(ctx, "_pathtrace_kernels", None)
+    if fns is None:
         from . import api
 
-        names = (C.c_char_p * 1)(b"diffuseBounceKernel")
-        fns = (C.c_void_p * 1)()
+        names = (C.c_char_p * 2)(b"diffuseBounceKernel", b"cameraRaysKernel")
+        out = (C.c_void_p * 2)()
         module = C.c_void_p()
-        ctx._check(api.lib().hiprtBuildTraceKernels(ctx.h, 1, names, open(_BOUNCE_SRC).read().encode(), b"pathtrace_kernels", 0, None, None, 0, None,
-                                                    0, 1, None, fns, C.byref(module), False), "hiprtBuildTraceKernels")
-        fn = ctx._pathtrace_bounce = C.c_void_p(fns[0])
-    return fn
+        ctx._check(api.lib().hiprtBuildTraceKernels(ctx.h, 2, names, open(_BOUNCE_SRC).read().encode(), b"pathtrace_kernels", 0, None, None, 0, None,
+                                                    0, 1, None, out, C.byref(module), False), "hiprtBuildTraceKernels")
+        fns = ctx._pathtrace_kernels = (C.c_void_p(out[0]), C.c_void_p(out[1]))
+    return fns
+
+
+class _Float3(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
+
+
+def _camera_basis(eye, look_at, up=(0.0, 1.0, 0.0), fov_deg=45.0):
+    f64 = np.float64
+    eye_n, look = np.asarray(eye, f64), np.asarray(look_at, f64)
+    w = look - eye_n
+    w /= np.linalg.norm(w)
+    u = np.cross(w, np.asarray(up, f64))
+    u /= np.linalg.norm(u)
+    v = np.cross(u, w)
+    f3 = lambda a: _Float3(*[float(np.float32(x)) for x in a])
+    return f3(eye_n), f3(u), f3(v), f3(w), float(np.tan(np.radians(fov_deg) / 2))
 
 
 def render_fused(ctx, target, pixels, width, height, eye, look_at, spp=4, max_depth=5, albedo=0.7, stats=None):
-    """As render(), with the bounce in one kernel. The order of the rays inside a wavefront (and nothing else) depends on the
-    order in which warps append, so images agree with render() up to float rounding of the bounce math, not bit for bit."""
+    """As render(), as a queue of launches the host never waits for: per sample one camera launch, per bounce one INDIRECT trace
+    launch (hiprtB200TraceGeometryIndirect: the ray count is the device word the previous bounce's append counter left) and one
+    bounce launch. Nothing is read back until the caller looks at the image; stats['rays'] (one read-back at the end) is the sum of
+    the per-launch counts. The order of the rays inside a wavefront (and nothing else) depends on the order in which warps append,
+    so images agree with render() up to float rounding of the bounce math, not bit for bit."""
+    from . import api
+
     torch = ctx.torch
     dev = pixels.device
     n = len(pixels)
-    fn = _bounce_kernel(ctx)
+    bounce, camera = _kernels(ctx)
     radiance = torch.zeros((n, 3), dtype=torch.float32, device=dev)
     rays = [torch.empty((n, 8), dtype=torch.float32, device=dev) for _ in range(2)]
     slots = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
     thr = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
     hits = torch.empty((n, HIT_WORDS), dtype=torch.int32, device=dev)
-    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    counts = torch.zeros(spp * (max_depth + 1), dtype=torch.int32, device=dev)  # live paths before every launch, one word each
     pixels = pixels.contiguous()
-    p = lambda t: C.c_void_p(t.data_ptr())
+    p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+    eye3, u3, v3, w3, half = _camera_basis(eye, look_at)
+    handle = target.h if hasattr(target, "h") else target
+    stream = api._stream_handle(None)
+    timed = stats is not None and stats.get("time_trace")
+    import time as _time
+
+    host0 = _time.perf_counter()
     for s in range(spp):
-        rays[0].copy_(camera_rays(torch, pixels, width, height, eye, look_at, s))
-        slots[0].copy_(torch.arange(n, device=dev, dtype=torch.int32))
-        thr[0].fill_(1.0)
-        count, cur = n, 0
+        k = s * (max_depth + 1)
+        _launch(camera, n, 128, [p(pixels), C.c_uint32(n), C.c_uint32(width), C.c_uint32(height), eye3, u3, v3, w3, C.c_float(half), C.c_uint32(s),
+                                 p(rays[0]), p(slots[0]), p(thr[0]), p(counts, 4 * k)])
+        cur = 0
         for depth in range(max_depth):
-            if count == 0:
-                break
-            if stats is not None and stats.get("time_trace"):
+            if timed:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                ctx.trace(target, rays[cur][:count].view(torch.uint8).reshape(-1, 32), hits[:count])
+            ctx._check(api.lib().hiprtB200TraceGeometryIndirect(ctx.h, handle, p(rays[cur]), n, p(counts, 4 * (k + depth)), p(hits), api.FORMAT_FULL,
+                                                                api.CLOSEST_HIT, stream), "hiprtB200TraceGeometryIndirect")
+            if timed:
                 e1.record()
                 e1.synchronize()
                 stats["trace_ms"] = stats.get("trace_ms", 0.0) + e0.elapsed_time(e1)
                 stats.setdefault("per_depth_ms", [0.0] * max_depth)[depth] += e0.elapsed_time(e1)
-                stats.setdefault("per_depth_rays", [0] * max_depth)[depth] += count
-            else:
-                ctx.trace(target, rays[cur][:count].view(torch.uint8).reshape(-1, 32), hits[:count])
-            if stats is not None:
-                stats["rays"] = stats.get("rays", 0) + count
-            counter.zero_()
             last = int(depth + 1 == max_depth)
-            _launch(fn, count, 128, [p(rays[cur]), p(hits), p(slots[cur]), p(thr[cur]), C.c_uint32(count), p(pixels), C.c_uint32(s), C.c_uint32(depth),
-                                     C.c_float(albedo), C.c_int(last), p(rays[1 - cur]), p(slots[1 - cur]), p(thr[1 - cur]), p(counter), p(radiance)])
-            count, cur = int(counter.item()), 1 - cur
+            _launch(bounce, n, 128, [p(rays[cur]), p(hits), p(slots[cur]), p(thr[cur]), p(counts, 4 * (k + depth)), p(pixels), C.c_uint32(s), C.c_uint32(depth),
+                                     C.c_float(albedo), C.c_int(last), p(rays[1 - cur]), p(slots[1 - cur]), p(thr[1 - cur]), p(counts, 4 * (k + depth + 1)),
+                                     p(radiance)])
+            cur = 1 - cur
+    if stats is not None:
+        stats["host_enqueue_ms"] = stats.get("host_enqueue_ms", 0.0) + (_time.perf_counter() - host0) * 1e3
+        per = counts.view(spp, max_depth + 1)[:, :max_depth].to(torch.int64).sum(0).cpu()
+        stats["rays"] = stats.get("rays", 0) + int(per.sum())
+        stats["per_depth_rays"] = [int(x) for x in per]
     return radiance / spp

@@ -1,6 +1,6 @@
 // Bounce kernel of the wavefront diffuse path tracer (hiprt_b200/pathtrace.py), compiled at run time through
 // hiprtBuildTraceKernels exactly like an application's own kernels (NVRTC, <hiprt/hiprt_device.h> prepended).
-// One thread per live path: a miss adds the sky to the path's pixel slot (one writer per slot and launch, no atomics on
+// One thread per path slot of the wavefront's capacity (the live count is a device word: the host never reads it); per live path: a miss adds the sky to the path's pixel slot (one writer per slot and launch, no atomics on
 // the image), a hit scatters a cosine-distributed ray from the hit point and appends it to the next wavefront.
 #if !defined( __CUDACC_RTC__ ) // offline compile (nvcc -I include): NVRTC gets the header and dispatchers from hiprtBuildTraceKernels
 #define HIPRT_B200_DEFAULT_FUNC_TABLE
@@ -22,7 +22,7 @@ extern "C" __global__ void diffuseBounceKernel(
 	const hiprtHit* __restrict__ hits,
 	const unsigned int* __restrict__ slotIn,
 	const float* __restrict__ throughputIn,
-	unsigned int n,
+	const unsigned int* __restrict__ countIn, // live paths of this wavefront (device word: the previous bounce's append counter)
 	const long long* __restrict__ pixels, // pixel index of every slot
 	unsigned int	 sample,
 	unsigned int	 depth,
@@ -35,7 +35,7 @@ extern "C" __global__ void diffuseBounceKernel(
 	float* __restrict__ radiance ) // [slots][3]
 {
 	const unsigned int i	= blockIdx.x * blockDim.x + threadIdx.x;
-	const bool		   live = i < n;
+	const bool		   live = i < *countIn;
 	bool			   scatter = false;
 	hiprtRay		   next;
 	unsigned int	   slot = 0;
@@ -94,4 +94,30 @@ extern "C" __global__ void diffuseBounceKernel(
 		slotOut[j]			 = slot;
 		throughputOut[j]	 = thr * albedo;
 	}
+}
+
+// Jittered pinhole camera rays of sample `sample` for the pixel list (the torch expression of pathtrace.camera_rays in one launch);
+// also resets the wavefront: slot = identity, throughput = 1, live count = n.
+extern "C" __global__ void cameraRaysKernel(
+	const long long* __restrict__ pixels, unsigned int n, unsigned int width, unsigned int height, float3 eye, float3 u, float3 v, float3 w, float halfTan,
+	unsigned int sample, hiprtRay* __restrict__ raysOut, unsigned int* __restrict__ slotOut, float* __restrict__ throughputOut, unsigned int* __restrict__ countOut )
+{
+	const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if ( i == 0 ) *countOut = n;
+	if ( i >= n ) return;
+	const unsigned long long pix = (unsigned long long)pixels[i];
+	const float px = float( pix % width ), py = float( pix / width );
+	const float jx = hashU01( pix, sample, 0, 1 ), jy = hashU01( pix, sample, 0, 2 );
+	const float sx = ( ( px + jx ) / float( width ) * 2.0f - 1.0f ) * ( halfTan * float( width ) / float( height ) );
+	const float sy = ( 1.0f - ( py + jy ) / float( height ) * 2.0f ) * halfTan;
+	float3		d  = make_float3( sx * u.x + sy * v.x + w.x, sx * u.y + sy * v.y + w.y, sx * u.z + sy * v.z + w.z );
+	const float dl = sqrtf( d.x * d.x + d.y * d.y + d.z * d.z );
+	hiprtRay	ray;
+	ray.origin	  = eye;
+	ray.minT	  = 0.0f;
+	ray.direction = make_float3( d.x / dl, d.y / dl, d.z / dl );
+	ray.maxT	  = 3.0e38f;
+	raysOut[i]		 = ray;
+	slotOut[i]		 = i;
+	throughputOut[i] = 1.0f;
 }

@@ -95,6 +95,22 @@ HIPRT_API hiprtError hiprtB200TraceGeometryFormat(
 	hiprtTraversalType traversalType,
 	hiprtApiStream	   stream );
 
+// Indirect launch for wavefront renderers: the number of rays is read from the DEVICE word *numRaysDevice when the kernel starts
+// (e.g. the append counter a shading kernel earlier on the stream has filled), `maxRays` is the capacity of the buffers. The host
+// never learns the count, so a path tracer's bounces queue up without a read-back per bounce (hiprt_b200/pathtrace.py). Triangle
+// geometries only. (The reference's test renderers launch one thread per pixel and loop over bounces inside the kernel,
+// test/kernels/AoRayKernel.h; a library that takes rays and returns hits needs the count on the device instead.)
+HIPRT_API hiprtError hiprtB200TraceGeometryIndirect(
+	hiprtContext	   context,
+	hiprtGeometry	   geometry,
+	const hiprtRay*	   rays,
+	uint32_t		   maxRays,
+	const uint32_t*	   numRaysDevice,
+	void*			   records,
+	hiprtB200HitFormat format,
+	hiprtTraversalType traversalType,
+	hiprtApiStream	   stream );
+
 HIPRT_API hiprtError hiprtB200TraceGeometryFormatHost(
 	hiprtContext	   context,
 	hiprtGeometry	   geometry,

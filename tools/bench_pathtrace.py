@@ -57,8 +57,8 @@ if rank == 0:
     print(json.dumps({"workload": "c5_pathtrace_terrain", "n_gpus": world, "image": [W, H], "spp": args.spp, "max_depth": args.depth,
                       "rays": int(tsum[2].item()), "render_ms_max_over_ranks": round(float(tmax[0]), 3), "gather_ms": round(float(tmax[1]), 3),
                       "mrays_per_s": round(float(tsum[2]) / float(tmax[0]) / 1e3, 1), "mean_radiance": round(float(full.mean()), 5),
-                      "trace_ms_rank0": round(stats.get("trace_ms", 0.0), 3), "per_depth_ms_rank0": [round(x, 3) for x in stats.get("per_depth_ms", [])],
+                      "trace_ms_rank0": round(stats.get("trace_ms", 0.0), 3), "host_enqueue_ms_rank0": round(stats.get("host_enqueue_ms", 0.0), 3), "per_depth_ms_rank0": [round(x, 3) for x in stats.get("per_depth_ms", [])],
                       "per_depth_rays_rank0": stats.get("per_depth_rays", []),
-                      "note": "wavefront: one trace launch + one bounce launch per bounce (time includes camera-ray generation and the per-bounce counter read-back)"}))
+                      "note": "wavefront: per sample one camera launch, per bounce one indirect trace launch + one bounce launch; the host queues the whole render and never reads a counter back"}))
 if dist is not None:
     dist.destroy_process_group()
