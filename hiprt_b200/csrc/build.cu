@@ -181,6 +181,9 @@ static void runSbvh(
 	P.leaves	  = temp + L.leaves;
 	P.taskQueue	  = taskQueue;
 	P.maxRefs	  = maxRefs;
+	// (read per build, so that a test can force either form of the per-task phases on small inputs)
+	const char* serialMin = getenv( "HIPRT_B200_SBVH_SERIAL_MIN" );
+	P.serialMin			  = serialMin ? uint32_t( atoll( serialMin ) ) : 32768u;
 	static const bool wantTimeline = getenv( "HIPRT_B200_SBVH_TIMELINE" ) != nullptr; // tools/profile_sbvh.py
 	P.timeline	  = wantTimeline ? reinterpret_cast<uint64_t*>( temp + L.timeline ) : nullptr;
 	if ( wantTimeline ) HIPRT_CUDA_CHECK( cudaMemsetAsync( temp + L.timeline, 0, sbvh::TimelineLevels * sbvh::TimelineSlots * sizeof( uint64_t ), stream ) );

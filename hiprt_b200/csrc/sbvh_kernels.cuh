@@ -100,6 +100,7 @@ struct Params
 	void*		   leaves;		// leaf records out
 	uint64_t*	   taskQueue;	// collapse queue: slot 0 receives the root task
 	uint64_t*	   timeline; // optional: %globaltimer after every grid barrier, TimelineSlots values per level (profiling)
+	uint32_t	   serialMin; // levels with at least this many tasks run their per-task phases with one thread per task
 	uint32_t	   maxRefs; // capacity of the reference / node / leaf arrays (sized on the host from the primitive count BEFORE pairing)
 };
 
@@ -541,13 +542,74 @@ __device__ __forceinline__ SplitChoice searchBins(
 	return best;
 }
 
+// The same search by ONE thread (deep levels: millions of tasks with few bins each -- a sub-warp per task spends about 400 warp
+// instructions per task on shuffles there, a thread per task about 20). Suffix unions go to a local array, the bins are read twice (the
+// second time out of L2), four bins in flight per batch. Same candidates in the same order, same arithmetic: the same choice.
+template <bool Spatial>
+__device__ __forceinline__ SplitChoice searchBinsSerial( const float* taskBins, bool active, const DBox& taskBox, float startCost, float edgeThreshold, uint32_t binCount )
+{
+	SplitChoice best;
+	best.cost = startCost, best.key = InvalidValue, best.box0 = emptyBox(), best.box1 = emptyBox(), best.count0 = 0, best.count1 = 0;
+	if ( !active ) return best;
+	float	 suffix[MaxBins][6];
+	uint32_t suffixCount[MaxBins];
+	for ( uint32_t axis = 0; axis < 3; ++axis )
+	{
+		if constexpr ( Spatial )
+			if ( __fsub_rn( axisOf( taskBox, true, axis ), axisOf( taskBox, false, axis ) ) < edgeThreshold ) continue;
+		const float* bins = taskBins + size_t( axis * binCount ) * 8;
+		BinAcc		 acc{ emptyBox(), 0u, 0u };
+		for ( int hi = int( binCount ) - 1; hi >= 1; hi -= 4 ) // bins hi, hi-1, hi-2, hi-3 (down to 1): loads first, unions after
+		{
+			BinAcc b[4];
+#pragma unroll
+			for ( int k = 0; k < 4; ++k )
+				b[k] = hi - k >= 1 ? loadBin( bins + size_t( hi - k ) * 8 ) : BinAcc{ emptyBox(), 0u, 0u };
+#pragma unroll
+			for ( int k = 0; k < 4; ++k )
+			{
+				if ( hi - k < 1 ) break;
+				acc.box = uniteBox( acc.box, b[k].box ), acc.enter += b[k].enter, acc.exit += b[k].exit;
+				float* d = suffix[hi - k];
+				d[0] = acc.box.lo.x, d[1] = acc.box.lo.y, d[2] = acc.box.lo.z, d[3] = acc.box.hi.x, d[4] = acc.box.hi.y, d[5] = acc.box.hi.z;
+				suffixCount[hi - k] = Spatial ? acc.exit : acc.enter;
+			}
+		}
+		BinAcc left{ emptyBox(), 0u, 0u };
+		for ( uint32_t lo = 0; lo + 1u < binCount; lo += 4 )
+		{
+			BinAcc b[4];
+#pragma unroll
+			for ( uint32_t k = 0; k < 4; ++k )
+				b[k] = lo + k + 1u < binCount ? loadBin( bins + size_t( lo + k ) * 8 ) : BinAcc{ emptyBox(), 0u, 0u };
+#pragma unroll
+			for ( uint32_t k = 0; k < 4; ++k )
+			{
+				const uint32_t i = lo + k;
+				if ( i + 1u >= binCount ) break;
+				left.box = uniteBox( left.box, b[k].box ), left.enter += b[k].enter;
+				const uint32_t nl = left.enter, nr = suffixCount[i + 1u];
+				if ( nl > 0u && nr > 0u )
+				{
+					const float* r = suffix[i + 1u];
+					const DBox	 right{ make_float3( r[0], r[1], r[2] ), make_float3( r[3], r[4], r[5] ) };
+					const float	 cost = sahCost( left.box, nl, right, nr );
+					if ( best.cost > cost ) best.cost = cost, best.key = axis * 32u + i, best.box0 = left.box, best.box1 = right, best.count0 = nl, best.count1 = nr;
+				}
+			}
+		}
+	}
+	return best;
+}
+
 // ---- phase: object split of every task ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void findObjectSplitPhase(
 	const Params& P, uint32_t cur, uint32_t level, uint32_t forceLevel, uint32_t taskCount, uint32_t binCount, float overlapThreshold )
 {
 	Task*		   tasks		 = P.tasks[cur];
 	const uint32_t lane			 = laneId();
-	const uint32_t width		 = binCount <= 8u ? 8u : ( binCount <= 16u ? 16u : 32u ); // lanes per task
+	const bool	   serial		 = taskCount >= P.serialMin;										   // one thread per task
+	const uint32_t width		 = serial ? 1u : ( binCount <= 8u ? 8u : ( binCount <= 16u ? 16u : 32u ) ); // lanes per task
 	const uint32_t laneInGroup	 = lane % width, group = lane / width, groupsPerWarp = 32u / width;
 	const uint32_t groupBase	 = group * width;
 	const uint32_t warpsInGrid	 = gridDim.x * ( Block / 32u );
@@ -561,7 +623,9 @@ __device__ __forceinline__ void findObjectSplitPhase(
 		const DBox	   box	  = loadBox6( task->box );
 		const uint32_t count  = __ldcg( &task->count );
 		const bool	   forced = level >= forceLevel;
-		SplitChoice	   c	  = searchBins<false>( P.objectBins + size_t( active ? t : 0u ) * 3u * binCount * 8, active && !forced, box, FltMax, 0.0f, binCount, width, laneInGroup, groupBase );
+		const float*   taskBins = P.objectBins + size_t( active ? t : 0u ) * 3u * binCount * 8;
+		SplitChoice	   c		= serial ? searchBinsSerial<false>( taskBins, active && !forced, box, FltMax, 0.0f, binCount )
+										 : searchBins<false>( taskBins, active && !forced, box, FltMax, 0.0f, binCount, width, laneInGroup, groupBase );
 		uint32_t axis = c.key >> 5, index = c.key & 31u;
 		if ( c.key == InvalidValue )
 		{
@@ -583,7 +647,10 @@ __device__ __forceinline__ void findObjectSplitPhase(
 				task->split = axis | ( trySpatial ? 8u : 0u ) | ( index << 4 );
 				if ( trySpatial ) ++spatialTasks;
 			}
-			if ( trySpatial && laneInGroup < binCount )
+			if ( trySpatial && serial )
+				for ( uint32_t i = 0; i < 3u * binCount; ++i )
+					resetBin( P.spatialBins + ( size_t( t ) * 3u * binCount + i ) * 8 );
+			else if ( trySpatial && laneInGroup < binCount )
 				for ( uint32_t a = 0; a < 3; ++a )
 					resetBin( P.spatialBins + ( size_t( t ) * 3u * binCount + a * binCount + laneInGroup ) * 8 );
 		}
@@ -607,7 +674,8 @@ __device__ __forceinline__ void splitPhase(
 	State*		   state	   = P.state;
 	LevelCounts*   next		   = &state->level[( level + 1u ) & 1u];
 	const uint32_t lane		   = laneId();
-	const uint32_t width	   = binCount <= 8u ? 8u : ( binCount <= 16u ? 16u : 32u ); // lanes per task
+	const bool	   serial	   = taskCount >= P.serialMin;											 // one thread per task
+	const uint32_t width	   = serial ? 1u : ( binCount <= 8u ? 8u : ( binCount <= 16u ? 16u : 32u ) ); // lanes per task
 	const uint32_t laneInGroup = lane % width, group = lane / width, groupsPerWarp = 32u / width;
 	const uint32_t groupBase   = group * width;
 	const uint32_t warpsInGrid = gridDim.x * ( Block / 32u );
@@ -625,7 +693,12 @@ __device__ __forceinline__ void splitPhase(
 		SplitChoice c;
 		c.key = InvalidValue;
 		if ( anySpatial )
-			c = searchBins<true>( P.spatialBins + size_t( active ? t : 0u ) * 3u * binCount * 8, trySpatial, box, trySpatial ? __ldcg( &task->cost ) : 0.0f, edgeThreshold, binCount, width, laneInGroup, groupBase );
+		{
+			const float* taskBins  = P.spatialBins + size_t( active ? t : 0u ) * 3u * binCount * 8;
+			const float	 startCost = trySpatial ? __ldcg( &task->cost ) : 0.0f;
+			c = serial ? searchBinsSerial<true>( taskBins, trySpatial, box, startCost, edgeThreshold, binCount )
+					   : searchBins<true>( taskBins, trySpatial, box, startCost, edgeThreshold, binCount, width, laneInGroup, groupBase );
+		}
 		const bool leader = active && laneInGroup == 0;
 		DBox	   box0 = emptyBox(), box1 = emptyBox();
 		uint32_t   count0 = 0, count1 = 0;
@@ -819,7 +892,7 @@ __device__ __forceinline__ void distributePhase( const Params& P, const Source& 
 
 // ---- the build --------------------------------------------------------------------------------------------------------------------
 template <typename Source>
-__global__ void __launch_bounds__( Block ) buildKernel( Source src, Params P )
+__global__ void __launch_bounds__( Block, 2 ) buildKernel( Source src, Params P )
 {
 	__shared__ __align__( 16 ) float sBins[3 * MaxBins * 8];
 	__shared__ uint32_t				 sWord;

@@ -61,6 +61,21 @@ def test_high_quality_build_equals_the_oracle(ctx, name, spatial):
     geom.destroy()
 
 
+@pytest.mark.parametrize("name", ["sphere", "needles", "soup"])
+def test_per_task_phases_by_single_threads_build_the_same_tree(ctx, name, monkeypatch):
+    """Levels with many tasks run the split search with one thread per task instead of a sub-warp (sbvh_kernels.cuh,
+    searchBinsSerial); HIPRT_B200_SBVH_SERIAL_MIN = 1 forces that form on every level: still the oracle's tree, byte for byte."""
+    monkeypatch.setenv("HIPRT_B200_SBVH_SERIAL_MIN", "1")
+    verts, idx = CASES[name]()
+    geom = ctx.build(to_dev(ctx, verts), None if idx is None else to_dev(ctx, idx), flags=api.HIGH_QUALITY_BUILD)
+    og = orc.Geometry(verts, idx, high_quality=True)
+    assert sbvh_state(geom)["error"] == 0 and int(og.sbvh_stats[3]) == 0
+    boxes, leaves = geom.nodes()
+    cb, cl = orc.canonicalize(boxes.view(orc.BOX4_DTYPE), leaves.view(orc.TRIPAIR_DTYPE))
+    assert cb.tobytes() == og.box_nodes.tobytes() and cl.tobytes() == og.leaves.tobytes()
+    geom.destroy()
+
+
 def test_high_quality_build_of_an_aabb_list_equals_the_oracle(ctx):
     rng = np.random.default_rng(2)
     c = rng.random((3000, 3)).astype(np.float32)

@@ -35,6 +35,7 @@ geoms = ctx.build_geometries(inputs, batch_max=512)
 torch.cuda.synchronize()
 if dist is not None:
     dist.barrier()
+    torch.cuda.synchronize()
 ms = []
 for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

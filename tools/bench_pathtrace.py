@@ -38,6 +38,13 @@ render(ctx, geom, pix, W, H, eye, look, spp=1, max_depth=args.depth)  # warm-up 
 torch.cuda.synchronize()
 if dist is not None:
     dist.barrier()
+    torch.cuda.synchronize()  # (the barrier's own kernel waits for the slowest rank: it must be over before the clock starts)
+if os.environ.get("PT_TWICE"):  # (diagnostic: the first full render after the process group came up may carry one-time costs)
+    render(ctx, geom, pix, W, H, eye, look, spp=args.spp, max_depth=args.depth)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
 stats = {"time_trace": True} if os.environ.get("PT_TIME_TRACE") else {}
 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 e0.record()
@@ -48,7 +55,11 @@ e2.record()
 e2.synchronize()
 ms_render, ms_gather = e0.elapsed_time(e1), e1.elapsed_time(e2)
 t = torch.tensor([ms_render, ms_gather, float(stats["rays"])], dtype=torch.float64, device=ctx.device)
+per_rank = None
 if dist is not None:
+    gathered = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(gathered, t)
+    per_rank = [round(float(g[0]), 3) for g in gathered]
     tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
 else:
@@ -57,7 +68,7 @@ if rank == 0:
     print(json.dumps({"workload": "c5_pathtrace_terrain", "n_gpus": world, "image": [W, H], "spp": args.spp, "max_depth": args.depth,
                       "rays": int(tsum[2].item()), "render_ms_max_over_ranks": round(float(tmax[0]), 3), "gather_ms": round(float(tmax[1]), 3),
                       "mrays_per_s": round(float(tsum[2]) / float(tmax[0]) / 1e3, 1), "mean_radiance": round(float(full.mean()), 5),
-                      "trace_ms_rank0": round(stats.get("trace_ms", 0.0), 3), "host_enqueue_ms_rank0": round(stats.get("host_enqueue_ms", 0.0), 3), "per_depth_ms_rank0": [round(x, 3) for x in stats.get("per_depth_ms", [])],
+                      "render_ms_per_rank": per_rank, "trace_ms_rank0": round(stats.get("trace_ms", 0.0), 3), "host_enqueue_ms_rank0": round(stats.get("host_enqueue_ms", 0.0), 3), "per_depth_ms_rank0": [round(x, 3) for x in stats.get("per_depth_ms", [])],
                       "per_depth_rays_rank0": stats.get("per_depth_rays", []),
                       "note": "wavefront: per sample one camera launch, per bounce one indirect trace launch + one bounce launch; the host queues the whole render and never reads a counter back"}))
 if dist is not None:
