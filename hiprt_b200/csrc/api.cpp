@@ -330,14 +330,23 @@ class Context
 		return geomType & 1u;
 	}
 
-	// ray-batch counters of the persistent trace kernels: a small ring so that launches in flight on different
-	// streams never share one
-	uint32_t* nextWorkCounter()
+	// Ray-batch counter of the persistent trace kernels: ONE 64-byte slot per stream. Launches on one stream run one after the other
+	// (the counter is reset on the stream right before each launch), launches on different streams never share a slot however many
+	// of them are queued -- a wavefront renderer queues hundreds per stream (hiprt_b200/pathtrace.py). (The reference has no
+	// counterpart: its kernels are the caller's, one thread per ray.)
+	uint32_t* workCounterFor( cudaStream_t stream )
 	{
 		std::lock_guard<std::mutex> lock( m_mutex );
-		if ( !m_workCounters ) checkCuda( cudaMalloc( reinterpret_cast<void**>( &m_workCounters ), 64 * 64 ), "cudaMalloc" );
-		m_workCounterNext = ( m_workCounterNext + 1 ) % 64;
-		return m_workCounters + m_workCounterNext * 16;
+		constexpr uint32_t			Slots = 1024;
+		if ( !m_workCounters ) checkCuda( cudaMalloc( reinterpret_cast<void**>( &m_workCounters ), size_t( Slots ) * 64 ), "cudaMalloc" );
+		auto it = m_workCounterOfStream.find( stream );
+		if ( it == m_workCounterOfStream.end() )
+		{
+			// (more streams than slots: the oldest assignments are forgotten; a slot is then shared by two streams only if both are
+			// still in use 1024 streams apart)
+			it = m_workCounterOfStream.emplace( stream, m_workCounterNext++ % Slots ).first;
+		}
+		return m_workCounters + size_t( it->second ) * 16;
 	}
 
   private:
@@ -359,6 +368,7 @@ class Context
 	std::mutex			  m_mutex;
 	uint32_t*			  m_workCounters	= nullptr;
 	uint32_t			  m_workCounterNext = 0;
+	std::unordered_map<cudaStream_t, uint32_t> m_workCounterOfStream;
 };
 
 inline Context* ctx( hiprtContext c ) { return reinterpret_cast<Context*>( c ); }
@@ -1021,7 +1031,7 @@ hiprtError hiprtB200TraceGeometry(
 		const void* q		 = nullptr;
 		const bool	triangles = ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ), &q );
 		traceGeometry(
-			geometry, triangles, rays, numRays, hits, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
+			geometry, triangles, rays, numRays, hits, type, ctx( context )->workCounterFor( static_cast<cudaStream_t>( stream ) ), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
 			hiprtB200HitFormatFull, q );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
@@ -1039,7 +1049,7 @@ hiprtError hiprtB200TraceScene(
 {
 	if ( !context || !scene || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
-		traceScene( scene, rays, numRays, hits, type, mask, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ) );
+		traceScene( scene, rays, numRays, hits, type, mask, ctx( context )->workCounterFor( static_cast<cudaStream_t>( stream ) ), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ) );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
 }
@@ -1059,7 +1069,7 @@ hiprtError hiprtB200TraceSceneAtTime(
 	if ( !context || !scene || ( numRays && ( !rays || !hits ) ) ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
 		traceScene(
-			scene, rays, numRays, hits, type, mask, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ), times,
+			scene, rays, numRays, hits, type, mask, ctx( context )->workCounterFor( static_cast<cudaStream_t>( stream ) ), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ), times,
 			time );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
@@ -1108,7 +1118,7 @@ hiprtError hiprtB200TraceGeometryFormat(
 	if ( !triangles && format != hiprtB200HitFormatFull ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
 		traceGeometry(
-			geometry, triangles, rays, numRays, records, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
+			geometry, triangles, rays, numRays, records, type, ctx( context )->workCounterFor( static_cast<cudaStream_t>( stream ) ), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
 			uint32_t( format ), q );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
@@ -1124,7 +1134,7 @@ hiprtError hiprtB200TraceGeometryIndirect(
 	if ( !triangles ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
 		traceGeometry(
-			geometry, true, rays, maxRays, records, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
+			geometry, true, rays, maxRays, records, type, ctx( context )->workCounterFor( static_cast<cudaStream_t>( stream ) ), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
 			uint32_t( format ), q, numRaysDevice );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );
@@ -1154,7 +1164,7 @@ hiprtError hiprtB200TraceGeometryStats(
 	if ( !ctx( context )->geometryHasTriangles( geometry, static_cast<cudaStream_t>( stream ), &q ) ) return hiprtErrorInvalidParameter;
 	return guarded( context, [&] {
 		traceGeometryStats(
-			geometry, rays, numRays, hits, type, ctx( context )->nextWorkCounter(), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
+			geometry, rays, numRays, hits, type, ctx( context )->workCounterFor( static_cast<cudaStream_t>( stream ) ), ctx( context )->info().smCount, static_cast<cudaStream_t>( stream ),
 			reinterpret_cast<unsigned long long*>( visitCounts ), q );
 		checkCuda( cudaGetLastError(), "trace launch" );
 	} );

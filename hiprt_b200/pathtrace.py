@@ -108,14 +108,14 @@ _BOUNCE_SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pathtrac
 _cuda = None
 
 
-def _launch(fn, n_threads, block, args):
-    """cuLaunchKernel on the current torch stream's context (args: ctypes values)."""
+def _launch(fn, n_threads, block, args, stream=None):
+    """cuLaunchKernel in the current CUDA context on `stream` (a CUstream as c_void_p; None: the default stream). args: ctypes values."""
     global _cuda
     if _cuda is None:
         _cuda = C.CDLL("libcuda.so.1")
         _cuda.cuLaunchKernel.argtypes = [C.c_void_p] + [C.c_uint] * 6 + [C.c_uint, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
     ptrs = (C.c_void_p * len(args))(*[C.cast(C.pointer(a), C.c_void_p) for a in args])
-    rc = _cuda.cuLaunchKernel(fn, (n_threads + block - 1) // block, 1, 1, block, 1, 1, 0, None, ptrs, None)
+    rc = _cuda.cuLaunchKernel(fn, (n_threads + block - 1) // block, 1, 1, block, 1, 1, 0, stream, ptrs, None)
     if rc != 0:
         raise RuntimeError(f"cuLaunchKernel failed: {rc}")
 
@@ -151,24 +151,32 @@ def _camera_basis(eye, look_at, up=(0.0, 1.0, 0.0), fov_deg=45.0):
     return f3(eye_n), f3(u), f3(v), f3(w), float(np.tan(np.radians(fov_deg) / 2))
 
 
-def render_fused(ctx, target, pixels, width, height, eye, look_at, spp=4, max_depth=5, albedo=0.7, stats=None):
-    """As render(), as a queue of launches the host never waits for: per sample one camera launch, per bounce one INDIRECT trace
-    launch (hiprtB200TraceGeometryIndirect: the ray count is the device word the previous bounce's append counter left) and one
-    bounce launch. Nothing is read back until the caller looks at the image; stats['rays'] (one read-back at the end) is the sum of
-    the per-launch counts. The order of the rays inside a wavefront (and nothing else) depends on the order in which warps append,
-    so images agree with render() up to float rounding of the bounce math, not bit for bit."""
+def render_fused(ctx, target, pixels, width, height, eye, look_at, spp=4, max_depth=5, albedo=0.7, stats=None, batch_paths=1 << 25):
+    """As render(), as a queue of launches the host never waits for. Samples are traced in BATCHES: a wavefront holds the paths of
+    `g` samples of every pixel (g * len(pixels) <= batch_paths), because the deep bounces of one sample of a small pixel list are a
+    few thousand long rays and a launch there is bound by its slowest warp, not by its ray count: eight ranks that
+    render an eighth of the image each would pay that tail 64 x 2 times per frame, batched they pay it 4 x 2 times. Per batch one
+    camera launch, per bounce one INDIRECT trace launch (hiprtB200TraceGeometryIndirect: the ray count is the device word the
+    previous bounce's append counter left) and one bounce launch; every (sample-in-batch, pixel) has its own radiance slot, summed
+    at the end, so the image does not depend on the order in which paths finish. Nothing is read back until the caller looks at
+    the image; stats['rays'] (one read-back at the end) is the sum of the per-launch counts. The order of the rays inside a
+    wavefront depends on the order in which warps append, so images agree with render() up to float rounding of the bounce math,
+    not bit for bit."""
     from . import api
 
     torch = ctx.torch
     dev = pixels.device
-    n = len(pixels)
+    n_pix = len(pixels)
     bounce, camera = _kernels(ctx)
-    radiance = torch.zeros((n, 3), dtype=torch.float32, device=dev)
-    rays = [torch.empty((n, 8), dtype=torch.float32, device=dev) for _ in range(2)]
-    slots = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
-    thr = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
-    hits = torch.empty((n, HIT_WORDS), dtype=torch.int32, device=dev)
-    counts = torch.zeros(spp * (max_depth + 1), dtype=torch.int32, device=dev)  # live paths before every launch, one word each
+    g = max(1, min(spp, batch_paths // max(n_pix, 1)))  # samples per batch
+    batches = [(s0, min(g, spp - s0)) for s0 in range(0, spp, g)]
+    cap = g * n_pix
+    radiance = torch.zeros((g, n_pix, 3), dtype=torch.float32, device=dev)
+    rays = [torch.empty((cap, 8), dtype=torch.float32, device=dev) for _ in range(2)]
+    slots = [torch.empty(cap, dtype=torch.int32, device=dev) for _ in range(2)]
+    thr = [torch.empty(cap, dtype=torch.float32, device=dev) for _ in range(2)]
+    hits = torch.empty((cap, HIT_WORDS), dtype=torch.int32, device=dev)
+    counts = torch.zeros(len(batches) * (max_depth + 1), dtype=torch.int32, device=dev)  # live paths before every launch, one word each
     pixels = pixels.contiguous()
     p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
     eye3, u3, v3, w3, half = _camera_basis(eye, look_at)
@@ -178,10 +186,11 @@ def render_fused(ctx, target, pixels, width, height, eye, look_at, spp=4, max_de
     import time as _time
 
     host0 = _time.perf_counter()
-    for s in range(spp):
-        k = s * (max_depth + 1)
-        _launch(camera, n, 128, [p(pixels), C.c_uint32(n), C.c_uint32(width), C.c_uint32(height), eye3, u3, v3, w3, C.c_float(half), C.c_uint32(s),
-                                 p(rays[0]), p(slots[0]), p(thr[0]), p(counts, 4 * k)])
+    for bi, (s0, gs) in enumerate(batches):
+        k = bi * (max_depth + 1)
+        n = gs * n_pix
+        _launch(camera, n, 128, [p(pixels), C.c_uint32(n_pix), C.c_uint32(n), C.c_uint32(width), C.c_uint32(height), eye3, u3, v3, w3, C.c_float(half),
+                                 C.c_uint32(s0), p(rays[0]), p(slots[0]), p(thr[0]), p(counts, 4 * k)], stream)
         cur = 0
         for depth in range(max_depth):
             if timed:
@@ -195,13 +204,14 @@ def render_fused(ctx, target, pixels, width, height, eye, look_at, spp=4, max_de
                 stats["trace_ms"] = stats.get("trace_ms", 0.0) + e0.elapsed_time(e1)
                 stats.setdefault("per_depth_ms", [0.0] * max_depth)[depth] += e0.elapsed_time(e1)
             last = int(depth + 1 == max_depth)
-            _launch(bounce, n, 128, [p(rays[cur]), p(hits), p(slots[cur]), p(thr[cur]), p(counts, 4 * (k + depth)), p(pixels), C.c_uint32(s), C.c_uint32(depth),
-                                     C.c_float(albedo), C.c_int(last), p(rays[1 - cur]), p(slots[1 - cur]), p(thr[1 - cur]), p(counts, 4 * (k + depth + 1)),
-                                     p(radiance)])
+            _launch(bounce, n, 128, [p(rays[cur]), p(hits), p(slots[cur]), p(thr[cur]), p(counts, 4 * (k + depth)), p(pixels), C.c_uint32(n_pix), C.c_uint32(s0),
+                                     C.c_uint32(depth), C.c_float(albedo), C.c_int(last), p(rays[1 - cur]), p(slots[1 - cur]), p(thr[1 - cur]),
+                                     p(counts, 4 * (k + depth + 1)), p(radiance)], stream)
             cur = 1 - cur
     if stats is not None:
         stats["host_enqueue_ms"] = stats.get("host_enqueue_ms", 0.0) + (_time.perf_counter() - host0) * 1e3
-        per = counts.view(spp, max_depth + 1)[:, :max_depth].to(torch.int64).sum(0).cpu()
+        stats["samples_per_batch"] = g
+        per = counts.view(len(batches), max_depth + 1)[:, :max_depth].to(torch.int64).sum(0).cpu()
         stats["rays"] = stats.get("rays", 0) + int(per.sum())
         stats["per_depth_rays"] = [int(x) for x in per]
-    return radiance / spp
+    return radiance.sum(0) / spp

@@ -23,8 +23,9 @@ extern "C" __global__ void diffuseBounceKernel(
 	const unsigned int* __restrict__ slotIn,
 	const float* __restrict__ throughputIn,
 	const unsigned int* __restrict__ countIn, // live paths of this wavefront (device word: the previous bounce's append counter)
-	const long long* __restrict__ pixels, // pixel index of every slot
-	unsigned int	 sample,
+	const long long* __restrict__ pixels, // pixel index of every pixel slot (numPixels of them)
+	unsigned int	 numPixels,			  // a path slot = sample-in-batch * numPixels + pixel slot
+	unsigned int	 sampleBase,		  // first sample of the batch
 	unsigned int	 depth,
 	float			 albedo,
 	int				 lastDepth,
@@ -62,7 +63,8 @@ extern "C" __global__ void diffuseBounceKernel(
 			const float3 p = make_float3(
 				ray.origin.x + ray.direction.x * hit.t + n.x * 1e-4f, ray.origin.y + ray.direction.y * hit.t + n.y * 1e-4f,
 				ray.origin.z + ray.direction.z * hit.t + n.z * 1e-4f );
-			const unsigned long long pix = (unsigned long long)pixels[slot];
+			const unsigned long long pix	= (unsigned long long)pixels[slot % numPixels];
+			const unsigned int		 sample = sampleBase + slot / numPixels;
 			const float u0 = hashU01( pix, sample, depth + 1, 1 ), u1 = hashU01( pix, sample, depth + 1, 2 );
 			const float phi = 6.2831853f * u0, sinT = sqrtf( u1 ), cosT = sqrtf( fmaxf( 1.0f - u1, 0.0f ) );
 			const float3 axis = fabsf( n.x ) > 0.5f ? make_float3( 0.0f, 1.0f, 0.0f ) : make_float3( 1.0f, 0.0f, 0.0f );
@@ -96,16 +98,19 @@ extern "C" __global__ void diffuseBounceKernel(
 	}
 }
 
-// Jittered pinhole camera rays of sample `sample` for the pixel list (the torch expression of pathtrace.camera_rays in one launch);
+// Jittered pinhole camera rays of a BATCH of samples (sampleBase, sampleBase + 1, ...) for the pixel list: path slot i belongs to
+// pixel slot i % numPixels and sample sampleBase + i / numPixels (the torch expression of pathtrace.camera_rays in one launch);
 // also resets the wavefront: slot = identity, throughput = 1, live count = n.
 extern "C" __global__ void cameraRaysKernel(
-	const long long* __restrict__ pixels, unsigned int n, unsigned int width, unsigned int height, float3 eye, float3 u, float3 v, float3 w, float halfTan,
-	unsigned int sample, hiprtRay* __restrict__ raysOut, unsigned int* __restrict__ slotOut, float* __restrict__ throughputOut, unsigned int* __restrict__ countOut )
+	const long long* __restrict__ pixels, unsigned int numPixels, unsigned int n, unsigned int width, unsigned int height, float3 eye, float3 u, float3 v, float3 w,
+	float halfTan, unsigned int sampleBase, hiprtRay* __restrict__ raysOut, unsigned int* __restrict__ slotOut, float* __restrict__ throughputOut,
+	unsigned int* __restrict__ countOut )
 {
 	const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if ( i == 0 ) *countOut = n;
 	if ( i >= n ) return;
-	const unsigned long long pix = (unsigned long long)pixels[i];
+	const unsigned long long pix	= (unsigned long long)pixels[i % numPixels];
+	const unsigned int		 sample = sampleBase + i / numPixels;
 	const float px = float( pix % width ), py = float( pix / width );
 	const float jx = hashU01( pix, sample, 0, 1 ), jy = hashU01( pix, sample, 0, 2 );
 	const float sx = ( ( px + jx ) / float( width ) * 2.0f - 1.0f ) * ( halfTan * float( width ) / float( height ) );

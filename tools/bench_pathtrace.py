@@ -19,6 +19,7 @@ ap.add_argument("--spp", type=int, default=8)
 ap.add_argument("--depth", type=int, default=5)
 ap.add_argument("--terrain", type=int, default=2236)
 ap.add_argument("--torch-bounce", action="store_true", help="bounce math in torch ops instead of the fused NVRTC kernel")
+ap.add_argument("--batch-paths", type=int, default=1 << 25, help="paths per wavefront: samples are traced in batches of batch_paths / pixels")
 args = ap.parse_args()
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 dist = None
@@ -33,8 +34,9 @@ geom = ctx.build(torch.from_numpy(verts).to(ctx.device), torch.from_numpy(idx.vi
 W = H = args.size
 pix = torch.from_numpy(multi_gpu.pixels_of_rank(W, H, rank, world, tile=64)).to(ctx.device)
 eye, look = (0.5, 0.6, -0.6), (0.5, 0.0, 0.5)
-render = pathtrace.render if args.torch_bounce else pathtrace.render_fused
-render(ctx, geom, pix, W, H, eye, look, spp=1, max_depth=args.depth)  # warm-up at full size: NVRTC compile, allocator growth
+import functools
+render = pathtrace.render if args.torch_bounce else functools.partial(pathtrace.render_fused, batch_paths=args.batch_paths)
+render(ctx, geom, pix, W, H, eye, look, spp=args.spp, max_depth=args.depth)  # warm-up = the whole render once: NVRTC compile, allocator growth
 torch.cuda.synchronize()
 if dist is not None:
     dist.barrier()
@@ -65,11 +67,11 @@ if dist is not None:
 else:
     tmax = tsum = t
 if rank == 0:
-    print(json.dumps({"workload": "c5_pathtrace_terrain", "n_gpus": world, "image": [W, H], "spp": args.spp, "max_depth": args.depth,
+    print(json.dumps({"workload": "c5_pathtrace_terrain", "n_gpus": world, "image": [W, H], "spp": args.spp, "max_depth": args.depth, "samples_per_batch": stats.get("samples_per_batch"),
                       "rays": int(tsum[2].item()), "render_ms_max_over_ranks": round(float(tmax[0]), 3), "gather_ms": round(float(tmax[1]), 3),
                       "mrays_per_s": round(float(tsum[2]) / float(tmax[0]) / 1e3, 1), "mean_radiance": round(float(full.mean()), 5),
                       "render_ms_per_rank": per_rank, "trace_ms_rank0": round(stats.get("trace_ms", 0.0), 3), "host_enqueue_ms_rank0": round(stats.get("host_enqueue_ms", 0.0), 3), "per_depth_ms_rank0": [round(x, 3) for x in stats.get("per_depth_ms", [])],
                       "per_depth_rays_rank0": stats.get("per_depth_rays", []),
-                      "note": "wavefront: per sample one camera launch, per bounce one indirect trace launch + one bounce launch; the host queues the whole render and never reads a counter back"}))
+                      "note": "wavefront over batches of samples: per batch one camera launch, per bounce one indirect trace launch + one bounce launch; the host queues the whole render and never reads a counter back"}))
 if dist is not None:
     dist.destroy_process_group()
