@@ -36,6 +36,7 @@ constexpr uint32_t MaxBins = 32; // BvhConfig.h:47
 constexpr float	   Beta	   = 1.0e-4f; // overlap of the object split's children, relative to the scene area, that makes a task try spatial splits
 constexpr float	   Gamma   = 1.0e-3f; // axes shorter than this fraction of the scene extent are not split spatially
 constexpr float	   Epsilon = 1.0e-2f; // centroid bins are scaled by (1 - Epsilon)
+constexpr uint32_t SmallTask = 4; // on thread-per-task levels, tasks of at most this many references are split straight from their references
 constexpr uint32_t TimelineSlots  = 8;	// per level: start, reset, object bins, object split, spatial bins, demand, split, distribute
 constexpr uint32_t TimelineLevels = 128;
 
@@ -312,11 +313,15 @@ __device__ __forceinline__ bool gridBarrier( State* state, uint32_t& epoch )
 __device__ __forceinline__ Rec32 loadRecL2( const void* base, size_t index ) { return loadRecCg( base, index ); }
 
 // ---- phase: reset the object bins of the level ----------------------------------------------------------------------------------
-__device__ __forceinline__ void resetBinsPhase( const Params& P, uint32_t taskCount, uint32_t bins )
+__device__ __forceinline__ void resetBinsPhase( const Params& P, uint32_t cur, uint32_t taskCount, uint32_t bins, bool serial )
 {
 	const uint32_t total = taskCount * 3u * bins;
 	for ( uint32_t i = blockIdx.x * Block + threadIdx.x; i < total; i += gridDim.x * Block )
+	{
+		// (small tasks of a thread-per-task level never touch their bins: findObjectSplitPhase)
+		if ( serial && __ldcg( &P.tasks[cur][i / ( 3u * bins )].count ) <= SmallTask ) continue;
 		resetBin( P.objectBins + size_t( i ) * 8 );
+	}
 }
 
 // ---- phases over references: a CTA walks a contiguous span, 256 references at a time; while the span stays inside one task the
@@ -393,7 +398,7 @@ __device__ __forceinline__ void flushBins( const float* sBins, float* taskBins, 
 
 template <typename Source, bool Spatial>
 __device__ __forceinline__ void binPhase(
-	const Params& P, const Source& src, uint32_t cur, uint32_t refCount, uint32_t binCount, float edgeThreshold, float* sBins, uint32_t* sWord )
+	const Params& P, const Source& src, uint32_t cur, uint32_t refCount, uint32_t binCount, float edgeThreshold, float* sBins, uint32_t* sWord, bool serial )
 {
 	const void*		refs	 = P.refs[cur];
 	const uint32_t* refTask	 = P.refTask[cur];
@@ -421,7 +426,10 @@ __device__ __forceinline__ void binPhase(
 		if ( valid )
 		{
 			bool wanted = true;
-			if constexpr ( Spatial ) wanted = ( __ldcg( &tasks[task].split ) & 8u ) != 0u;
+			if constexpr ( Spatial )
+				wanted = ( __ldcg( &tasks[task].split ) & 8u ) != 0u;
+			else
+				wanted = !( serial && __ldcg( &tasks[task].count ) <= SmallTask ); // (split straight from the references)
 			if ( wanted )
 			{
 				const Rec32 ref		= loadRecL2( refs, index );
@@ -602,6 +610,54 @@ __device__ __forceinline__ SplitChoice searchBinsSerial( const float* taskBins, 
 	return best;
 }
 
+// A task of at most SmallTask references, split straight from its references (a contiguous segment of the reference buffer): the
+// bins would hold at most four boxes in a kilobyte. Same candidates as the binned search -- the planes right above a reference's
+// centroid bin, except the highest -- same costs; among equal costs the lowest (axis, bin) wins, as in the ordered scan.
+// Also returns the smallest first word of the references (what the binning phase collects for two-reference tasks).
+__device__ __forceinline__ SplitChoice searchSmallTask( const void* refs, uint32_t begin, uint32_t count, const DBox& taskBox, uint32_t binCount, uint32_t& minWord )
+{
+	SplitChoice best;
+	best.cost = FltMax, best.key = InvalidValue, best.box0 = emptyBox(), best.box1 = emptyBox(), best.count0 = 0, best.count1 = 0;
+	DBox	 box[SmallTask];
+	uint32_t bin[SmallTask][3];
+	minWord = InvalidValue;
+#pragma unroll
+	for ( uint32_t r = 0; r < SmallTask; ++r )
+	{
+		if ( r >= count ) break;
+		const Rec32 ref = loadRecCg( refs, begin + r );
+		box[r]			= ref.box;
+		minWord			= min( minWord, ref.a );
+		bin[r][0]		= centroidBin( ref.box.lo.x, ref.box.hi.x, taskBox.lo.x, taskBox.hi.x, binCount );
+		bin[r][1]		= centroidBin( ref.box.lo.y, ref.box.hi.y, taskBox.lo.y, taskBox.hi.y, binCount );
+		bin[r][2]		= centroidBin( ref.box.lo.z, ref.box.hi.z, taskBox.lo.z, taskBox.hi.z, binCount );
+	}
+#pragma unroll
+	for ( uint32_t axis = 0; axis < 3; ++axis )
+#pragma unroll
+		for ( uint32_t c = 0; c < SmallTask; ++c )
+		{
+			if ( c >= count ) break;
+			const uint32_t plane = bin[c][axis];
+			DBox		   l = emptyBox(), r = emptyBox();
+			uint32_t	   nl = 0, nr = 0;
+#pragma unroll
+			for ( uint32_t k = 0; k < SmallTask; ++k )
+			{
+				if ( k >= count ) break;
+				if ( bin[k][axis] <= plane )
+					l = uniteBox( l, box[k] ), ++nl;
+				else
+					r = uniteBox( r, box[k] ), ++nr;
+			}
+			if ( nr == 0u ) continue; // the highest bin: no plane above it separates anything
+			const float	   cost = sahCost( l, nl, r, nr );
+			const uint32_t key	= axis * 32u + plane;
+			if ( cost < best.cost || ( cost == best.cost && key < best.key ) ) best.cost = cost, best.key = key, best.box0 = l, best.box1 = r, best.count0 = nl, best.count1 = nr;
+		}
+	return best;
+}
+
 // ---- phase: object split of every task ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void findObjectSplitPhase(
 	const Params& P, uint32_t cur, uint32_t level, uint32_t forceLevel, uint32_t taskCount, uint32_t binCount, float overlapThreshold )
@@ -624,8 +680,18 @@ __device__ __forceinline__ void findObjectSplitPhase(
 		const uint32_t count  = __ldcg( &task->count );
 		const bool	   forced = level >= forceLevel;
 		const float*   taskBins = P.objectBins + size_t( active ? t : 0u ) * 3u * binCount * 8;
-		SplitChoice	   c		= serial ? searchBinsSerial<false>( taskBins, active && !forced, box, FltMax, 0.0f, binCount )
-										 : searchBins<false>( taskBins, active && !forced, box, FltMax, 0.0f, binCount, width, laneInGroup, groupBase );
+		const bool	   small	= serial && active && count <= SmallTask;
+		SplitChoice	   c;
+		if ( small )
+		{
+			uint32_t minWord;
+			c = searchSmallTask( P.refs[cur], __ldcg( &task->cursor0 ), count, box, binCount, minWord );
+			if ( forced ) c.key = InvalidValue;
+			if ( count == 2u ) task->out0 = minWord;
+		}
+		else
+			c = serial ? searchBinsSerial<false>( taskBins, active && !forced, box, FltMax, 0.0f, binCount )
+					   : searchBins<false>( taskBins, active && !forced, box, FltMax, 0.0f, binCount, width, laneInGroup, groupBase );
 		uint32_t axis = c.key >> 5, index = c.key & 31u;
 		if ( c.key == InvalidValue )
 		{
@@ -781,6 +847,7 @@ __device__ __forceinline__ void splitPhase(
 				Task* c2	   = nextTasks + nt;
 				storeBox6( c2->box, side ? box1 : box0 );
 				c2->count = n, c2->node = node, c2->split = 0u, c2->out0 = InvalidValue;
+				c2->cursor0 = out[side]; // (until the split phase: first reference of the task in the next buffer)
 			}
 			else
 			{
@@ -922,7 +989,7 @@ __global__ void __launch_bounds__( Block, 2 ) buildKernel( Source src, Params P 
 	{
 		Task* root = P.tasks[0];
 		storeBox6( root->box, sceneBox );
-		root->count = n, root->node = 0u, root->split = 0u, root->out0 = InvalidValue;
+		root->count = n, root->node = 0u, root->split = 0u, root->out0 = InvalidValue, root->cursor0 = 0u;
 		state->level[0] = LevelCounts{ 1u, n, 0u, 0u };
 		state->level[1] = LevelCounts{ 0u, 0u, 0u, 0u };
 		state->totalRefs = n, state->leafCount = 0u, state->nodeCount = 1u;
@@ -956,12 +1023,13 @@ __global__ void __launch_bounds__( Block, 2 ) buildKernel( Source src, Params P 
 		const uint32_t remaining = budget - min( ldVolatile( &state->totalRefs ), budget ); // (changes in the split phase only)
 		stamp( 0 );
 
-		resetBinsPhase( P, taskCount, binCount );
+		const bool serial = taskCount >= P.serialMin; // one thread per task in the per-task phases
+		resetBinsPhase( P, cur, taskCount, binCount, serial );
 		if ( blockIdx.x == 0 && threadIdx.x == 0 ) state->level[cur ^ 1u] = LevelCounts{ 0u, 0u, 0u, 0u };
 		HIPRT_SBVH_BARRIER();
 		stamp( 1 );
 
-		binPhase<Source, false>( P, src, cur, refCount, binCount, edgeThreshold, sBins, &sWord );
+		binPhase<Source, false>( P, src, cur, refCount, binCount, edgeThreshold, sBins, &sWord, serial );
 		HIPRT_SBVH_BARRIER();
 		stamp( 2 );
 
@@ -972,7 +1040,7 @@ __global__ void __launch_bounds__( Block, 2 ) buildKernel( Source src, Params P 
 		const uint32_t spatialTasks = ldVolatile( &state->level[cur].spatialTasks );
 		if ( spatialTasks != 0u )
 		{
-			binPhase<Source, true>( P, src, cur, refCount, binCount, edgeThreshold, sBins, &sWord );
+			binPhase<Source, true>( P, src, cur, refCount, binCount, edgeThreshold, sBins, &sWord, serial );
 			HIPRT_SBVH_BARRIER();
 		}
 		stamp( 4 );

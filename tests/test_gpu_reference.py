@@ -106,7 +106,9 @@ def test_scene_hits_match_reference(ctx):
     geoms = [ctx.build(to_dev(ctx, v), to_dev(ctx, i)) for v, i in meshes]
     scene = ctx.build_scene([geoms[g] for g in geom_of], frames)
     ours = ctx.hits_to_host(ctx.trace(scene, ctx.rays_to_device(rays)))
-    ties = compare_hits(ours, theirs, rel=5e-5, uv_tol=1e-3)  # see tests/test_gpu_scene.py SCENE_UV_TOL
+    # north_star's bar for t (1e-5 relative) holds against the reference with ITS OWN matrices: measured worst case 3.0e-6
+    # (profiles/r02_scene_vs_reference.txt); barycentrics of grazing hits differ by up to 2.3e-4 absolute (tests/test_gpu_scene.py SCENE_UV_TOL)
+    ties = compare_hits(ours, theirs, rel=1e-5, uv_tol=1e-3)
     hit = (ours["primID"] == theirs["primID"]) & (theirs["primID"] != api.INVALID)
     # the measured worst case against the reference with ITS OWN matrices (printed for the record: pytest -s)
     dt = np.abs(ours["t"][hit] - theirs["t"][hit]) / np.maximum(np.abs(theirs["t"][hit]), 1e-20)
@@ -118,6 +120,6 @@ def test_scene_hits_match_reference(ctx):
     assert ties <= 0.002 * len(rays)
     # their traversal on our scene (instance nodes point at our geometries)
     cross, _ = ref.trace_scene(scene.h, rays, kind=2)
-    compare_hits(cross, theirs, rel=5e-5, uv_tol=1e-3)
+    compare_hits(cross, theirs, rel=1e-5, uv_tol=1e-3)
     rs.destroy()
     scene.destroy()

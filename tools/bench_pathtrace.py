@@ -36,7 +36,9 @@ pix = torch.from_numpy(multi_gpu.pixels_of_rank(W, H, rank, world, tile=64)).to(
 eye, look = (0.5, 0.6, -0.6), (0.5, 0.0, 0.5)
 import functools
 render = pathtrace.render if args.torch_bounce else functools.partial(pathtrace.render_fused, batch_paths=args.batch_paths)
-render(ctx, geom, pix, W, H, eye, look, spp=args.spp, max_depth=args.depth)  # warm-up = the whole render once: NVRTC compile, allocator growth
+warm = render(ctx, geom, pix, W, H, eye, look, spp=args.spp, max_depth=args.depth)  # warm-up = the whole render once: NVRTC compile, allocator growth
+multi_gpu.gather_framebuffer(warm, W, H, rank, world, tile=64, dist=dist)  # ... and the gather once (NCCL sets up its peer channels lazily)
+del warm
 torch.cuda.synchronize()
 if dist is not None:
     dist.barrier()
