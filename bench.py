@@ -610,6 +610,30 @@ def main():
                     line["hiprt_reference_gpu"] = {"unavailable": "oracle/_ref is not built (make -C oracle/ref needs /root/reference)"}
             except Exception as e:  # the reference is optional infrastructure
                 line["hiprt_reference_gpu"] = {"unavailable": str(e)[:200]}
+        if world == 1:
+            # (untimed side figure, N = 1) the third builder of the API on the same mesh: PreferHighQualityBuild = SBVH, and the
+            # reference's own SBVH when oracle/_ref is there (tools/bench_sbvh.py compares the trees as well)
+            try:
+                hq = ctx.build(d_verts, d_idx, flags=api.HIGH_QUALITY_BUILD)
+                best = 1e30
+                for _ in range(3):
+                    e0, e1 = ev(), ev()
+                    e0.record(); ctx.build_geometry(hq.inp, hq.h, hq.temp, api.HIGH_QUALITY_BUILD); e1.record(); e1.synchronize()
+                    best = min(best, e0.elapsed_time(e1))
+                line["build"]["high_quality"] = {"ms_per_build": round(best, 3), "mtris_per_s": round(n_tris / best / 1e3, 1),
+                                                 "leaves": int(hq.header()["primNodeCount"]), "builder": "SBVH: binned SAH + spatial splits, one cooperative launch"}
+                hq.destroy()
+                del hq
+                ref_line = line.get("hiprt_reference_gpu", {})
+                if "unavailable" not in ref_line and not args.no_hiprt_reference:
+                    from oracle import ref_binding as ref
+
+                    rg = ref.RefGeometry(verts, idx, build_flags=api.HIGH_QUALITY_BUILD, reps=2)
+                    ref_line["high_quality_build_ms"] = round(rg.build_ms, 3)
+                    ref_line["high_quality_build_ratio"] = round(rg.build_ms / best, 2)
+                    rg.destroy()
+            except Exception as e:
+                line["build"]["high_quality"] = {"unavailable": str(e)[:200]}
         print(json.dumps(line))
     fr.close()
     if world > 1:

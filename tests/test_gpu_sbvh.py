@@ -173,3 +173,51 @@ def test_large_high_quality_build(ctx, name):
     hit = same & (a["primID"] != api.INVALID)
     assert hit.mean() > 0.05 and np.array_equal(a["t"][hit], b["t"][hit]) and np.array_equal(a["uv"][hit], b["uv"][hit])
     fast.destroy(), hq.destroy()
+
+
+def test_degenerate_inputs_terminate_and_stay_valid(ctx):
+    """Inputs no plane can separate (1000 copies of one triangle: every split is by arrival, down to the depth bound), tiny
+    geometries, zero-area triangles: the build ends, the tree is valid, rays find what the LBVH build finds."""
+    one = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    cases = {
+        "copies": np.tile(one, (1000, 1)),
+        "two": np.concatenate([one, one + np.float32(2)]),
+        "three": np.concatenate([one, one + np.float32(2), one * np.float32(0.5) - np.float32(1)]),
+        "points": np.repeat(np.random.default_rng(3).random((500, 1, 3)).astype(np.float32), 3, axis=1).reshape(-1, 3),  # zero-area triangles
+        "line": np.stack([np.linspace(0, 1, 900, dtype=np.float32), np.zeros(900, np.float32), np.zeros(900, np.float32)], 1),  # collinear
+    }
+    for name, verts in cases.items():
+        verts = np.ascontiguousarray(verts, np.float32)
+        hq = ctx.build(to_dev(ctx, verts), None, flags=api.HIGH_QUALITY_BUILD)
+        st = sbvh_state(hq)
+        assert st["error"] == 0 and hq.build_error_flag() == 0, (name, st)
+        boxes, leaves = hq.nodes()
+        H.validate_wide_bvh(boxes, leaves, len(verts) // 3, duplicated_references=True)
+        fast = ctx.build(to_dev(ctx, verts), None)
+        lo, hi = verts.min(0) - 0.5, verts.max(0) + 0.5
+        d_rays = ctx.rays_to_device(scenes.random_rays(20000, lo, hi, seed=1))
+        a, b = ctx.hits_to_host(ctx.trace(fast, d_rays)), ctx.hits_to_host(ctx.trace(hq, d_rays))
+        assert np.array_equal(a["t"][a["primID"] != api.INVALID], b["t"][b["primID"] != api.INVALID]), name
+        assert np.array_equal(a["primID"] != api.INVALID, b["primID"] != api.INVALID), name
+        fast.destroy(), hq.destroy()
+
+
+def test_several_high_quality_geometries_in_one_call_and_given_pairs(ctx):
+    meshes = [scenes.sphere_mesh(40, 20), scenes.terrain_mesh(30), (scenes.random_soup(1500, seed=2), None)]
+    inputs = [ctx.mesh_input(to_dev(ctx, v), None if i is None else to_dev(ctx, i)) for v, i in meshes]
+    geoms = ctx.build_geometries(inputs, flags=api.HIGH_QUALITY_BUILD, batch_max=0)  # no batch builder: three SBVH builds, one temporary buffer
+    for (v, i), g in zip(meshes, geoms):
+        og = orc.Geometry(v, i, high_quality=True)
+        boxes, leaves = g.nodes()
+        cb, cl = orc.canonicalize(boxes.view(orc.BOX4_DTYPE), leaves.view(orc.TRIPAIR_DTYPE))
+        assert cb.tobytes() == og.box_nodes.tobytes() and cl.tobytes() == og.leaves.tobytes()
+    ctx.destroy_geometries(geoms)
+    # pairs given by the caller (hiprtTriangleMeshPrimitive::trianglePairIndices)
+    verts, idx = scenes.sphere_mesh(40, 20)
+    pairs = orc.Geometry(verts, idx).pairs
+    g = ctx.build(to_dev(ctx, verts), to_dev(ctx, idx), flags=api.HIGH_QUALITY_BUILD, pairs=to_dev(ctx, pairs))
+    og = orc.Geometry(verts, idx, pairs=pairs, high_quality=True)
+    boxes, leaves = g.nodes()
+    cb, cl = orc.canonicalize(boxes.view(orc.BOX4_DTYPE), leaves.view(orc.TRIPAIR_DTYPE))
+    assert cb.tobytes() == og.box_nodes.tobytes() and cl.tobytes() == og.leaves.tobytes()
+    g.destroy()

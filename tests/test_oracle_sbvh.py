@@ -92,3 +92,12 @@ def test_high_quality_cornell_box_matches_reference_image():
     a = orc.Geometry(verts, idx).trace(H.cornell_rays(), tie_mode=1)
     b = orc.Geometry(verts, idx, high_quality=True).trace(H.cornell_rays(), tie_mode=1)
     assert np.array_equal(a["primID"], b["primID"]) and np.array_equal(a["t"], b["t"])
+
+
+def test_inputs_no_plane_separates_terminate():
+    one = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    verts = np.ascontiguousarray(np.tile(one, (300, 1)))
+    g = orc.Geometry(verts, None, high_quality=True)
+    levels, refs, _, unordered, inconsistent = (int(x) for x in g.sbvh_stats)
+    assert inconsistent == 0 and unordered > 0 and 300 <= refs <= 450 and levels < 80  # (the copies overlap entirely: spatial splits are tried too)
+    H.validate_wide_bvh(g.box_nodes, g.leaves, 300, duplicated_references=True)
