@@ -50,24 +50,52 @@ def split_batch(count, rank, world):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def _untile(tiles, width, height, tile):
+    """[tiles, tile * tile, ...] in row-major tile order -> the row-major image [width * height, ...]: two views and one copy on
+    the device, no index tensor (full tiles only)."""
+    tx, ty = width // tile, height // tile
+    rest = tuple(tiles.shape[2:])
+    t = tiles.reshape((ty, tx, tile, tile) + rest)
+    dims = (0, 2, 1, 3) + tuple(range(4, 4 + len(rest)))
+    return t.permute(*dims).reshape((width * height,) + rest)
+
+
 def gather_framebuffer(local_values, width, height, rank, world, tile=64, dist=None, dst=0):
     """Gather per-pixel values rendered by each rank (in pixels_of_rank order; any trailing shape/dtype torch supports)
-    into the full row-major image on rank `dst`. Returns the image there, None elsewhere."""
+    into the full row-major image on rank `dst`. Returns the image there, None elsewhere.
+    When the tiles are full and deal out evenly (the usual case: 4096 x 4096 in 64 x 64 tiles on 1 / 2 / 4 / 8 ranks) the
+    image is assembled from the gathered buffers by reshapes on the device: rank r's k-th tile is tile k * world + r.
+    Otherwise (ragged borders, uneven deal) through index tensors."""
     import torch
 
+    tx, ty = tile_grid(width, height, tile)
+    even = width % tile == 0 and height % tile == 0 and (tx * ty) % world == 0
+    rest = tuple(local_values.shape[1:])
     if world == 1:
-        out = torch.empty((width * height,) + tuple(local_values.shape[1:]), dtype=local_values.dtype, device=local_values.device)
+        if even:
+            return _untile(local_values.reshape((tx * ty, tile * tile) + rest), width, height, tile)
+        out = torch.empty((width * height,) + rest, dtype=local_values.dtype, device=local_values.device)
         out[torch.from_numpy(pixels_of_rank(width, height, 0, 1, tile)).to(local_values.device)] = local_values
         return out
+    if even:
+        local_values = local_values.contiguous()
+        bufs = [torch.empty_like(local_values) for _ in range(world)] if rank == dst else None
+        dist.gather(local_values, bufs, dst=dst)
+        if rank != dst:
+            return None
+        per_rank = (tx * ty) // world
+        stacked = torch.stack(bufs).reshape((world, per_rank, tile * tile) + rest)  # [rank, k, pixel-in-tile, ...]
+        tiles = stacked.transpose(0, 1).reshape((tx * ty, tile * tile) + rest)     # tile index = k * world + rank
+        return _untile(tiles, width, height, tile)
     counts = [len(pixels_of_rank(width, height, r, world, tile)) for r in range(world)]
     most = max(counts)
-    padded = torch.zeros((most,) + tuple(local_values.shape[1:]), dtype=local_values.dtype, device=local_values.device)
+    padded = torch.zeros((most,) + rest, dtype=local_values.dtype, device=local_values.device)
     padded[: len(local_values)] = local_values
     bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
     dist.gather(padded, bufs, dst=dst)
     if rank != dst:
         return None
-    out = torch.empty((width * height,) + tuple(local_values.shape[1:]), dtype=local_values.dtype, device=local_values.device)
+    out = torch.empty((width * height,) + rest, dtype=local_values.dtype, device=local_values.device)
     for r in range(world):
         idx = torch.from_numpy(pixels_of_rank(width, height, r, world, tile)).to(local_values.device)
         out[idx] = bufs[r][: counts[r]]

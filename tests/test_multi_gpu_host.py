@@ -53,9 +53,9 @@ def _worker(rank, world, port, w, h, tile, out_path):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_framebuffer_gather_gloo(world, tmp_path):
-    w, h, tile = 200, 136, 32
+@pytest.mark.parametrize("world, w, h, tile", [(2, 200, 136, 32), (3, 200, 136, 32), (2, 256, 128, 32), (4, 256, 128, 32)])
+def test_framebuffer_gather_gloo(world, w, h, tile, tmp_path):
+    # (ragged borders / an uneven deal go through index tensors, full tiles dealt evenly through reshapes on the device)
     out = str(tmp_path / "img.npy")
     mp.spawn(_worker, args=(world, _free_port(), w, h, tile, out), nprocs=world, join=True)
     img = np.load(out)
