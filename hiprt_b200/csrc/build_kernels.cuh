@@ -582,6 +582,13 @@ __global__ void __launch_bounds__( Block ) hplocKernel(
 			if ( count > threshold && lane < count )
 				box = ( isBoxIndex( id ) ? loadRecCg( scratch, nodeAddr( id ) ) : loadRecCg( sortedRefs, nodeAddr( id ) ) ).box;
 
+			// The rounds below leave exactly `threshold` clusters (the last round merges no more pairs than that takes: what it drops
+			// is found again one level up), so the nodes of all rounds are allocated with ONE atomic on the grid-wide counter, issued
+			// before the first round's neighbour search; one atomic per round had its round trip through L2 in every round's
+			// dependency chain.
+			uint32_t nodeBase = 0;
+			if ( lane == 0 && count > threshold ) nodeBase = atomicAdd( nodeCounter, count - threshold );
+			nodeBase = __shfl_sync( FullMask, nodeBase, 0 );
 			while ( count > threshold )
 			{
 				// nearest neighbour within PlocRadius positions, both directions
@@ -603,14 +610,16 @@ __global__ void __launch_bounds__( Block ) hplocKernel(
 				const uint32_t nbLane = has ? ( pa == lane ? pb : pa ) : lane;
 				const uint64_t nbBest = shflU64( best, nbLane );
 				const bool	   mutual = has && nbBest == best;
-				const bool	   merging = mutual && lane < nbLane; // the lower position keeps the merged cluster
-				const bool	   dropped = mutual && lane > nbLane;
+				// the lower position keeps the merged cluster; only as many pairs as still separate the window from `threshold`
+				uint32_t	   mmask   = __ballot_sync( FullMask, mutual && lane < nbLane );
+				const uint32_t allowed = count - threshold;
+				if ( uint32_t( __popc( mmask ) ) > allowed ) mmask &= ( 1u << __fns( mmask, 0, allowed + 1 ) ) - 1u; // the lowest `allowed` of them
+				const bool	   merging = ( ( mmask >> lane ) & 1u ) != 0u;
+				const bool	   dropped = mutual && lane > nbLane && ( ( mmask >> nbLane ) & 1u ) != 0u;
 				const uint32_t nbId	   = __shfl_sync( FullMask, id, nbLane );
 				const DBox	   nbBox   = shflBox( box, nbLane );
-				const uint32_t mmask   = __ballot_sync( FullMask, merging );
-				uint32_t	   base	   = 0;
-				if ( lane == 0 ) base = atomicAdd( nodeCounter, __popc( mmask ) );
-				base = __shfl_sync( FullMask, base, 0 );
+				const uint32_t base	   = nodeBase;
+				nodeBase += __popc( mmask );
 				if ( merging )
 				{
 					const uint32_t addr = n - 2u - ( base + __popc( mmask & laneMaskLt() ) );
