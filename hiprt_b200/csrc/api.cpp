@@ -671,7 +671,7 @@ hiprtError hiprtCreateScenes(
 		{
 			// instance ids are 24 bits wide (reference: Context.cpp:366-373)
 			if ( buildInputs[i].instanceCount >= ( 1u << InstanceIDBits ) ) throw std::runtime_error( "too many instances (24-bit instance ids)" );
-			sizes[i] = sceneStorageSize( buildInputs[i] );
+			sizes[i] = sceneStorageSize( buildInputs[i], buildOptions );
 		}
 		const std::vector<void*> ptrs = ctx( context )->allocatePool( sizes );
 		for ( uint32_t i = 0; i < numScenes; ++i )

@@ -459,23 +459,35 @@ struct SceneLayout
 	size_t boxNodes, primNodes, instances, frames, total;
 };
 
-static SceneLayout sceneLayout( const hiprtSceneBuildInput& input )
+// Instance leaves a scene build may create: one per instance, except that a high-quality build with spatial splits may reference an
+// instance from several leaves (each with the part of the instance's box it is responsible for), up to half as many again.
+static size_t sceneLeafCapacity( const hiprtSceneBuildInput& input, hiprtBuildOptions options )
+{
+	const size_t n = input.instanceCount;
+	if ( usesSbvhBuilder( options ) && !isImport( options ) && !( options.buildFlags & hiprtBuildFlagBitDisableSpatialSplits ) ) return n + n / 2;
+	return n;
+}
+
+static SceneLayout sceneLayout( const hiprtSceneBuildInput& input, hiprtBuildOptions options )
 {
 	SceneLayout	 L{};
-	const size_t n = input.instanceCount;
+	const size_t n = input.instanceCount, leaves = sceneLeafCapacity( input, options );
 	L.boxNodes	   = alignUp( sizeof( SceneHeader ) );
-	L.primNodes	   = L.boxNodes + alignUp( maxBoxNodeCount( n ) * sizeof( Box4Node ) );
-	L.instances	   = L.primNodes + alignUp( n * sizeof( InstanceNode ) );
+	L.primNodes	   = L.boxNodes + alignUp( maxBoxNodeCount( leaves ) * sizeof( Box4Node ) );
+	L.instances	   = L.primNodes + alignUp( leaves * sizeof( InstanceNode ) );
 	L.frames	   = L.instances + alignUp( n * sizeof( InstanceRecord ) );
 	L.total		   = L.frames + alignUp( size_t( input.frameCount ) * sizeof( SRTFrame ) );
 	return L;
 }
 
-size_t sceneStorageSize( const hiprtSceneBuildInput& input ) { return sceneLayout( input ).total; }
+size_t sceneStorageSize( const hiprtSceneBuildInput& input, hiprtBuildOptions options ) { return sceneLayout( input, options ).total; }
 size_t sceneTempSize( const hiprtSceneBuildInput& input, hiprtBuildOptions options )
 {
-	// a high-quality scene build bins whole instances (no spatial splits: the instance-node array holds one node per instance)
-	if ( usesSbvhBuilder( options ) && !isImport( options ) ) return sbvhLayout( input.instanceCount, 0, input.instanceCount, false ).total;
+	if ( usesSbvhBuilder( options ) && !isImport( options ) )
+	{
+		const size_t leaves = sceneLeafCapacity( input, options );
+		return sbvhLayout( input.instanceCount, 0, leaves, leaves > input.instanceCount ).total;
+	}
 	return tempLayout( input.instanceCount, 0 ).total;
 }
 
@@ -486,7 +498,7 @@ void buildScene(
 	const uint32_t n		= input.instanceCount;
 	if ( n == 0 ) throw std::runtime_error( "empty scene" );
 	if ( input.instances == nullptr ) throw std::runtime_error( "scene without instances" );
-	const SceneLayout S	   = sceneLayout( input );
+	const SceneLayout S	   = sceneLayout( input, options );
 	const TempLayout  L	   = tempLayout( n, 0 );
 	uint8_t*		  temp = static_cast<uint8_t*>( tempBuffer );
 	uint8_t*		  out  = static_cast<uint8_t*>( storage );
@@ -524,9 +536,12 @@ void buildScene(
 	const uint32_t streamGrid = std::min<uint32_t>( DivideRoundUp( n, 256u ), dev.smCount * 8 );
 	if ( usesSbvhBuilder( options ) )
 	{
-		const SbvhLayout Q = sbvhLayout( n, 0, n, false );
+		// instances are cut like custom primitives: the half of the instance's world box on either side of the plane (the reference
+		// cuts along the boxes of the instance's root children, InstanceList.h:125-166: tighter, same guarantee)
+		const uint32_t	 leaves = uint32_t( sceneLeafCapacity( input, options ) );
+		const SbvhLayout Q		= sbvhLayout( n, 0, leaves, leaves > n );
 		primBoxesKernel<InstanceSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + Q.primRefs );
-		runSbvh( dev, src, n, n, false, temp, Q, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
+		runSbvh( dev, src, n, leaves, leaves > n, temp, Q, stream, &header->boxNodeCount, &header->primNodeCount, boxNodes, instNodes );
 		return;
 	}
 	primBoxesKernel<InstanceSource><<<streamGrid, 256, 0, stream>>>( src, ctl, temp + L.primRefs );
@@ -582,7 +597,8 @@ void updateScene(
 	const uint32_t work = std::max( n, input.frameCount );
 	updateSceneInputsKernel<<<DivideRoundUp( work, 256u ), 256, 0, stream>>>(
 		header, src, n, input.instanceFrames, input.frameType == hiprtFrameTypeMatrix );
-	refitKernel<InstanceSource><<<DivideRoundUp( uint32_t( maxBoxNodeCount( n ) ), 128u ), 128, 0, stream>>>( src, header, &header->boxNodeCount );
+	// (grid: an upper bound of the box-node count whatever builder made the scene; trimmed by header->boxNodeCount)
+	refitKernel<InstanceSource><<<DivideRoundUp( uint32_t( maxBoxNodeCount( n + n / 2 ) ), 128u ), 128, 0, stream>>>( src, header, &header->boxNodeCount );
 	HIPRT_CUDA_CHECK( cudaGetLastError() );
 }
 

@@ -48,7 +48,7 @@ size_t geometryStorageSize( const hiprtGeometryBuildInput& input, hiprtBuildOpti
 size_t geometryAllocationSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options ); // + the traversal-only Q region of triangle meshes (qnode.h)
 void*  geometryQRegion( const hiprtGeometryBuildInput& input, hiprtBuildOptions options, void* storage ); // nullptr: this build has none
 size_t geometryTempSize( const hiprtGeometryBuildInput& input, hiprtBuildOptions options );
-size_t sceneStorageSize( const hiprtSceneBuildInput& input );
+size_t sceneStorageSize( const hiprtSceneBuildInput& input, hiprtBuildOptions options );
 size_t sceneTempSize( const hiprtSceneBuildInput& input, hiprtBuildOptions options );
 
 // ---- builds (asynchronous on `stream`) -----------------------------------------------------------

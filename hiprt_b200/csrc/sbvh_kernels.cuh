@@ -219,7 +219,7 @@ struct Clipper<AabbListSource>
 	}
 };
 template <>
-struct Clipper<InstanceSource> // (scenes are built without spatial splits: one instance node per instance)
+struct Clipper<InstanceSource> // (an instance is cut like a box: the part of its world box on either side of the plane)
 {
 	__device__ __forceinline__ Clipper( const InstanceSource&, uint32_t, uint32_t ) {}
 	__device__ __forceinline__ void split( uint32_t axis, float position, const DBox& box, DBox& left, DBox& right ) const
