@@ -123,3 +123,32 @@ def test_scene_hits_match_reference(ctx):
     compare_hits(cross, theirs, rel=1e-5, uv_tol=1e-3)
     rs.destroy()
     scene.destroy()
+
+
+@pytest.mark.parametrize("case", ["sphere", "needles"])
+def test_high_quality_build_against_the_references_sbvh(ctx, case):
+    """PreferHighQualityBuild, ours and the reference's own SBVH (which does run on sm_100) on the same mesh: the same number
+    of leaves within a few percent (the same reference budget spent), the same tree quality, the same hits, and each library's
+    traversal walks the other's tree."""
+    from tests import helpers as H
+    from tests.test_oracle_sbvh import long_thin_soup
+
+    verts, idx = scenes.sphere_mesh(300, 150) if case == "sphere" else long_thin_soup(20000, seed=7)
+    n_tris = len(verts) // 3 if idx is None else len(idx)
+    rg = ref.RefGeometry(verts, idx, build_flags=api.HIGH_QUALITY_BUILD)
+    geom = ctx.build(to_dev(ctx, verts), None if idx is None else to_dev(ctx, idx), flags=api.HIGH_QUALITY_BUILD)
+    rboxes, rleaves = rg.nodes()
+    boxes, leaves = geom.nodes()
+    cost_ref = H.validate_wide_bvh(rboxes.view(api.BOX4_DTYPE), rleaves.view(api.TRIPAIR_DTYPE), n_tris, duplicated_references=True)
+    cost = H.validate_wide_bvh(boxes, leaves, n_tris, duplicated_references=True)
+    print(f"{case}: leaves {len(leaves)} / reference {len(rleaves)}, SAH-style cost {cost:.3f} / reference {cost_ref:.3f}")
+    assert abs(len(leaves) - len(rleaves)) <= 0.03 * len(rleaves)
+    assert cost <= 1.03 * cost_ref
+    rays = scenes.random_rays(30000, verts.min(0) - 0.1, verts.max(0) + 0.1, seed=5)
+    theirs, _ = rg.trace(rays, kind=2)
+    ours = ctx.hits_to_host(ctx.trace(geom, ctx.rays_to_device(rays)))
+    assert compare_hits(ours, theirs) <= 0.002 * len(rays)
+    cross, _ = ref.trace_geometry(geom.h, rays, kind=2)  # their traversal through our high-quality tree
+    compare_hits(cross, theirs)
+    rg.destroy()
+    geom.destroy()
