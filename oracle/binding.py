@@ -102,6 +102,8 @@ def lib():
         L.orc_scene_read.argtypes = [vp, i32, vp]
         L.orc_scene_trace.argtypes = [vp, vp, u32, vp, u32, i32]
         L.orc_scene_set_inv_matrices.argtypes = [vp, vp]
+        L.orc_scene_build_flags.argtypes = [i32]
+        L.orc_scene_build_flags.restype = None
         L.orc_scene_create_multilevel.argtypes = [vp, u32, vp, vp, i32, vp, u32, vp]
         L.orc_scene_create_multilevel.restype = vp
         L.orc_geometry_create_aabbs.argtypes = [vp, u32, u32, u32]
@@ -350,7 +352,9 @@ class Scene:
     """Two-level scene of the oracle: instances of oracle Geometry objects, one frame per instance
     (frame_type 0: hiprtFrameSRT rows of 12 floats, 1: hiprtFrameMatrix rows of 16 floats)."""
 
-    def __init__(self, geometries, geometry_of_instance, frames, frame_type=1, masks=None):
+    def __init__(self, geometries, geometry_of_instance, frames, frame_type=1, masks=None, high_quality=False, spatial_splits=True):
+        """high_quality: the top level is built by the SBVH restatement over instance boxes (an instance may then sit in several
+        instance nodes) instead of the LBVH."""
         self.geometries = list(geometries)
         self.geometry_of_instance = np.ascontiguousarray(geometry_of_instance, np.uint32)
         n = len(self.geometry_of_instance)
@@ -359,8 +363,10 @@ class Scene:
         handles = (C.c_void_p * len(self.geometries))(*[g.h for g in self.geometries])
         # an entry of `geometries` may itself be a Scene: it is then instanced as hiprtInstanceTypeScene (multi-level instancing)
         nested = np.array([isinstance(g, Scene) for g in self.geometries], np.uint32)
+        lib().orc_scene_build_flags((1 | (2 if spatial_splits else 0)) if high_quality else 0)
         self.h = lib().orc_scene_create_multilevel(handles, len(self.geometries), _p(self.geometry_of_instance), _p(self.frames),
                                                    frame_type, _p(self.masks), n, _p(nested))
+        lib().orc_scene_build_flags(0)
 
     def __del__(self):
         try:

@@ -101,3 +101,23 @@ def test_inputs_no_plane_separates_terminate():
     levels, refs, _, unordered, inconsistent = (int(x) for x in g.sbvh_stats)
     assert inconsistent == 0 and unordered > 0 and 300 <= refs <= 450 and levels < 80  # (the copies overlap entirely: spatial splits are tried too)
     H.validate_wide_bvh(g.box_nodes, g.leaves, 300, duplicated_references=True)
+
+
+def test_high_quality_scene_of_the_oracle_returns_the_lbvh_scene_hits():
+    verts, idx = scenes.icosphere(2, 1.0)
+    g = orc.Geometry(verts, idx)
+    frames = scenes.random_matrix_frames(400, seed=3, extent=20.0).reshape(-1, 4, 4).copy()
+    frames[::5, :3, 0] *= 20.0  # long thin instances: what instance splits are for
+    frames = frames.reshape(-1, 16)
+    geom_of = np.zeros(len(frames), np.uint32)
+    lbvh = orc.Scene([g], geom_of, frames)
+    hq = orc.Scene([g], geom_of, frames, high_quality=True)
+    nosplit = orc.Scene([g], geom_of, frames, high_quality=True, spatial_splits=False)
+    assert len(frames) < hq.leaf_count <= len(frames) + len(frames) // 2 and nosplit.leaf_count == len(frames)
+    assert np.array_equal(np.unique(hq.leaves["bits"] & 0xFFFFFF), np.arange(len(frames)))
+    rays = scenes.random_rays(20000, np.full(3, -30.0, np.float32), np.full(3, 30.0, np.float32), seed=4)
+    a = lbvh.trace(rays)
+    assert (a["primID"] != orc.INVALID).mean() > 0.02
+    for s in (hq, nosplit):
+        b = s.trace(rays)
+        assert np.array_equal(a["primID"], b["primID"]) and np.array_equal(a["instanceIDs"], b["instanceIDs"]) and np.array_equal(a["t"], b["t"])
